@@ -1,0 +1,165 @@
+"""Pins the CPU oracle (`oracle/restate.py`) against golden vectors produced by the
+reference's own modules (`oracle/make_golden.py`).  CPU only."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+from oracle.reference_shim import make_config
+
+from conftest import GOLDEN
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def test_filterbank_matches_torchaudio_slaney():
+    g = load("features.npz")
+    fb = restate.make_mel_filterbanks("mel_2048_1024_128")
+    assert fb.shape == (128, 1025) and fb.dtype == np.float32
+    ta = np.zeros((128, 1025), np.float32)
+    ta[g["ta_rows"], g["ta_cols"]] = g["ta_vals"]
+    assert np.abs(fb - ta).max() <= 2e-7 + 1e-5 * np.abs(ta).max()
+    assert int(g["fb_checksum"][1]) == np.count_nonzero(fb)
+    assert abs(g["fb_checksum"][0] - fb.astype(np.float64).sum()) < 1e-6
+
+
+def test_features_match_reference():
+    g = load("features.npz")
+    wav = restate.synth_waveforms(int(g["n"]), int(g["t"]), seed=int(g["seed"]))
+    mag = restate.stft_magnitude(torch.from_numpy(wav), 2048, 1024).numpy()
+    assert mag.shape == g["stft_mag_2048"].shape == (2, 1025, 40)
+    assert rel_err(mag, g["stft_mag_2048"]) < 2e-6
+    logmel = restate.features(torch.from_numpy(wav)[..., None], "mel_2048_1024_128").numpy()
+    assert np.abs(logmel - g["logmel"]).max() < 5e-5
+    logstft = restate.features(torch.from_numpy(wav)[..., None], "stft_256_128").numpy()
+    assert logstft.shape == g["logstft_256"].shape
+    # log amplifies relative error of near-zero bins: compare in the magnitude domain too
+    assert rel_err(np.exp(logstft), np.exp(g["logstft_256"])) < 2e-6
+
+
+def test_scipy_style_stft():
+    g = load("features.npz")
+    wav = restate.synth_waveforms(2, 40000, seed=7)
+    s = restate.scipy_style_stft(wav[0][:8000], 256, 128, log=True)
+    assert s.shape == g["scipy_stft"].shape
+    assert rel_err(np.exp(s), np.exp(g["scipy_stft"])) < 1e-5
+
+
+CASES = [
+    ("net2d_small.npz", True, dict(conv_base_depth=8, growth_rate=1.5)),
+    ("net2d_pow2.npz", True, dict(conv_base_depth=8, growth_rate=2.0, start_deep_supervision_on=2)),
+    ("net1d_small.npz", False, dict(features="stft_256_128", conv_base_depth=8, growth_rate=1.5)),
+]
+
+
+@pytest.mark.parametrize("name,two_d,cfg", CASES)
+def test_network_matches_reference(name, two_d, cfg):
+    g = load(name)
+    config = make_config(**cfg)
+    fwd = restate.net2d_forward if two_d else restate.net1d_forward
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    wav = restate.synth_waveforms(int(g["n"]), int(g["t"]), seed=int(g["seed"]), kind=str(g["wave_kind"]))
+    labels = torch.from_numpy(restate.synth_labels(int(g["n"]), 80, seed=int(g["seed"])))
+    signal = torch.from_numpy(wav)[..., None]
+
+    with torch.no_grad():
+        le = fwd(sd, config, signal, training=False)
+    assert rel_err(le.numpy(), g["logits_eval"]) < 1e-5
+
+    params = {k: v.clone().requires_grad_() if v.dtype.is_floating_point and "running" not in k else v
+              for k, v in sd.items()}
+    stats = {}
+    lt = fwd(params, config, signal, training=True, stats_out=stats)
+    # train mode: batch-statistic BN over a 3-4 clip batch amplifies the ~1e-7 difference
+    # between torch.stft (reference) and the explicit rfft restatement
+    # (ill-conditioned by construction: the head's BatchNorm1d normalises over 3-4 samples);
+    # the gate is the north-star's 1e-3, eval mode above is held to 1e-5
+    assert rel_err(lt.detach().numpy(), g["logits_train"]) < 1e-3
+    per = restate.lsep_loss(lt, labels, average=False)
+    assert rel_err(per.detach().numpy(), g["per_sample_loss"]) < 1e-3
+    per.mean().backward()
+    # biases that feed a train-mode BN have an analytically zero gradient (float noise in
+    # the reference), so the absolute floor is tied to the global gradient scale
+    gmax = max(np.abs(g[k]).max() for k in g.files if k.startswith("grad/"))
+    for k in g.files:
+        if k.startswith("grad/"):
+            got = params[k[5:]].grad.numpy()
+            assert np.abs(got - g[k]).max() <= 1e-2 * np.abs(g[k]).max() + 1e-3 * gmax, k
+    # running statistics after one train-mode forward (momentum 0.1, unbiased var)
+    for prefix, (mean, var) in stats.items():
+        rm = 0.9 * sd[prefix + ".running_mean"] + 0.1 * mean
+        rv = 0.9 * sd[prefix + ".running_var"] + 0.1 * var
+        assert rel_err(rm.numpy(), g["sd_after/" + prefix + ".running_mean"]) < 1e-4
+        assert rel_err(rv.numpy(), g["sd_after/" + prefix + ".running_var"]) < 1e-4
+    assert abs(restate.lwlrap(labels.numpy(), torch.sigmoid(lt).detach().numpy()) - float(g["lwlrap_train"])) < 5e-5
+    # default-init RNG consumption identical to the reference constructor
+    init = restate.init_state_dict(config, two_d=two_d, seed=42)
+    chk = np.array([float(v.double().sum()) for k, v in sorted(init.items())])
+    assert np.allclose(chk, g["init_checksum"], rtol=0, atol=0)
+
+
+def test_lsep():
+    g = load("lsep.npz")
+    s = torch.from_numpy(g["scores"]).requires_grad_()
+    t = torch.from_numpy(g["targets"])
+    per = restate.lsep_loss(s, t, average=False)
+    assert rel_err(per.detach().numpy(), g["per_sample"]) < 1e-6
+    assert per[5].item() == 0.0
+    per.mean().backward()
+    assert rel_err(s.grad.numpy(), g["grad_mean"]) < 1e-6
+    assert abs(restate.lsep_loss(s, t).item() - float(g["mean"])) < 1e-6
+
+
+def test_adam_and_onecycle():
+    g = load("adam.npz")
+    p = g["params"][0].copy()
+    m, v, vmax = np.zeros_like(p), np.zeros_like(p), np.zeros_like(p)
+    for step in range(10):
+        lr = restate.onecycle_lr(step, 0.0001, 0.005, 10)
+        assert abs(lr - g["lrs"][step]) < 1e-12
+        restate.adam_amsgrad_step(p, g["grads"][step], m, v, vmax, step + 1, lr,
+                                  weight_decay=float(g["weight_decay"]))
+        assert np.abs(p - g["params"][step + 1]).max() < 2e-6
+
+
+def test_lwlrap():
+    g = load("lwlrap.npz")
+    # sklearn evaluates per-row precision in the dtype of `scores` (float32 here)
+    assert abs(restate.lwlrap(g["truth"], g["scores"]) - float(g["value"])) < 1e-7
+
+
+def test_padding_and_bucketing():
+    g = load("padding.npz")
+    lens = g["lens"]
+    raw, off = [], 0
+    for l in lens:
+        raw.append(g["raw"][off:off + l].reshape(l, 1))
+        off += l
+    assert np.array_equal(restate.pad_collate(raw, 0.0), g["collated"])
+    rng = random.Random()
+    random.seed(6)
+    # reference uses the module-level `random`; replay it through the same global stream
+    batches = restate.bucket_batches(g["ds_lengths"], 64 * 441000 // 8,
+                                     [0, 5 * 44100, 10 * 44100, 20 * 44100, 31 * 44100], rng=random)
+    assert np.array_equal(np.array([len(b) for b in batches]), g["batch_sizes"])
+    assert np.array_equal(np.array([i for b in batches for i in b]), g["batch_flat"])
+
+
+def test_mixup():
+    g = load("mixup.npz")
+    mixed, labels = restate.mix_audio_and_labels(g["a1"].copy(), g["a2"].copy(), g["l1"], g["l2"])
+    assert np.array_equal(mixed, g["mixed"]) and np.array_equal(labels, g["labels"])
+    mixed_u, labels_u = restate.mix_audio_and_labels(g["a1"].copy(), g["a3"].copy(), g["l1"], g["l2"],
+                                                     a=float(g["a"]), start=int(g["start"]))
+    assert np.allclose(mixed_u, g["mixed_unequal"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(labels_u, g["labels_unequal"])
