@@ -1,0 +1,104 @@
+// Shared definitions for libfsb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fsb200.h"
+
+namespace fsb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every C-ABI function returns an int and records text for fsb_last_error()
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern long long g_launch_count;
+
+#define FSB_CUDA(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            fsb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                \
+                           cudaGetErrorString(_e));                                     \
+            return (int)_e;                                                             \
+        }                                                                               \
+    } while (0)
+
+#define FSB_TRY(expr)                                                                   \
+    do {                                                                                \
+        int _r = (expr);                                                                \
+        if (_r != 0) return _r;                                                         \
+    } while (0)
+
+#define FSB_REQUIRE(cond, ...)                                                          \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            fsb::set_error(__VA_ARGS__);                                                \
+            return FSB_E_INVALID;                                                       \
+        }                                                                               \
+    } while (0)
+
+// count + check a kernel launch (cudaGetLastError only reports launch-configuration errors; it
+// does not synchronise)
+#define FSB_LAUNCHED()                                                                  \
+    do {                                                                                \
+        ++fsb::g_launch_count;                                                          \
+        FSB_CUDA(cudaGetLastError());                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Padded-flat NHWC geometry ("PF"): a tensor of N images, H x W pixels, C channels is stored as
+// rows = N * Hp * Wp pixels of Cs channels each (channels innermost, Cs = C rounded up to 16),
+// with a zero border of padH rows / padW columns around every image.  A 3x3 "same" convolution
+// then reads, for output row r and tap (dy,dx), input row r + (dy-1)*Wp + (dx-1): every conv is a
+// sum of row-shifted GEMMs and the zero border supplies the padding.
+// ---------------------------------------------------------------------------------------------
+struct Geo {
+    int N, H, W, C, Cs, padH, padW, Hp, Wp;
+    long long rows;      // N * Hp * Wp
+    long long pixels;    // N * H * W (interior)
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline Geo make_geo(int N, int H, int W, int C, int padH, int padW) {
+    Geo g;
+    g.N = N; g.H = H; g.W = W; g.C = C; g.Cs = round_up(C, 16);
+    g.padH = padH; g.padW = padW; g.Hp = H + 2 * padH; g.Wp = W + 2 * padW;
+    g.rows = (long long)N * g.Hp * g.Wp;
+    g.pixels = (long long)N * H * W;
+    return g;
+}
+
+__host__ __device__ inline long long geo_row(const Geo& g, int n, int y, int x) {
+    return ((long long)n * g.Hp + (y + g.padH)) * g.Wp + (x + g.padW);
+}
+
+// interior pixel index q in [0, N*H*W) -> padded row
+__device__ __forceinline__ long long geo_q_to_row(const Geo& g, long long q) {
+    int x = (int)(q % g.W);
+    long long t = q / g.W;
+    int y = (int)(t % g.H);
+    int n = (int)(t / g.H);
+    return ((long long)n * g.Hp + (y + g.padH)) * g.Wp + (x + g.padW);
+}
+
+// ---------------------------------------------------------------------------------------------
+// activation storage formats consumed by the GEMM kernels
+//   FMT_F32  : one float32 plane                      (precision 0, CUDA-core GEMM)
+//   FMT_BF16X2: two bf16 planes hi, lo with x ~= hi+lo (precision 1: bf16x3 tcgen05 GEMM;
+//               precision 2 reads the hi plane only)
+// A "plane" is rows*Cs elements; for FMT_BF16X2 the lo plane follows the hi plane.
+// ---------------------------------------------------------------------------------------------
+enum { FMT_F32 = 0, FMT_BF16X2 = 1 };
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace fsb

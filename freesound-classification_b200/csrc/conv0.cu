@@ -1,0 +1,260 @@
+#include "conv0.cuh"
+
+namespace fsb {
+
+static const int PS_BLOCKS = 592;
+
+__global__ void __launch_bounds__(256) plain_stats_kernel(const float* __restrict__ x, long long n, double* partials16) {
+    double s = 0.0, ss = 0.0;
+    float fs = 0.f, fss = 0.f;
+    int cnt = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[i];
+        fs += v; fss += v * v;
+        if (++cnt == 32) { s += fs; ss += fss; fs = fss = 0.f; cnt = 0; }
+    }
+    s += fs; ss += fss;
+    __shared__ double r0[256], r1[256];
+    r0[threadIdx.x] = s; r1[threadIdx.x] = ss;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) { r0[threadIdx.x] += r0[threadIdx.x + st]; r1[threadIdx.x] += r1[threadIdx.x + st]; }
+        __syncthreads();
+    }
+    if (threadIdx.x < 16) {
+        // channel 0 carries the sums; the remaining 15 channels of the record are zeroed
+        partials16[((long long)blockIdx.x * 2 + 0) * 16 + threadIdx.x] = threadIdx.x == 0 ? r0[0] : 0.0;
+        partials16[((long long)blockIdx.x * 2 + 1) * 16 + threadIdx.x] = threadIdx.x == 0 ? r1[0] : 0.0;
+    }
+}
+
+int plain_stats_blocks() { return PS_BLOCKS; }
+
+int plain_stats(const float* x, long long n, double* partials16, cudaStream_t s) {
+    plain_stats_kernel<<<PS_BLOCKS, 256, 0, s>>>(x, n, partials16);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static constexpr int C0_PX = 32;                 // pooled pixels per tile (one pooled row segment)
+static constexpr int C0_PW = 2 * C0_PX + 2;      // input patch width
+static constexpr int C0_THREADS = 128;
+
+__device__ __forceinline__ float freq_enc(int h, int H) {
+    float step = 2.0f / (float)(H - 1);
+    return h < H / 2 ? -1.0f + step * (float)h : 1.0f - step * (float)(H - 1 - h);
+}
+
+// loads the BN-applied 2-channel input patch (rows 2*py-1 .. 2*py+2, cols 2*px0-1 .. 2*px0+2*PX) into
+// shared memory; out-of-image positions are zero (conv padding) and flagged in `valid`.
+__device__ __forceinline__ void load_patch(const float* __restrict__ feat, int n, int H, int W, int py, int px0,
+                                           float sc0, float sh0, float sc1, float sh1, float mean0, float istd0,
+                                           float mean1, float istd1, float (*u)[4][C0_PW], float (*xh)[4][C0_PW],
+                                           float (*valid)[C0_PW]) {
+    for (int e = threadIdx.x; e < 4 * C0_PW; e += blockDim.x) {
+        int r = e / C0_PW, c = e - r * C0_PW;
+        int y = 2 * py - 1 + r, x = 2 * px0 - 1 + c;
+        bool ok = y >= 0 && y < H && x >= 0 && x < W;
+        float v0 = 0.f, v1 = 0.f, h0 = 0.f, h1 = 0.f;
+        if (ok) {
+            float f = __ldg(feat + ((long long)n * H + y) * W + x);
+            float e1 = freq_enc(y, H);
+            v0 = fmaf(f, sc0, sh0);
+            v1 = fmaf(e1, sc1, sh1);
+            h0 = (f - mean0) * istd0;
+            h1 = (e1 - mean1) * istd1;
+        }
+        u[0][r][c] = v0; u[1][r][c] = v1;
+        if (xh) { xh[0][r][c] = h0; xh[1][r][c] = h1; valid[r][c] = ok ? 1.f : 0.f; }
+    }
+}
+
+__global__ void __launch_bounds__(C0_THREADS)
+conv0_fwd_kernel(const float* __restrict__ feat, int N, int H, int W, const float* __restrict__ scale,
+                 const float* __restrict__ shift, const float* __restrict__ w, const float* __restrict__ b,
+                 float* __restrict__ zp, Geo gp) {
+    __shared__ float u[2][4][C0_PW];
+    const int px0 = blockIdx.x * C0_PX, py = blockIdx.y, n = blockIdx.z;
+    load_patch(feat, n, H, W, py, px0, scale[0], shift[0], scale[1], shift[1], 0.f, 0.f, 0.f, 0.f, u, nullptr, nullptr);
+    __syncthreads();
+    const int npx = min(C0_PX, gp.W - px0);
+    for (int c = threadIdx.x; c < gp.Cs; c += blockDim.x) {
+        float wr[2][3][3];
+        float bias = 0.f;
+        const bool real = c < gp.C;
+        if (real) {
+#pragma unroll
+            for (int i = 0; i < 18; ++i) (&wr[0][0][0])[i] = w[c * 18 + i];
+            bias = b[c];
+        }
+        for (int p = 0; p < npx; ++p) {
+            float best = 0.f;
+            if (real) {
+                best = -INFINITY;
+#pragma unroll
+                for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+                    for (int sx = 0; sx < 2; ++sx) {
+                        float acc = bias;
+#pragma unroll
+                        for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    acc = fmaf(wr[ci][dy][dx], u[ci][sy + dy][2 * p + sx + dx], acc);
+                        best = fmaxf(best, acc);
+                    }
+            }
+            zp[geo_row(gp, n, py, px0 + p) * gp.Cs + c] = best;
+        }
+    }
+}
+
+int conv0_forward(const float* feat, int N, int H, int W, const float* scale, const float* shift, const float* w,
+                  const float* b, float* zp, const Geo& gp, cudaStream_t s) {
+    FSB_REQUIRE(gp.H == H / 2 && gp.W == W / 2 && gp.N == N, "conv0: geometry mismatch");
+    FSB_REQUIRE(gp.H <= 65535 && N <= 65535, "conv0: grid too large");
+    dim3 grid((gp.W + C0_PX - 1) / C0_PX, gp.H, N);
+    conv0_fwd_kernel<<<grid, C0_THREADS, 0, s>>>(feat, N, H, W, scale, shift, w, b, zp, gp);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static const int C0B_BLOCKS = 1184;
+static const int C0B_REC = 22;    // 18 dW + 2 dgamma-terms + 2 dbeta-terms per output channel
+
+int conv0_bwd_blocks() { return C0B_BLOCKS; }
+size_t conv0_bwd_scratch_bytes(const Geo& gp) { return (size_t)C0B_BLOCKS * C0B_REC * gp.Cs * sizeof(float); }
+
+__global__ void __launch_bounds__(C0_THREADS)
+conv0_bwd_kernel(const float* __restrict__ feat, int N, int H, int W, const float* __restrict__ scale,
+                 const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                 const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ dzp, Geo gp,
+                 float* __restrict__ partials) {
+    __shared__ float u[2][4][C0_PW];
+    __shared__ float xh[2][4][C0_PW];
+    __shared__ float valid[4][C0_PW];
+    const int tiles_x = (gp.W + C0_PX - 1) / C0_PX;
+    const long long ntiles = (long long)tiles_x * gp.H * N;
+    // each thread owns channels c = threadIdx.x + k*blockDim.x ; accumulators live across tiles, so
+    // the channel loop is the OUTER loop and tiles are re-visited per channel chunk
+    for (int c = threadIdx.x; c < gp.Cs + (int)blockDim.x; c += blockDim.x) {
+        const bool real = c < gp.C;   // uniform participation in __syncthreads below
+        if (c - (int)threadIdx.x >= gp.Cs) break;
+        float wr[2][3][3];
+        float bias = 0.f;
+        float acc[C0B_REC];
+#pragma unroll
+        for (int i = 0; i < C0B_REC; ++i) acc[i] = 0.f;
+        if (real) {
+#pragma unroll
+            for (int i = 0; i < 18; ++i) (&wr[0][0][0])[i] = w[c * 18 + i];
+            bias = b[c];
+        }
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int tx = (int)(tile % tiles_x);
+            long long t2 = tile / tiles_x;
+            int py = (int)(t2 % gp.H);
+            int n = (int)(t2 / gp.H);
+            int px0 = tx * C0_PX;
+            __syncthreads();
+            load_patch(feat, n, H, W, py, px0, scale[0], shift[0], scale[1], shift[1], mean[0], invstd[0], mean[1],
+                       invstd[1], u, xh, valid);
+            __syncthreads();
+            if (!real) continue;
+            const int npx = min(C0_PX, gp.W - px0);
+            for (int p = 0; p < npx; ++p) {
+                float g = dzp[geo_row(gp, n, py, px0 + p) * gp.Cs + c];
+                // recompute the four conv outputs to find the (first) arg-max of the pool window
+                float best = -INFINITY;
+                int bsy = 0, bsx = 0;
+#pragma unroll
+                for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+                    for (int sx = 0; sx < 2; ++sx) {
+                        float a = bias;
+#pragma unroll
+                        for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    a = fmaf(wr[ci][dy][dx], u[ci][sy + dy][2 * p + sx + dx], a);
+                        if (a > best) { best = a; bsy = sy; bsx = sx; }
+                    }
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            int r = bsy + dy, cc = 2 * p + bsx + dx;
+                            acc[ci * 9 + dy * 3 + dx] = fmaf(g, u[ci][r][cc], acc[ci * 9 + dy * 3 + dx]);
+                            float gw = g * wr[ci][dy][dx];
+                            acc[18 + ci] = fmaf(gw, xh[ci][r][cc], acc[18 + ci]);
+                            acc[20 + ci] = fmaf(gw, valid[r][cc], acc[20 + ci]);
+                        }
+            }
+        }
+        if (c < gp.Cs) {
+            float* o = partials + (long long)blockIdx.x * C0B_REC * gp.Cs;
+#pragma unroll
+            for (int i = 0; i < C0B_REC; ++i) o[i * gp.Cs + c] = acc[i];
+        }
+    }
+}
+
+__global__ void conv0_bwd_finalize_kernel(const float* partials, int nblk, Geo gp, float* dw, float* db) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int ndw = gp.C * 18;
+    if (i < ndw) {
+        int c = i / 18, k = i % 18;
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += partials[((long long)b * C0B_REC + k) * gp.Cs + c];
+        dw[i] = (float)s;
+    } else if (i < ndw + gp.C) {
+        db[i - ndw] = 0.f;   // conv bias feeds a batch-statistics BN: analytically zero gradient
+    }
+}
+
+// one block per BN_in term (dgamma[0], dgamma[1], dbeta[0], dbeta[1]): sum over blocks and channels
+__global__ void __launch_bounds__(256)
+conv0_bwd_bn_kernel(const float* partials, int nblk, Geo gp, float* dgamma_in, float* dbeta_in) {
+    const int k = 18 + blockIdx.x;
+    double s = 0.0;
+    long long total = (long long)nblk * gp.C;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+        int b = (int)(e / gp.C), c = (int)(e % gp.C);
+        s += partials[((long long)b * C0B_REC + k) * gp.Cs + c];
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (blockIdx.x < 2) dgamma_in[blockIdx.x] = (float)red[0];
+        else dbeta_in[blockIdx.x - 2] = (float)red[0];
+    }
+}
+
+int conv0_backward(const float* feat, int N, int H, int W, const float* scale, const float* shift, const float* mean,
+                   const float* invstd, const float* w, const float* b, const float* dzp, const Geo& gp, float* dw,
+                   float* db, float* dgamma_in, float* dbeta_in, void* scratch, cudaStream_t s) {
+    conv0_bwd_kernel<<<C0B_BLOCKS, C0_THREADS, 0, s>>>(feat, N, H, W, scale, shift, mean, invstd, w, b, dzp, gp,
+                                                       (float*)scratch);
+    FSB_LAUNCHED();
+    int total = gp.C * 18 + gp.C;
+    conv0_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>((const float*)scratch, C0B_BLOCKS, gp, dw, db);
+    FSB_LAUNCHED();
+    conv0_bwd_bn_kernel<<<4, 256, 0, s>>>((const float*)scratch, C0B_BLOCKS, gp, dgamma_in, dbeta_in);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace fsb

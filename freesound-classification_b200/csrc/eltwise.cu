@@ -1,0 +1,698 @@
+#include "eltwise.cuh"
+
+namespace fsb {
+
+// ---------------------------------------------------------------------------------------------
+// launch shape shared by all kernels here: threadIdx.x <-> a float4 of channels (fixed for the
+// thread, so per-channel reductions stay in registers), threadIdx.y <-> pixel; blockIdx.y covers
+// channel chunks when Cs/4 exceeds blockDim.x; blockIdx.x strides over interior pixels.
+// Consecutive x-threads touch consecutive 16 B and consecutive pixels are consecutive rows, so a
+// warp's accesses are contiguous.
+// ---------------------------------------------------------------------------------------------
+struct EwShape {
+    dim3 grid, block;
+};
+
+static const int EW_MAX_BLOCKS = 1184;  // 8 x 148 SMs
+
+static EwShape ew_shape(const Geo& g) {
+    int cv = g.Cs / 4;
+    int bx = cv < 64 ? cv : 64;
+    int by = 256 / bx;
+    if (by < 1) by = 1;
+    long long need = (g.pixels + by * 4 - 1) / (by * 4);
+    int gx = (int)(need < 1 ? 1 : (need > EW_MAX_BLOCKS ? EW_MAX_BLOCKS : need));
+    EwShape s;
+    s.block = dim3(bx, by);
+    s.grid = dim3(gx, (cv + bx - 1) / bx);
+    return s;
+}
+
+int ew_num_blocks(const Geo& g) { return (int)ew_shape(g).grid.x; }
+
+#define EW_PROLOGUE                                                        \
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;                  \
+    const bool cok = cv < g.Cs / 4;                                        \
+    const int c0 = cv * 4;
+
+#define EW_PIXEL_LOOP                                                      \
+    for (long long q = (long long)blockIdx.x * blockDim.y + threadIdx.y; q < g.pixels; \
+         q += (long long)gridDim.x * blockDim.y)
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ void store_fmt(void* base, int fmt, long long plane_elems, long long idx, float4 v) {
+    if (fmt == FMT_F32) {
+        st4(reinterpret_cast<float*>(base) + idx, v);
+    } else {
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v.x, h[0], l[0]);
+        split_bf16(v.y, h[1], l[1]);
+        split_bf16(v.z, h[2], l[2]);
+        split_bf16(v.w, h[3], l[3]);
+        __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(base) + idx;
+        __nv_bfloat16* lp = hp + plane_elems;
+        *reinterpret_cast<uint2*>(hp) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(lp) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// accumulate float4 streams: float32 inside runs of 32 pixels, double across runs
+struct Acc4 {
+    float4 f;
+    double d[4];
+    int n;
+    __device__ __forceinline__ void init() {
+        f = make_float4(0.f, 0.f, 0.f, 0.f);
+        d[0] = d[1] = d[2] = d[3] = 0.0;
+        n = 0;
+    }
+    __device__ __forceinline__ void add(float4 v) {
+        f.x += v.x; f.y += v.y; f.z += v.z; f.w += v.w;
+        if (++n == 32) flush();
+    }
+    __device__ __forceinline__ void flush() {
+        d[0] += f.x; d[1] += f.y; d[2] += f.z; d[3] += f.w;
+        f = make_float4(0.f, 0.f, 0.f, 0.f);
+        n = 0;
+    }
+};
+
+// reduce K Acc4 records across threadIdx.y and write partials[(blockIdx.x*K + k)*Cs + c]
+template <int K>
+__device__ __forceinline__ void block_reduce_store(Acc4 (&acc)[K], double* partials, int Cs, int c0, bool cok) {
+    __shared__ double red[256 * 4];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc[k].flush();
+        int t = threadIdx.y * blockDim.x + threadIdx.x;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[t * 4 + i] = acc[k].d[i];
+        __syncthreads();
+        if (threadIdx.y == 0 && cok) {
+            double s[4] = {0, 0, 0, 0};
+            for (int y = 0; y < (int)blockDim.y; ++y) {
+                int tt = y * blockDim.x + threadIdx.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s[i] += red[tt * 4 + i];
+            }
+            double* o = partials + ((long long)blockIdx.x * K + k) * Cs + c0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = s[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void zero_border_kernel(float4* buf, Geo g, long long plane_vec, int nplanes, int vec_per_row) {
+    // one thread per (border row, vec); border rows enumerated per image
+    int border_per_img = g.Hp * g.Wp - g.H * g.W;
+    long long total = (long long)g.N * border_per_img * vec_per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(i % vec_per_row);
+        long long t = i / vec_per_row;
+        int b = (int)(t % border_per_img);
+        int n = (int)(t / border_per_img);
+        // map border index -> (y, x) in padded coords
+        int y, x;
+        int top = g.padH * g.Wp;
+        if (b < top) {
+            y = b / g.Wp; x = b % g.Wp;
+        } else if (b < 2 * top) {
+            int bb = b - top;
+            y = g.Hp - g.padH + bb / g.Wp; x = bb % g.Wp;
+        } else {
+            int bb = b - 2 * top;             // side columns: H rows x 2*padW
+            y = g.padH + bb / (2 * g.padW);
+            int sx = bb % (2 * g.padW);
+            x = sx < g.padW ? sx : g.Wp - 2 * g.padW + sx;
+        }
+        long long row = ((long long)n * g.Hp + y) * g.Wp + x;
+        for (int p = 0; p < nplanes; ++p) buf[p * plane_vec + row * vec_per_row + v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+int pf_zero_border(void* buf, int fmt, const Geo& g, cudaStream_t s) {
+    int border_per_img = g.Hp * g.Wp - g.H * g.W;
+    if (border_per_img == 0) return 0;
+    // a float4 is 4 float32 or 8 bf16: vec_per_row counts 16-byte units per row per plane
+    int vec_per_row = fmt == FMT_F32 ? g.Cs / 4 : g.Cs / 8;
+    int nplanes = fmt == FMT_F32 ? 1 : 2;
+    long long plane_vec = g.rows * vec_per_row;
+    long long total = (long long)g.N * border_per_img * vec_per_row;
+    int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+    zero_border_kernel<<<blocks, 256, 0, s>>>((float4*)buf, g, plane_vec, nplanes, vec_per_row);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+int pf_zero_all(void* buf, int fmt, const Geo& g, cudaStream_t s) {
+    size_t bytes = (size_t)g.rows * g.Cs * 4;   // f32: 4 B/elem ; bf16x2: 2 planes x 2 B/elem
+    (void)fmt;
+    FSB_CUDA(cudaMemsetAsync(buf, 0, bytes, s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ x, Geo g, double* partials) {
+    EW_PROLOGUE
+    Acc4 acc[2];
+    acc[0].init(); acc[1].init();
+    if (cok) {
+        EW_PIXEL_LOOP {
+            long long row = geo_q_to_row(g, q);
+            float4 v = ld4(x + row * g.Cs + c0);
+            acc[0].add(v);
+            acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
+        }
+    }
+    block_reduce_store<2>(acc, partials, g.Cs, c0, cok);
+}
+
+int pf_stats(const float* x, const Geo& g, double* partials, cudaStream_t s) {
+    EwShape sh = ew_shape(g);
+    stats_kernel<<<sh.grid, sh.block, 0, s>>>(x, g, partials);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+__global__ void bn_finalize_kernel(const double* partials, int nblk, long long count, const float* gamma,
+                                   const float* beta, float* run_mean, float* run_var, long long* bn_count,
+                                   int training, int C, int Cs, float* scale, float* shift, float* mean,
+                                   float* invstd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cs) return;
+    if (c >= C) {
+        scale[c] = 0.f; shift[c] = 0.f;
+        if (mean) mean[c] = 0.f;
+        if (invstd) invstd[c] = 0.f;
+        return;
+    }
+    const float eps = 1e-5f, momentum = 0.1f;
+    float m, istd;
+    if (training) {
+        double s = 0.0, ss = 0.0;
+        for (int b = 0; b < nblk; ++b) {
+            s += partials[((long long)b * 2 + 0) * Cs + c];
+            ss += partials[((long long)b * 2 + 1) * Cs + c];
+        }
+        double mu = s / (double)count;
+        double var = ss / (double)count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        m = (float)mu;
+        istd = (float)(1.0 / sqrt(var + (double)eps));
+        if (run_mean) {
+            double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+            run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unbiased;
+        }
+        if (c == 0 && bn_count) *bn_count += 1;
+    } else {
+        m = run_mean[c];
+        istd = 1.0f / sqrtf(run_var[c] + eps);
+    }
+    float sc = gamma[c] * istd;
+    scale[c] = sc;
+    shift[c] = beta[c] - m * sc;
+    if (mean) mean[c] = m;
+    if (invstd) invstd[c] = istd;
+}
+
+int bn_finalize(const double* partials, int nblk, long long count, const float* gamma, const float* beta,
+                float* run_mean, float* run_var, long long* bn_count, int training, int C, int Cs,
+                float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
+    bn_finalize_kernel<<<(Cs + 127) / 128, 128, 0, s>>>(partials, nblk, count, gamma, beta, run_mean,
+                                                       run_var, bn_count, training, C, Cs, scale, shift,
+                                                       mean, invstd);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+__global__ void freq_stats_kernel(int H, long long n_times_w, double* partials16) {
+    // channel 1 of the block-0 input: v_h = linspace(-1, 1, H)[h] (float32, as torch.linspace)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0, ss = 0.0;
+        float step = 2.0f / (float)(H - 1);
+        for (int h = 0; h < H; ++h) {
+            float v = h < H / 2 ? -1.0f + step * (float)h : 1.0f - step * (float)(H - 1 - h);
+            s += v; ss += (double)v * v;
+        }
+        partials16[0 * 16 + 1] = s * (double)n_times_w;
+        partials16[1 * 16 + 1] = ss * (double)n_times_w;
+    }
+}
+
+int freq_encoding_stats(int H, long long n_times_w, double* partials16, cudaStream_t s) {
+    freq_stats_kernel<<<1, 32, 0, s>>>(H, n_times_w, partials16);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float prelu1(float y, float a) { return y > 0.f ? y : a * y; }
+
+__device__ __forceinline__ float4 affine4(float4 z, float4 sc, float4 sh) {
+    return make_float4(fmaf(z.x, sc.x, sh.x), fmaf(z.y, sc.y, sh.y), fmaf(z.z, sc.z, sh.z), fmaf(z.w, sc.w, sh.w));
+}
+__device__ __forceinline__ float4 prelu4(float4 y, float4 a) {
+    return make_float4(prelu1(y.x, a.x), prelu1(y.y, a.y), prelu1(y.z, a.z), prelu1(y.w, a.w));
+}
+
+__device__ __forceinline__ float keep_scale(Dropout dr, long long elem) {
+    // counter-based hash (splitmix64 finaliser) -> uniform in [0,1)
+    unsigned long long h = dr.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(elem + 1);
+    h = (h ^ (h >> 30)) * 0xBF58476D1CE4E5B9ull;
+    h = (h ^ (h >> 27)) * 0x94D049BB133111EBull;
+    h ^= h >> 31;
+    float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+    return u >= dr.p ? 1.0f / (1.0f - dr.p) : 0.f;
+}
+
+struct Coef4 {
+    float4 sc, sh, sl;
+    bool has_sl;
+};
+
+__device__ __forceinline__ Coef4 load_coef(const float* scale, const float* shift, const float* slope, int c0) {
+    Coef4 c;
+    c.sc = ld4(scale + c0);
+    c.sh = ld4(shift + c0);
+    c.has_sl = slope != nullptr;
+    c.sl = c.has_sl ? ld4(slope + c0) : make_float4(1.f, 1.f, 1.f, 1.f);
+    return c;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr, void* a_mma,
+                  int fmt, float* a_f32) {
+    EW_PROLOGUE
+    if (!cok) return;
+    Coef4 cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
+    Coef4 cr;
+    if (res.zr) cr = load_coef(res.scale, res.shift, res.slope, c0);
+    const long long plane = g.rows * g.Cs;
+    EW_PIXEL_LOOP {
+        long long row = geo_q_to_row(g, q);
+        long long idx = row * g.Cs + c0;
+        float4 y = affine4(ld4(z + idx), cb.sc, cb.sh);
+        if (res.zr) {
+            float4 r = affine4(ld4(res.zr + idx), cr.sc, cr.sh);
+            if (cr.has_sl) r = prelu4(r, cr.sl);
+            y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+        }
+        if (cb.has_sl) y = prelu4(y, cb.sl);
+        if (dr.p > 0.f) {
+            y.x *= keep_scale(dr, idx); y.y *= keep_scale(dr, idx + 1);
+            y.z *= keep_scale(dr, idx + 2); y.w *= keep_scale(dr, idx + 3);
+        }
+        if (a_f32) st4(a_f32 + idx, y);
+        if (a_mma) store_fmt(a_mma, fmt, plane, idx, y);
+    }
+}
+
+int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropout dr, void* a_mma, int fmt,
+                   float* a_f32, cudaStream_t s) {
+    EwShape sh = ew_shape(g);
+    bn_act_fwd_kernel<<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int pool_h) {
+    EW_PROLOGUE
+    if (!cok) return;
+    EW_PIXEL_LOOP {
+        int x = (int)(q % g.W);
+        long long t = q / g.W;
+        int y = (int)(t % g.H);
+        int n = (int)(t / g.H);
+        long long r00 = geo_row(gf, n, y * pool_h, 2 * x);
+        float4 m = max4(ld4(zf + r00 * gf.Cs + c0), ld4(zf + (r00 + 1) * gf.Cs + c0));
+        if (pool_h == 2) {
+            long long r10 = r00 + gf.Wp;
+            m = max4(m, max4(ld4(zf + r10 * gf.Cs + c0), ld4(zf + (r10 + 1) * gf.Cs + c0)));
+        }
+        st4(zp + geo_row(g, n, y, x) * g.Cs + c0, m);
+    }
+}
+
+int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, cudaStream_t s) {
+    EwShape sh = ew_shape(gp);
+    maxpool_fwd_kernel<<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// dzf over FULL-RES interior pixels: each pixel decides whether it is the (first) arg-max of its window
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restrict__ zf, Geo g, int pool_h,
+                   void* dzf, int fmt) {
+    EW_PROLOGUE
+    if (!cok) return;
+    const long long plane = g.rows * g.Cs;
+    EW_PIXEL_LOOP {
+        int x = (int)(q % g.W);
+        long long t = q / g.W;
+        int y = (int)(t % g.H);
+        int n = (int)(t / g.H);
+        long long row = geo_row(g, n, y, x);
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        int py = y / pool_h, px = x / 2;
+        if (py < gp.H && px < gp.W) {
+            long long r00 = geo_row(g, n, py * pool_h, px * 2);
+            int my = y - py * pool_h, mx = x - px * 2;
+            int me = my * 2 + mx;                 // position of this pixel in scan order
+            float v[4][4];
+            int cnt = pool_h == 2 ? 4 : 2;
+            for (int k = 0; k < cnt; ++k) {
+                long long rr = r00 + (k >> 1) * g.Wp + (k & 1);
+                float4 t4 = ld4(zf + rr * g.Cs + c0);
+                v[k][0] = t4.x; v[k][1] = t4.y; v[k][2] = t4.z; v[k][3] = t4.w;
+            }
+            float4 gsrc = ld4(dzp + geo_row(gp, n, py, px) * gp.Cs + c0);
+            float gs[4] = {gsrc.x, gsrc.y, gsrc.z, gsrc.w};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int best = 0;
+                float bv = v[0][i];
+                for (int k = 1; k < cnt; ++k)
+                    if (v[k][i] > bv) { bv = v[k][i]; best = k; }
+                o[i] = best == me ? gs[i] : 0.f;
+            }
+            out = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        store_fmt(dzf, fmt, plane, row * g.Cs + c0, out);
+    }
+}
+
+int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h, void* dzf,
+                     int fmt, cudaStream_t s) {
+    EwShape sh = ew_shape(gf);
+    maxpool_bwd_kernel<<<sh.grid, sh.block, 0, s>>>(dzp, gp, zf, gf, pool_h, dzf, fmt);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// global max: grid (channel chunks, N); block (bx cvec, by pixels)
+__global__ void __launch_bounds__(256)
+gmax_fwd_kernel(const float* __restrict__ x, Geo g, float* feat, int feat_stride, int feat_off, int* argrow) {
+    const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool cok = cv < g.Cs / 4;
+    const int c0 = cv * 4;
+    const int n = blockIdx.y;
+    float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    const int hw = g.H * g.W;
+    if (cok) {
+        for (int p = threadIdx.y; p < hw; p += blockDim.y) {
+            int yy = p / g.W, xx = p - yy * g.W;
+            long long row = geo_row(g, n, yy, xx);
+            float4 v4 = ld4(x + row * g.Cs + c0);
+            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (v[i] > bv[i]) { bv[i] = v[i]; bi[i] = (int)row; }
+        }
+    }
+    __shared__ float sv[256 * 4];
+    __shared__ int si[256 * 4];
+    int t = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sv[t * 4 + i] = bv[i]; si[t * 4 + i] = bi[i]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && cok) {
+        for (int i = 0; i < 4; ++i) {
+            float b = -INFINITY;
+            int r = 0x7fffffff;
+            for (int y = 0; y < (int)blockDim.y; ++y) {
+                int tt = (y * blockDim.x + threadIdx.x) * 4 + i;
+                // first maximum in scan order: larger value wins, ties go to the smaller row
+                if (sv[tt] > b || (sv[tt] == b && si[tt] < r)) { b = sv[tt]; r = si[tt]; }
+            }
+            int c = c0 + i;
+            if (c < g.C) {
+                feat[(long long)n * feat_stride + feat_off + c] = b;
+                argrow[(long long)n * g.C + c] = r;
+            }
+        }
+    }
+}
+
+int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int feat_off, int* argrow,
+                 cudaStream_t s) {
+    int cv = g.Cs / 4;
+    int bx = cv < 32 ? cv : 32;
+    int by = 256 / bx;
+    dim3 grid((cv + bx - 1) / bx, g.N);
+    gmax_fwd_kernel<<<grid, dim3(bx, by), 0, s>>>(x, g, feat, feat_stride, feat_off, argrow);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+__global__ void gmax_bwd_kernel(const float* dfeat, int feat_stride, int feat_off, const int* argrow, Geo g,
+                                float* dx) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)g.N * g.C) return;
+    int n = (int)(i / g.C), c = (int)(i % g.C);
+    long long row = argrow[i];
+    dx[row * g.Cs + c] += dfeat[(long long)n * feat_stride + feat_off + c];
+}
+
+int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* argrow, const Geo& g,
+                  float* dx, cudaStream_t s) {
+    long long total = (long long)g.N * g.C;
+    gmax_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(dfeat, feat_stride, feat_off, argrow, g, dx);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of a = act(BN(z) [+ r]) : shared recomputation of dy (and the PReLU slope term)
+struct BwdCoef {
+    Coef4 cb, cr;
+    float4 mean, invstd;
+    bool has_res;
+};
+
+__device__ __forceinline__ void bwd_point(const float* dA1, const float* dA2, const float* z, const Residual& res,
+                                          const BwdCoef& k, const Dropout& dr, long long idx, float4& dy,
+                                          float4& zhat, float4& dsl) {
+    float4 zz = ld4(z + idx);
+    float4 y = affine4(zz, k.cb.sc, k.cb.sh);
+    if (k.has_res) {
+        float4 r = affine4(ld4(res.zr + idx), k.cr.sc, k.cr.sh);
+        if (k.cr.has_sl) r = prelu4(r, k.cr.sl);
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+    }
+    float4 g = ld4(dA1 + idx);
+    if (dA2) {
+        float4 g2 = ld4(dA2 + idx);
+        g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+    }
+    if (dr.p > 0.f) {
+        g.x *= keep_scale(dr, idx); g.y *= keep_scale(dr, idx + 1);
+        g.z *= keep_scale(dr, idx + 2); g.w *= keep_scale(dr, idx + 3);
+    }
+    if (k.cb.has_sl) {
+        dsl = make_float4(y.x > 0.f ? 0.f : y.x * g.x, y.y > 0.f ? 0.f : y.y * g.y,
+                          y.z > 0.f ? 0.f : y.z * g.z, y.w > 0.f ? 0.f : y.w * g.w);
+        dy = make_float4(y.x > 0.f ? g.x : k.cb.sl.x * g.x, y.y > 0.f ? g.y : k.cb.sl.y * g.y,
+                         y.z > 0.f ? g.z : k.cb.sl.z * g.z, y.w > 0.f ? g.w : k.cb.sl.w * g.w);
+    } else {
+        dsl = make_float4(0.f, 0.f, 0.f, 0.f);
+        dy = g;
+    }
+    zhat = make_float4((zz.x - k.mean.x) * k.invstd.x, (zz.y - k.mean.y) * k.invstd.y,
+                       (zz.z - k.mean.z) * k.invstd.z, (zz.w - k.mean.w) * k.invstd.w);
+}
+
+__device__ __forceinline__ BwdCoef load_bwd(const BnCoef& bn, const Residual& res, int c0) {
+    BwdCoef k;
+    k.cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
+    k.has_res = res.zr != nullptr;
+    if (k.has_res) k.cr = load_coef(res.scale, res.shift, res.slope, c0);
+    k.mean = ld4(bn.mean + c0);
+    k.invstd = ld4(bn.invstd + c0);
+    return k;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2,
+                         const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr,
+                         double* partials) {
+    EW_PROLOGUE
+    Acc4 acc[3];
+    acc[0].init(); acc[1].init(); acc[2].init();
+    if (cok) {
+        BwdCoef k = load_bwd(bn, res, c0);
+        EW_PIXEL_LOOP {
+            long long idx = geo_q_to_row(g, q) * g.Cs + c0;
+            float4 dy, zh, dsl;
+            bwd_point(dA1, dA2, z, res, k, dr, idx, dy, zh, dsl);
+            acc[0].add(dy);
+            acc[1].add(make_float4(dy.x * zh.x, dy.y * zh.y, dy.z * zh.z, dy.w * zh.w));
+            acc[2].add(dsl);
+        }
+    }
+    block_reduce_store<3>(acc, partials, g.Cs, c0, cok);
+}
+
+int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
+                      Dropout dr, double* partials, cudaStream_t s) {
+    EwShape sh = ew_shape(g);
+    bn_act_bwd_reduce_kernel<<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs,
+                                       float* dgamma, float* dbeta, float* dslope, float* c1, float* c2) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cs) return;
+    if (c >= C) { c1[c] = 0.f; c2[c] = 0.f; return; }
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int b = 0; b < nblk; ++b) {
+        s0 += partials[((long long)b * 3 + 0) * Cs + c];
+        s1 += partials[((long long)b * 3 + 1) * Cs + c];
+        s2 += partials[((long long)b * 3 + 2) * Cs + c];
+    }
+    if (dbeta) dbeta[c] = (float)s0;
+    if (dgamma) dgamma[c] = (float)s1;
+    if (dslope) dslope[c] = (float)s2;
+    c1[c] = (float)(s0 / (double)count);
+    c2[c] = (float)(s1 / (double)count);
+}
+
+int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, float* dgamma, float* dbeta,
+                    float* dslope, float* c1, float* c2, cudaStream_t s) {
+    bn_bwd_finalize_kernel<<<(Cs + 127) / 128, 128, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
+                                                           c1, c2);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2, const float* __restrict__ z,
+                        Geo g, BnCoef bn, Residual res, Dropout dr, const float* c1, const float* c2, void* dz,
+                        int fmt, float* dres) {
+    EW_PROLOGUE
+    if (!cok) return;
+    BwdCoef k = load_bwd(bn, res, c0);
+    float4 m1 = ld4(c1 + c0), m2 = ld4(c2 + c0);
+    const long long plane = g.rows * g.Cs;
+    EW_PIXEL_LOOP {
+        long long idx = geo_q_to_row(g, q) * g.Cs + c0;
+        float4 dy, zh, dsl;
+        bwd_point(dA1, dA2, z, res, k, dr, idx, dy, zh, dsl);
+        float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
+                               k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
+        store_fmt(dz, fmt, plane, idx, o);
+        if (dres) st4(dres + idx, dy);
+    }
+}
+
+int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
+                     Dropout dr, const float* c1, const float* c2, void* dz, int fmt, float* dres, cudaStream_t s) {
+    EwShape sh = ew_shape(g);
+    bn_act_bwd_apply_kernel<<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const float* x, long long rows, int C, int ld, float* out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (long long r = 0; r < rows; ++r) s += x[r * ld + c];
+    out[c] = (float)s;
+}
+
+int colsum(const float* x, long long rows, int C, int ld, float* out, cudaStream_t s) {
+    colsum_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, rows, C, ld, out);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+__global__ void copy2d_kernel(const float* src, long long rows, int C, int lds, float* dst, int ldd) {
+    long long total = rows * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / C;
+        int c = (int)(i % C);
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+
+int copy2d(const float* src, long long rows, int C, int lds, float* dst, int ldd, cudaStream_t s) {
+    long long total = rows * C;
+    int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    copy2d_kernel<<<blocks, 256, 0, s>>>(src, rows, C, lds, dst, ldd);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw_to_pf_kernel(const float* x, Geo g, void* dst, int fmt) {
+    long long total = g.pixels * g.Cs;
+    long long plane = g.rows * g.Cs;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % g.Cs);
+        long long q = i / g.Cs;
+        int xx = (int)(q % g.W);
+        long long t = q / g.W;
+        int yy = (int)(t % g.H);
+        int n = (int)(t / g.H);
+        float v = c < g.C ? x[(((long long)n * g.C + c) * g.H + yy) * g.W + xx] : 0.f;
+        long long idx = geo_row(g, n, yy, xx) * g.Cs + c;
+        if (fmt == FMT_F32) {
+            reinterpret_cast<float*>(dst)[idx] = v;
+        } else {
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            reinterpret_cast<__nv_bfloat16*>(dst)[idx] = h;
+            reinterpret_cast<__nv_bfloat16*>(dst)[plane + idx] = l;
+        }
+    }
+}
+
+int nchw_to_pf(const float* x, const Geo& g, void* dst, int fmt, cudaStream_t s) {
+    nchw_to_pf_kernel<<<1184, 256, 0, s>>>(x, g, dst, fmt);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+__global__ void pf_to_nchw_kernel(const float* src, Geo g, float* dst) {
+    long long total = g.pixels * g.C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int xx = (int)(i % g.W);
+        long long t = i / g.W;
+        int yy = (int)(t % g.H);
+        t /= g.H;
+        int c = (int)(t % g.C);
+        int n = (int)(t / g.C);
+        dst[i] = src[geo_row(g, n, yy, xx) * g.Cs + c];
+    }
+}
+
+int pf_to_nchw(const float* src, const Geo& g, float* dst, cudaStream_t s) {
+    pf_to_nchw_kernel<<<1184, 256, 0, s>>>(src, g, dst);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace fsb

@@ -1,0 +1,89 @@
+// Element-wise / reduction kernels over padded-flat NHWC tensors: BatchNorm statistics, BN-apply +
+// PReLU (+ residual, + dropout), max-pool, global max heads, and all their backward passes.
+// These replace the reference's nn.BatchNorm{1,2}d / nn.PReLU / nn.MaxPool{1,2}d /
+// nn.AdaptiveMaxPool{1,2}d / nn.Dropout call sites (networks/classifiers.py:524-549, :72-104) and
+// their autograd mirrors.
+#pragma once
+#include "common.cuh"
+
+namespace fsb {
+
+struct BnCoef {            // per-channel vectors of length Cs (padded entries are zero)
+    const float* scale;    // gamma * invstd
+    const float* shift;    // beta - mean * scale
+    const float* slope;    // PReLU slope, nullptr = no activation
+    const float* mean;     // batch mean      (backward only)
+    const float* invstd;   // 1/sqrt(var+eps) (backward only)
+};
+
+struct Residual {          // identity branch r = prelu(zr*scale+shift, slope); nullptr zr = none
+    const float* zr;
+    const float* scale;
+    const float* shift;
+    const float* slope;
+};
+
+struct Dropout {           // keep mask = hash(seed, element) >= p ; scale 1/(1-p); p == 0 = off
+    float p;
+    unsigned long long seed;
+};
+
+// number of pixel-blocks an element-wise reduction over `g` uses (partials are [nblk][K][Cs] doubles)
+int ew_num_blocks(const Geo& g);
+
+int pf_zero_border(void* buf, int fmt, const Geo& g, cudaStream_t s);
+int pf_zero_all(void* buf, int fmt, const Geo& g, cudaStream_t s);
+
+// sum / sum of squares per channel over interior pixels -> partials [nblk][2][Cs] (double)
+int pf_stats(const float* x, const Geo& g, double* partials, cudaStream_t s);
+
+// Finalize BN statistics.  training: batch statistics from `partials` (count = interior pixels),
+// running stats updated in place (momentum 0.1, unbiased variance), *bn_count += 1.
+// eval: running stats.  gamma/beta/run_* have C entries; outputs have Cs entries (tail zeroed).
+int bn_finalize(const double* partials, int nblk, long long count, const float* gamma,
+                const float* beta, float* run_mean, float* run_var, long long* bn_count, int training,
+                int C, int Cs, float* scale, float* shift, float* mean, float* invstd, cudaStream_t s);
+
+// analytic statistics of the frequency-encoding channel linspace(-1, 1, H) (2D block 0, channel 1):
+// appends channel 1 to a 2-channel partial record [1][2][16] (count = N*H*W)
+int freq_encoding_stats(int H, long long n_times_w, double* partials16, cudaStream_t s);
+
+// a = act(BN(z) [+ residual]) ; writes any of: GEMM-format plane(s) `a_mma` (fmt), float32 `a_f32`
+int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropout dr, void* a_mma,
+                   int fmt, float* a_f32, cudaStream_t s);
+
+// 2x2 (pool_h = 2) or 1x2 (pool_h = 1) max pool, floor mode: zf (gf) -> zp (gp)
+int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, cudaStream_t s);
+// dzf (fmt planes, full-res geometry) <- dzp routed to the first maximum of every window
+int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h,
+                     void* dzf, int fmt, cudaStream_t s);
+
+// global max over (H, W) per (n, c): feat[n*feat_stride + feat_off + c], argrow[n*C + c] (padded row)
+int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int feat_off, int* argrow,
+                 cudaStream_t s);
+// dx[argrow, c] += dfeat[n*feat_stride + feat_off + c]
+int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* argrow, const Geo& g,
+                  float* dx, cudaStream_t s);
+
+// backward of a = act(BN(z) [+ residual]) given dA = dA1 (+ dA2):
+//   reduce  : partials [nblk][3][Cs] doubles = sum dy, sum dy*zhat, sum dslope
+//   finalize: dgamma, dbeta, dslope (C entries, written) and c1 = mean dy, c2 = mean dy*zhat (Cs)
+//   apply   : dz = scale * (dy - c1 - zhat*c2) -> fmt planes ; dres (float32, optional) = dy
+int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn,
+                      Residual res, Dropout dr, double* partials, cudaStream_t s);
+int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, float* dgamma,
+                    float* dbeta, float* dslope, float* c1, float* c2, cudaStream_t s);
+int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn,
+                     Residual res, Dropout dr, const float* c1, const float* c2, void* dz, int fmt,
+                     float* dres, cudaStream_t s);
+
+// column sums of a dense (rows, C) matrix with row stride ld (final Linear bias gradient)
+int colsum(const float* x, long long rows, int C, int ld, float* out, cudaStream_t s);
+// dst[r*ldd + c] = src[r*lds + c]
+int copy2d(const float* src, long long rows, int C, int lds, float* dst, int ldd, cudaStream_t s);
+
+// layout converters for taps / unit tests
+int nchw_to_pf(const float* x, const Geo& g, void* dst, int fmt, cudaStream_t s);
+int pf_to_nchw(const float* src, const Geo& g, float* dst, cudaStream_t s);
+
+}  // namespace fsb

@@ -1,0 +1,66 @@
+// Row-shifted GEMM interface: every convolution / linear layer of the network is
+//     Z[r, :Cout] = bias + sum_t A[r + off_t, :Cin] * W_t          (forward)
+//     dA[r, :Cin] = sum_t dZ[r - off_t, :Cout] * W_t^T             (dgrad)
+//     dW_t        = sum_r A[r + off_t, :]^T dZ[r, :]               (wgrad)
+// over padded-flat NHWC tensors (common.cuh).  Two back ends implement it:
+//   precision 0 : float32 CUDA-core tiles            (gemm_simt.cu)
+//   precision 1 : bf16x3 split tcgen05 / TMEM / TMA  (gemm_tc.cu)   -- fp32-grade accuracy
+//   precision 2 : single-pass bf16 tcgen05           (gemm_tc.cu)
+// Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.Conv1d / nn.Linear
+// (networks/classifiers.py:526-531, :75-80, :544-549) and their autograd backward.
+#pragma once
+#include "common.cuh"
+
+namespace fsb {
+
+struct ConvGeom {
+    long long rows;      // padded-flat rows of the output (== rows of the input)
+    int ntaps;           // 1 (1x1 / linear), 3 (1x3) or 9 (3x3)
+    int offs[9];         // input row offset per tap, torch tap order (dy major, dx minor)
+    int Cin, CsIn, Cout, CsOut;
+};
+
+inline ConvGeom make_conv_geom(const Geo& g, int Cin, int Cout, int kh, int kw) {
+    ConvGeom c;
+    c.rows = g.rows;
+    c.ntaps = kh * kw;
+    for (int i = 0; i < 9; ++i) c.offs[i] = 0;
+    for (int dy = 0; dy < kh; ++dy)
+        for (int dx = 0; dx < kw; ++dx) c.offs[dy * kw + dx] = (dy - kh / 2) * g.Wp + (dx - kw / 2);
+    c.Cin = Cin; c.CsIn = round_up(Cin, 16);
+    c.Cout = Cout; c.CsOut = round_up(Cout, 16);
+    return c;
+}
+
+inline int act_fmt(int precision) { return precision == 0 ? FMT_F32 : FMT_BF16X2; }
+
+// bytes of the packed-weight record (forward pack + dgrad pack + padded bias)
+size_t packed_weight_bytes(int precision, const ConvGeom& c);
+// w: torch layout (Cout, Cin, taps) float32; bias: Cout or nullptr
+int pack_weights(int precision, const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s);
+
+int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s);
+int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
+
+size_t wgrad_scratch_bytes(int precision, const ConvGeom& c);
+// dw: torch layout (Cout, Cin, taps), fully overwritten
+int conv_gemm_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,
+                    cudaStream_t s);
+
+// --- per-backend entry points -------------------------------------------------------------------
+size_t simt_packed_weight_bytes(const ConvGeom& c);
+int simt_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s);
+int simt_fwd(const float* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s);
+int simt_dgrad(const float* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
+size_t simt_wgrad_scratch_bytes(const ConvGeom& c);
+int simt_wgrad(const float* A, const float* dZ, float* dw, void* scratch, const ConvGeom& c, cudaStream_t s);
+
+size_t tc_packed_weight_bytes(const ConvGeom& c);
+int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s);
+int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s);
+int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
+size_t tc_wgrad_scratch_bytes(const ConvGeom& c);
+int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,
+             cudaStream_t s);
+
+}  // namespace fsb

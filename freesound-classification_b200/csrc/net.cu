@@ -1,0 +1,727 @@
+// Whole-network executor ("plan"): feature kernel -> conv blocks -> global-max heads -> FC head,
+// forward and backward, for TwoDimensionalCNNClassificationModel (networks/classifiers.py:483-607)
+// and HierarchicalCNNClassificationModel (:107-217).  The host side is a flat C++ schedule of kernel
+// launches on the caller's stream; every tensor lives in the caller-provided workspace.
+//
+// Parameter order ("canonical order", == named_parameters() of the reference module tree), per block k:
+//   0 bn_in.w 1 bn_in.b 2 conv.w 3 conv.b 4 bn_a.w 5 bn_a.b 6 prelu_a.w
+//   7 res.conv1.w 8 res.conv1.b 9 res.bn1.w 10 res.bn1.b 11 res.conv2.w 12 res.conv2.b 13 res.bn2.w 14 res.bn2.b
+//   15 res.conv3.w 16 res.conv3.b 17 res.bn3.w 18 res.bn3.b 19 res.prelu1.w 20 res.prelu2.w 21 res.prelu3.w
+// then the head: bn0.w bn0.b lin1.w lin1.b bn2.w bn2.b prelu.w lin5.w lin5.b
+// BN buffer order: per block bn_in, bn_a, bn1, bn2, bn3 ; head bn0, bn2.
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv0.cuh"
+#include "eltwise.cuh"
+#include "gemm.cuh"
+
+using namespace fsb;
+
+namespace {
+
+enum { P_BNIN_W = 0, P_BNIN_B, P_CONV_W, P_CONV_B, P_BNA_W, P_BNA_B, P_PRELUA, P_C1_W, P_C1_B, P_BN1_W, P_BN1_B,
+       P_C2_W, P_C2_B, P_BN2_W, P_BN2_B, P_C3_W, P_C3_B, P_BN3_W, P_BN3_B, P_PRELU1, P_PRELU2, P_PRELU3,
+       P_PER_BLOCK };
+enum { H_BN0_W = 0, H_BN0_B, H_L1_W, H_L1_B, H_BN2_W, H_BN2_B, H_PRELU, H_L5_W, H_L5_B, H_COUNT };
+enum { B_IN = 0, B_A, B_1, B_2, B_3, B_PER_BLOCK };
+
+enum Cat { CAT_FEAT = 0, CAT_GEMM_FWD, CAT_GEMM_DGRAD, CAT_GEMM_WGRAD, CAT_CONV0, CAT_ELT_FWD, CAT_ELT_BWD,
+           CAT_HEAD, CAT_PACK, CAT_COUNT };
+const char* kCatNames[CAT_COUNT] = {"feat", "gemm_fwd", "gemm_dgrad", "gemm_wgrad", "conv0", "eltwise_fwd",
+                                    "eltwise_bwd", "head", "pack"};
+
+struct BnBuf {
+    float *scale, *shift, *mean, *invstd, *c1, *c2;
+    int C, Cs;
+    BnCoef coef(const float* slope) const { return BnCoef{scale, shift, slope, mean, invstd}; }
+};
+
+struct Bump {
+    char* base;
+    size_t off;
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+    void* take_bytes(size_t bytes) { return take<char>(bytes); }
+};
+
+struct BlockPlan {
+    int Cin, C;
+    Geo g_in, g_full, g;
+    ConvGeom entry, c1, c2, c3;
+    BnBuf bn_in, bn_a, bn1, bn2, bn3;
+    void *pk_entry, *pk1, *pk2, *pk3;
+    float *x_in;         // float32 PF block input (1D block 0: features; k>0: previous out)
+    void *u;             // BN_in output, GEMM format (unused for 2D block 0)
+    float *zf, *zp, *z1, *z2, *z3, *out;
+    void *r0, *a1, *a2;
+    int* argrow;
+    int head_off;        // column offset in the concatenated head input, -1 if no head
+    // backward
+    float *d_out, *da2, *da1, *dr0a, *dr0b, *dzp, *du;
+    void *dz3, *dz2, *dz1, *dzf;
+};
+
+}  // namespace
+
+struct fsb_net {
+    fsb_net_config cfg;
+    std::vector<float> fb_vals;
+    std::vector<int> fb_off, fb_start, fb_len;
+    int D, Ds, CsCls;
+    std::vector<long long> param_numel, param_offset;
+    long long total_params;
+
+    // binding state
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    int N = 0, T = 0, training = 0, frames = 0;
+    bool tables_ready = false, fwd_done = false;
+    unsigned long long dropout_seed = 0;
+
+    // carved buffers
+    std::vector<BlockPlan> blocks;
+    void* feat_tables;
+    float* d_fb_vals;
+    int *d_fb_off, *d_fb_start, *d_fb_len;
+    float* feat;          // 2D: (N, F, frames) plain
+    double* partials;     // shared reduction scratch
+    void* wgrad_scratch;
+    float *feats, *h0, *z1h, *h1, *zl, *dzl, *dh1, *dz1h, *dh0, *dfeats;
+    BnBuf hbn0, hbn2;
+    ConvGeom lin1, lin5;
+    void *pk_l1, *pk_l5;
+    Geo g_head, g_cls;
+
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Rec { int cat; int e0, e1; double flops; };
+    std::vector<Rec> recs;
+    size_t ev_used = 0;
+};
+
+namespace {
+
+long long conv_numel(int cout, int cin, int taps) { return (long long)cout * cin * taps; }
+
+void build_param_table(fsb_net* net) {
+    const fsb_net_config& c = net->cfg;
+    int taps = c.two_d ? 9 : 3;
+    net->param_numel.clear();
+    for (int k = 0; k < c.num_blocks; ++k) {
+        int cin = k == 0 ? (c.two_d ? 2 : c.n_features) : c.depth[k - 1];
+        int d = c.depth[k];
+        long long v[P_PER_BLOCK] = {cin, cin, conv_numel(d, cin, taps), d, d, d, d,
+                                    conv_numel(d, d, 1), d, d, d, conv_numel(d, d, taps), d, d, d,
+                                    conv_numel(d, d, 1), d, d, d, d, d, d};
+        for (int i = 0; i < P_PER_BLOCK; ++i) net->param_numel.push_back(v[i]);
+    }
+    long long D = net->D;
+    long long h[H_COUNT] = {D, D, D * D, D, D, D, D, (long long)c.n_classes * D, c.n_classes};
+    for (int i = 0; i < H_COUNT; ++i) net->param_numel.push_back(h[i]);
+    net->param_offset.resize(net->param_numel.size());
+    long long off = 0;
+    for (size_t i = 0; i < net->param_numel.size(); ++i) {
+        net->param_offset[i] = off;
+        off += net->param_numel[i];
+    }
+    net->total_params = off;
+}
+
+void carve_bn(Bump& b, BnBuf& bn, int C) {
+    bn.C = C;
+    bn.Cs = round_up(C, 16);
+    bn.scale = b.take<float>(bn.Cs);
+    bn.shift = b.take<float>(bn.Cs);
+    bn.mean = b.take<float>(bn.Cs);
+    bn.invstd = b.take<float>(bn.Cs);
+    bn.c1 = b.take<float>(bn.Cs);
+    bn.c2 = b.take<float>(bn.Cs);
+}
+
+size_t plane_bytes(const Geo& g) { return (size_t)g.rows * g.Cs * 4; }   // f32 plane == 2 bf16 planes
+
+// Carves every buffer for (N, T); with base == nullptr this is the size query.
+size_t carve(fsb_net* net, char* base, int N, int T, int training) {
+    const fsb_net_config& c = net->cfg;
+    const int prec = c.precision;
+    Bump b{base, 0};
+    int frames = 1 + T / c.hop;
+    net->frames = frames;
+    net->feat_tables = b.take_bytes(fsb_feat_table_bytes(c.n_fft));
+    net->d_fb_vals = b.take<float>(net->fb_vals.size() + 1);
+    net->d_fb_off = b.take<int>(net->fb_off.size() + 1);
+    net->d_fb_start = b.take<int>(net->fb_start.size() + 1);
+    net->d_fb_len = b.take<int>(net->fb_len.size() + 1);
+    net->feat = c.two_d ? b.take<float>((size_t)N * c.n_features * frames) : nullptr;
+
+    net->blocks.assign(c.num_blocks, BlockPlan());
+    size_t max_partials = (size_t)plain_stats_blocks() * 2 * 16;
+    size_t max_wgrad = 0;
+    int Hin = c.two_d ? c.n_features : 1, Win = frames;
+    int head_off = 0;
+    for (int k = 0; k < c.num_blocks; ++k) {
+        BlockPlan& B = net->blocks[k];
+        B.Cin = k == 0 ? (c.two_d ? 2 : c.n_features) : c.depth[k - 1];
+        B.C = c.depth[k];
+        int padH = c.two_d ? 1 : 0;
+        int H = c.two_d ? Hin / 2 : 1, W = Win / 2;
+        B.g_in = make_geo(N, Hin, Win, B.Cin, padH, 1);
+        B.g_full = make_geo(N, Hin, Win, B.C, padH, 1);
+        B.g = make_geo(N, H, W, B.C, padH, 1);
+        int kh = c.two_d ? 3 : 1;
+        B.entry = make_conv_geom(B.g_in, B.Cin, B.C, kh, 3);
+        B.c1 = make_conv_geom(B.g, B.C, B.C, 1, 1);
+        B.c2 = make_conv_geom(B.g, B.C, B.C, kh, 3);
+        B.c3 = make_conv_geom(B.g, B.C, B.C, 1, 1);
+        carve_bn(b, B.bn_in, B.Cin);
+        carve_bn(b, B.bn_a, B.C);
+        carve_bn(b, B.bn1, B.C);
+        carve_bn(b, B.bn2, B.C);
+        carve_bn(b, B.bn3, B.C);
+        bool direct0 = c.two_d && k == 0;
+        B.pk_entry = direct0 ? nullptr : b.take_bytes(packed_weight_bytes(prec, B.entry));
+        B.pk1 = b.take_bytes(packed_weight_bytes(prec, B.c1));
+        B.pk2 = b.take_bytes(packed_weight_bytes(prec, B.c2));
+        B.pk3 = b.take_bytes(packed_weight_bytes(prec, B.c3));
+        if (direct0) {
+            B.x_in = nullptr; B.u = nullptr; B.zf = nullptr;
+        } else {
+            B.x_in = k == 0 ? b.take<float>((size_t)B.g_in.rows * B.g_in.Cs) : net->blocks[k - 1].out;
+            B.u = b.take_bytes(plane_bytes(B.g_in));
+            B.zf = b.take<float>((size_t)B.g_full.rows * B.g_full.Cs);
+        }
+        size_t pe = (size_t)B.g.rows * B.g.Cs;
+        B.zp = b.take<float>(pe);
+        B.r0 = b.take_bytes(pe * 4);
+        B.z1 = b.take<float>(pe);
+        B.a1 = b.take_bytes(pe * 4);
+        B.z2 = b.take<float>(pe);
+        B.a2 = b.take_bytes(pe * 4);
+        B.z3 = b.take<float>(pe);
+        B.out = b.take<float>(pe);
+        if (k >= c.start_deep_supervision_on) {
+            B.head_off = head_off;
+            head_off += B.C;
+            B.argrow = b.take<int>((size_t)N * B.C);
+        } else {
+            B.head_off = -1;
+            B.argrow = nullptr;
+        }
+        if (training) {
+            B.d_out = b.take<float>(pe);
+            B.da2 = b.take<float>(pe);
+            B.da1 = b.take<float>(pe);
+            B.dr0a = b.take<float>(pe);
+            B.dr0b = b.take<float>(pe);
+            B.dzp = b.take<float>(pe);
+            B.dz3 = b.take_bytes(pe * 4);
+            B.dz2 = b.take_bytes(pe * 4);
+            B.dz1 = b.take_bytes(pe * 4);
+            if (!direct0) {
+                B.dzf = b.take_bytes(plane_bytes(B.g_full));
+                B.du = b.take<float>((size_t)B.g_in.rows * B.g_in.Cs);
+                max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.entry));
+            } else {
+                max_wgrad = std::max(max_wgrad, conv0_bwd_scratch_bytes(B.g));
+            }
+            max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c1));
+            max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c2));
+        }
+        max_partials = std::max(max_partials, (size_t)ew_num_blocks(B.g_in) * 3 * B.g_in.Cs);
+        max_partials = std::max(max_partials, (size_t)ew_num_blocks(B.g) * 3 * B.g.Cs);
+        Hin = H; Win = W;
+    }
+    // head
+    net->g_head = make_geo(1, 1, N, net->D, 0, 0);
+    net->g_cls = make_geo(1, 1, N, c.n_classes, 0, 0);
+    net->lin1 = make_conv_geom(net->g_head, net->D, net->D, 1, 1);
+    net->lin5 = make_conv_geom(net->g_head, net->D, c.n_classes, 1, 1);
+    carve_bn(b, net->hbn0, net->D);
+    carve_bn(b, net->hbn2, net->D);
+    net->pk_l1 = b.take_bytes(simt_packed_weight_bytes(net->lin1));
+    net->pk_l5 = b.take_bytes(simt_packed_weight_bytes(net->lin5));
+    size_t he = (size_t)N * net->Ds;
+    net->feats = b.take<float>(he);
+    net->h0 = b.take<float>(he);
+    net->z1h = b.take<float>(he);
+    net->h1 = b.take<float>(he);
+    net->zl = b.take<float>((size_t)N * net->CsCls);
+    if (training) {
+        net->dzl = b.take<float>((size_t)N * net->CsCls);
+        net->dh1 = b.take<float>(he);
+        net->dz1h = b.take<float>(he);
+        net->dh0 = b.take<float>(he);
+        net->dfeats = b.take<float>(he);
+        max_wgrad = std::max(max_wgrad, simt_wgrad_scratch_bytes(net->lin1));
+        max_wgrad = std::max(max_wgrad, simt_wgrad_scratch_bytes(net->lin5));
+    }
+    max_partials = std::max(max_partials, (size_t)ew_num_blocks(net->g_head) * 3 * net->g_head.Cs);
+    net->partials = b.take<double>(max_partials);
+    net->wgrad_scratch = b.take_bytes(max_wgrad + 256);
+    return align_up(b.off, 256);
+}
+
+// ---- profiling helpers ---------------------------------------------------------------------------
+struct Scope {
+    fsb_net* net;
+    cudaStream_t s;
+    int idx;
+    Scope(fsb_net* n, cudaStream_t st, int cat, double flops = 0.0) : net(n), s(st), idx(-1) {
+        if (!net->profiling) return;
+        if (net->ev_used + 2 > net->ev_pool.size()) {
+            size_t old = net->ev_pool.size();
+            net->ev_pool.resize(old + 256);
+            for (size_t i = old; i < net->ev_pool.size(); ++i) cudaEventCreate(&net->ev_pool[i]);
+        }
+        fsb_net::Rec r{cat, (int)net->ev_used, (int)net->ev_used + 1, flops};
+        net->ev_used += 2;
+        cudaEventRecord(net->ev_pool[r.e0], s);
+        idx = (int)net->recs.size();
+        net->recs.push_back(r);
+    }
+    ~Scope() {
+        if (idx >= 0) cudaEventRecord(net->ev_pool[net->recs[idx].e1], s);
+    }
+};
+
+double conv_flops(const ConvGeom& c, const Geo& g) { return 2.0 * c.Cin * c.Cout * c.ntaps * (double)g.pixels; }
+
+#define RUN(cat, flops, expr)               \
+    do {                                    \
+        Scope _sc(net, s, cat, flops);      \
+        FSB_TRY(expr);                      \
+    } while (0)
+
+const Residual kNoRes = {nullptr, nullptr, nullptr, nullptr};
+const Dropout kNoDrop = {0.f, 0ull};
+
+int bn_forward_stats(fsb_net* net, cudaStream_t s, const float* x, const Geo& g, BnBuf& bn, const float* gamma,
+                     const float* beta, float* rm, float* rv, long long* cnt, int training, int cat) {
+    if (training) RUN(cat, 0, pf_stats(x, g, net->partials, s));
+    RUN(cat, 0, bn_finalize(net->partials, ew_num_blocks(g), g.pixels, gamma, beta, rm, rv, cnt, training, bn.C,
+                            bn.Cs, bn.scale, bn.shift, bn.mean, bn.invstd, s));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, const int* fb_off,
+                              const int* fb_start, const int* fb_len, int fb_nnz, fsb_net** out) {
+    FSB_REQUIRE(cfg && out, "net_create: null argument");
+    FSB_REQUIRE(cfg->num_blocks >= 1 && cfg->num_blocks <= FSB_MAX_BLOCKS, "net_create: num_blocks out of range");
+    FSB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, "net_create: precision must be 0, 1 or 2");
+    FSB_REQUIRE(cfg->feat_mode == 1 || cfg->feat_mode == 2, "net_create: feat_mode must be 1 (stft) or 2 (mel)");
+    FSB_REQUIRE(cfg->start_deep_supervision_on < cfg->num_blocks, "net_create: no deep-supervision head");
+    FSB_REQUIRE(cfg->dropout_p >= 0.f && cfg->dropout_p < 1.f, "net_create: dropout must be in [0, 1)");
+    fsb_net* net = new fsb_net();
+    net->cfg = *cfg;
+    if (cfg->feat_mode == 2) {
+        FSB_REQUIRE(fb_vals && fb_off && fb_start && fb_len && fb_nnz > 0, "net_create: mel mode needs a filterbank");
+        int n_mel = cfg->n_features;
+        net->fb_vals.assign(fb_vals, fb_vals + fb_nnz);
+        net->fb_off.assign(fb_off, fb_off + n_mel);
+        net->fb_start.assign(fb_start, fb_start + n_mel);
+        net->fb_len.assign(fb_len, fb_len + n_mel);
+    }
+    net->D = 0;
+    for (int k = cfg->start_deep_supervision_on; k < cfg->num_blocks; ++k) net->D += cfg->depth[k];
+    net->Ds = round_up(net->D, 16);
+    net->CsCls = round_up(cfg->n_classes, 16);
+    build_param_table(net);
+    *out = net;
+    return 0;
+}
+
+extern "C" void fsb_net_destroy(fsb_net* net) {
+    if (!net) return;
+    for (cudaEvent_t e : net->ev_pool) cudaEventDestroy(e);
+    delete net;
+}
+
+extern "C" int fsb_net_num_params(const fsb_net* net) { return (int)net->param_numel.size(); }
+extern "C" int fsb_net_num_bn(const fsb_net* net) { return net->cfg.num_blocks * B_PER_BLOCK + 2; }
+extern "C" long long fsb_net_param_numel(const fsb_net* net, int index) {
+    return index >= 0 && index < (int)net->param_numel.size() ? net->param_numel[index] : -1;
+}
+
+static int check_shape(const fsb_net* net, int n, int t) {
+    const fsb_net_config& c = net->cfg;
+    FSB_REQUIRE(n >= 1 && t > c.n_fft / 2, "net: need N >= 1 and T > n_fft/2 (N=%d, T=%d)", n, t);
+    int frames = 1 + t / c.hop;
+    int w = frames, h = c.two_d ? c.n_features : 1;
+    for (int k = 0; k < c.num_blocks; ++k) {
+        w /= 2;
+        if (c.two_d) h /= 2;
+    }
+    FSB_REQUIRE(w >= 1 && h >= 1, "net: clip too short for %d pooling stages (T=%d -> %d frames)", c.num_blocks, t,
+                frames);
+    return 0;
+}
+
+extern "C" size_t fsb_net_workspace_bytes(const fsb_net* net, int n, int t, int training) {
+    if (check_shape(net, n, t) != 0) return 0;
+    fsb_net tmp = *net;     // carve mutates the plan; run the size query on a copy
+    tmp.ev_pool.clear();
+    return carve(&tmp, nullptr, n, t, training);
+}
+
+static int bind(fsb_net* net, void* ws, size_t ws_bytes, int n, int t, int training, cudaStream_t s) {
+    if (net->ws == ws && net->N == n && net->T == t && net->training == training && net->ws_bytes == ws_bytes) return 0;
+    FSB_TRY(check_shape(net, n, t));
+    size_t need = carve(net, nullptr, n, t, training);
+    if (ws_bytes < need) {
+        set_error("net: workspace too small (%zu < %zu)", ws_bytes, need);
+        return FSB_E_WORKSPACE;
+    }
+    carve(net, (char*)ws, n, t, training);
+    net->ws = ws; net->ws_bytes = ws_bytes; net->N = n; net->T = t; net->training = training;
+    net->fwd_done = false;
+    // zero once: GEMM inputs rely on zero borders / zero channel tails, which the element-wise
+    // kernels (interior-only writers) then preserve for the lifetime of the binding
+    FSB_CUDA(cudaMemsetAsync(ws, 0, need, s));
+    const fsb_net_config& c = net->cfg;
+    FSB_TRY(fsb_feat_init_tables(c.n_fft, net->feat_tables, s));
+    if (c.feat_mode == 2) {
+        FSB_CUDA(cudaMemcpyAsync(net->d_fb_vals, net->fb_vals.data(), net->fb_vals.size() * 4, cudaMemcpyHostToDevice, s));
+        FSB_CUDA(cudaMemcpyAsync(net->d_fb_off, net->fb_off.data(), net->fb_off.size() * 4, cudaMemcpyHostToDevice, s));
+        FSB_CUDA(cudaMemcpyAsync(net->d_fb_start, net->fb_start.data(), net->fb_start.size() * 4, cudaMemcpyHostToDevice, s));
+        FSB_CUDA(cudaMemcpyAsync(net->d_fb_len, net->fb_len.data(), net->fb_len.size() * 4, cudaMemcpyHostToDevice, s));
+    }
+    return 0;
+}
+
+extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, long long signal_stride,
+                               const float* const* params, float* const* bn_mean, float* const* bn_var,
+                               long long* const* bn_count, int training, unsigned long long dropout_seed,
+                               void* workspace, size_t workspace_bytes, float* logits, void* stream) {
+    FSB_REQUIRE(net && signal && params && bn_mean && bn_var && workspace && logits, "net_forward: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    FSB_TRY(fsb_device_ok());
+    FSB_TRY(bind(net, workspace, workspace_bytes, n, t, training ? 1 : 0, s));
+    const fsb_net_config& c = net->cfg;
+    const int prec = c.precision, fmt = act_fmt(prec);
+    net->recs.clear();
+    net->ev_used = 0;
+    net->dropout_seed = dropout_seed;
+    const int frames = net->frames;
+
+    for (int k = 0; k < c.num_blocks; ++k) {
+        BlockPlan& B = net->blocks[k];
+        const float* const* P = params + (size_t)k * P_PER_BLOCK;
+        float* const* RM = bn_mean + (size_t)k * B_PER_BLOCK;
+        float* const* RV = bn_var + (size_t)k * B_PER_BLOCK;
+        long long* const* CT = bn_count ? bn_count + (size_t)k * B_PER_BLOCK : nullptr;
+        auto cnt = [&](int i) { return CT ? CT[i] : nullptr; };
+
+        if (c.two_d && k == 0) {
+            RUN(CAT_FEAT, 0, fsb_feat_forward(signal, n, signal_stride, t, c.n_fft, c.hop, c.feat_mode, 1e-4f,
+                                              c.n_features, net->d_fb_vals, net->d_fb_off, net->d_fb_start,
+                                              net->d_fb_len, net->feat_tables, net->feat,
+                                              (long long)c.n_features * frames, frames, 1, s));
+            long long cnt0 = (long long)n * c.n_features * frames;
+            if (training) {
+                RUN(CAT_ELT_FWD, 0, plain_stats(net->feat, cnt0, net->partials, s));
+                RUN(CAT_ELT_FWD, 0, freq_encoding_stats(c.n_features, (long long)n * frames, net->partials, s));
+            }
+            RUN(CAT_ELT_FWD, 0, bn_finalize(net->partials, plain_stats_blocks(), cnt0, P[P_BNIN_W], P[P_BNIN_B],
+                                            RM[B_IN], RV[B_IN], cnt(B_IN), training, 2, 16, B.bn_in.scale,
+                                            B.bn_in.shift, B.bn_in.mean, B.bn_in.invstd, s));
+            RUN(CAT_CONV0, 2.0 * 2 * B.C * 9 * (double)n * c.n_features * frames,
+                conv0_forward(net->feat, n, c.n_features, frames, B.bn_in.scale, B.bn_in.shift, P[P_CONV_W],
+                              P[P_CONV_B], B.zp, B.g, s));
+        } else {
+            if (k == 0) {
+                // 1D: features land directly in the padded-flat block input (channels = STFT bins)
+                float* dst = B.x_in + geo_row(B.g_in, 0, 0, 0) * B.g_in.Cs;
+                RUN(CAT_FEAT, 0, fsb_feat_forward(signal, n, signal_stride, t, c.n_fft, c.hop, c.feat_mode, 1e-4f,
+                                                  c.n_features, net->d_fb_vals, net->d_fb_off, net->d_fb_start,
+                                                  net->d_fb_len, net->feat_tables, dst,
+                                                  (long long)B.g_in.Hp * B.g_in.Wp * B.g_in.Cs, 1, B.g_in.Cs, s));
+            }
+            FSB_TRY(bn_forward_stats(net, s, B.x_in, B.g_in, B.bn_in, P[P_BNIN_W], P[P_BNIN_B], RM[B_IN], RV[B_IN],
+                                     cnt(B_IN), training, CAT_ELT_FWD));
+            RUN(CAT_ELT_FWD, 0, bn_act_forward(B.x_in, B.g_in, B.bn_in.coef(nullptr), kNoRes, kNoDrop, B.u, fmt,
+                                               nullptr, s));
+            RUN(CAT_PACK, 0, pack_weights(prec, P[P_CONV_W], P[P_CONV_B], B.entry, B.pk_entry, s));
+            RUN(CAT_GEMM_FWD, conv_flops(B.entry, B.g_in), conv_gemm_fwd(prec, B.u, B.pk_entry, B.zf, B.entry, s));
+            RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1, s));
+        }
+        // BN_a + PReLU_a -> r0
+        FSB_TRY(bn_forward_stats(net, s, B.zp, B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A], cnt(B_A),
+                                 training, CAT_ELT_FWD));
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.zp, B.g, B.bn_a.coef(P[P_PRELUA]), kNoRes, kNoDrop, B.r0, fmt, nullptr, s));
+        // resnet block
+        RUN(CAT_PACK, 0, pack_weights(prec, P[P_C1_W], P[P_C1_B], B.c1, B.pk1, s));
+        RUN(CAT_PACK, 0, pack_weights(prec, P[P_C2_W], P[P_C2_B], B.c2, B.pk2, s));
+        RUN(CAT_PACK, 0, pack_weights(prec, P[P_C3_W], P[P_C3_B], B.c3, B.pk3, s));
+        RUN(CAT_GEMM_FWD, conv_flops(B.c1, B.g), conv_gemm_fwd(prec, B.r0, B.pk1, B.z1, B.c1, s));
+        FSB_TRY(bn_forward_stats(net, s, B.z1, B.g, B.bn1, P[P_BN1_W], P[P_BN1_B], RM[B_1], RV[B_1], cnt(B_1),
+                                 training, CAT_ELT_FWD));
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z1, B.g, B.bn1.coef(P[P_PRELU1]), kNoRes, kNoDrop, B.a1, fmt, nullptr, s));
+        RUN(CAT_GEMM_FWD, conv_flops(B.c2, B.g), conv_gemm_fwd(prec, B.a1, B.pk2, B.z2, B.c2, s));
+        FSB_TRY(bn_forward_stats(net, s, B.z2, B.g, B.bn2, P[P_BN2_W], P[P_BN2_B], RM[B_2], RV[B_2], cnt(B_2),
+                                 training, CAT_ELT_FWD));
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z2, B.g, B.bn2.coef(P[P_PRELU2]), kNoRes, kNoDrop, B.a2, fmt, nullptr, s));
+        RUN(CAT_GEMM_FWD, conv_flops(B.c3, B.g), conv_gemm_fwd(prec, B.a2, B.pk3, B.z3, B.c3, s));
+        FSB_TRY(bn_forward_stats(net, s, B.z3, B.g, B.bn3, P[P_BN3_W], P[P_BN3_B], RM[B_3], RV[B_3], cnt(B_3),
+                                 training, CAT_ELT_FWD));
+        Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z3, B.g, B.bn3.coef(P[P_PRELU3]), res, kNoDrop, nullptr, fmt, B.out, s));
+        if (B.head_off >= 0)
+            RUN(CAT_ELT_FWD, 0, gmax_forward(B.out, B.g, net->feats, net->Ds, B.head_off, B.argrow, s));
+    }
+
+    // ---- FC head (float32 CUDA-core GEMMs in every precision mode)
+    {
+        const float* const* P = params + (size_t)c.num_blocks * P_PER_BLOCK;
+        float* const* RM = bn_mean + (size_t)c.num_blocks * B_PER_BLOCK;
+        float* const* RV = bn_var + (size_t)c.num_blocks * B_PER_BLOCK;
+        long long* const* CT = bn_count ? bn_count + (size_t)c.num_blocks * B_PER_BLOCK : nullptr;
+        FSB_TRY(bn_forward_stats(net, s, net->feats, net->g_head, net->hbn0, P[H_BN0_W], P[H_BN0_B], RM[0], RV[0],
+                                 CT ? CT[0] : nullptr, training, CAT_HEAD));
+        RUN(CAT_HEAD, 0, bn_act_forward(net->feats, net->g_head, net->hbn0.coef(nullptr), kNoRes, kNoDrop, nullptr,
+                                        FMT_F32, net->h0, s));
+        RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L1_W], P[H_L1_B], net->lin1, net->pk_l1, s));
+        RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L5_W], P[H_L5_B], net->lin5, net->pk_l5, s));
+        RUN(CAT_HEAD, 0, simt_fwd(net->h0, net->pk_l1, net->z1h, net->lin1, s));
+        FSB_TRY(bn_forward_stats(net, s, net->z1h, net->g_head, net->hbn2, P[H_BN2_W], P[H_BN2_B], RM[1], RV[1],
+                                 CT ? CT[1] : nullptr, training, CAT_HEAD));
+        Dropout dr = {training ? c.dropout_p : 0.f, dropout_seed};
+        RUN(CAT_HEAD, 0, bn_act_forward(net->z1h, net->g_head, net->hbn2.coef(P[H_PRELU]), kNoRes, dr, nullptr,
+                                        FMT_F32, net->h1, s));
+        RUN(CAT_HEAD, 0, simt_fwd(net->h1, net->pk_l5, net->zl, net->lin5, s));
+        RUN(CAT_HEAD, 0, copy2d(net->zl, n, c.n_classes, net->CsCls, logits, c.n_classes, s));
+    }
+    net->fwd_done = true;
+    return 0;
+}
+
+// =================================================================================================
+static int bn_backward(fsb_net* net, cudaStream_t s, const float* dA1, const float* dA2, const float* z, const Geo& g,
+                       BnBuf& bn, const float* slope, Residual res, Dropout dr, float* dgamma, float* dbeta,
+                       float* dslope, void* dz, int fmt, float* dres, int cat) {
+    BnCoef coef = bn.coef(slope);
+    RUN(cat, 0, bn_act_bwd_reduce(dA1, dA2, z, g, coef, res, dr, net->partials, s));
+    RUN(cat, 0, bn_bwd_finalize(net->partials, ew_num_blocks(g), g.pixels, bn.C, bn.Cs, dgamma, dbeta, dslope, bn.c1,
+                                bn.c2, s));
+    if (dz) RUN(cat, 0, bn_act_bwd_apply(dA1, dA2, z, g, coef, res, dr, bn.c1, bn.c2, dz, fmt, dres, s));
+    return 0;
+}
+
+extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float* const* params, float* grads,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    FSB_REQUIRE(net && dlogits && params && grads && workspace, "net_backward: null argument");
+    if (!net->fwd_done || !net->training || net->ws != workspace) {
+        set_error("net_backward: needs a preceding training-mode forward on the same workspace");
+        return FSB_E_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const fsb_net_config& c = net->cfg;
+    const int prec = c.precision, fmt = act_fmt(prec);
+    const int n = net->N;
+    auto G = [&](int index) { return grads + net->param_offset[index]; };
+    // conv / linear biases that feed a batch-statistics BN have an analytically zero gradient
+    FSB_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->total_params * sizeof(float), s));
+
+    // ---- head
+    {
+        const int hb = c.num_blocks * P_PER_BLOCK;
+        const float* const* P = params + hb;
+        RUN(CAT_HEAD, 0, copy2d(dlogits, n, c.n_classes, c.n_classes, net->dzl, net->CsCls, s));
+        RUN(CAT_HEAD, 0, colsum(dlogits, n, c.n_classes, c.n_classes, G(hb + H_L5_B), s));
+        RUN(CAT_HEAD, 0, simt_wgrad(net->h1, net->dzl, G(hb + H_L5_W), net->wgrad_scratch, net->lin5, s));
+        RUN(CAT_HEAD, 0, simt_dgrad(net->dzl, net->pk_l5, net->dh1, net->lin5, s));
+        Dropout dr = {c.dropout_p, net->dropout_seed};
+        FSB_TRY(bn_backward(net, s, net->dh1, nullptr, net->z1h, net->g_head, net->hbn2, P[H_PRELU], kNoRes, dr,
+                            G(hb + H_BN2_W), G(hb + H_BN2_B), G(hb + H_PRELU), net->dz1h, FMT_F32, nullptr, CAT_HEAD));
+        RUN(CAT_HEAD, 0, simt_wgrad(net->h0, net->dz1h, G(hb + H_L1_W), net->wgrad_scratch, net->lin1, s));
+        RUN(CAT_HEAD, 0, simt_dgrad(net->dz1h, net->pk_l1, net->dh0, net->lin1, s));
+        FSB_TRY(bn_backward(net, s, net->dh0, nullptr, net->feats, net->g_head, net->hbn0, nullptr, kNoRes, kNoDrop,
+                            G(hb + H_BN0_W), G(hb + H_BN0_B), nullptr, net->dfeats, FMT_F32, nullptr, CAT_HEAD));
+    }
+
+    // ---- conv blocks, last to first
+    for (int k = c.num_blocks - 1; k >= 0; --k) {
+        BlockPlan& B = net->blocks[k];
+        const int pb = k * P_PER_BLOCK;
+        const float* const* P = params + pb;
+        if (k == c.num_blocks - 1) FSB_CUDA(cudaMemsetAsync(B.d_out, 0, (size_t)B.g.rows * B.g.Cs * 4, s));
+        if (B.head_off >= 0)
+            RUN(CAT_ELT_BWD, 0, gmax_backward(net->dfeats, net->Ds, B.head_off, B.argrow, B.g, B.d_out, s));
+        // out = prelu3(bn3(z3) + r0)
+        Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
+        FSB_TRY(bn_backward(net, s, B.d_out, nullptr, B.z3, B.g, B.bn3, P[P_PRELU3], res, kNoDrop, G(pb + P_BN3_W),
+                            G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, CAT_ELT_BWD));
+        RUN(CAT_GEMM_WGRAD, conv_flops(B.c3, B.g),
+            conv_gemm_wgrad(prec, B.a2, B.dz3, G(pb + P_C3_W), net->wgrad_scratch, B.c3, s));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c3, B.g), conv_gemm_dgrad(prec, B.dz3, B.pk3, B.da2, B.c3, s));
+        FSB_TRY(bn_backward(net, s, B.da2, nullptr, B.z2, B.g, B.bn2, P[P_PRELU2], kNoRes, kNoDrop, G(pb + P_BN2_W),
+                            G(pb + P_BN2_B), G(pb + P_PRELU2), B.dz2, fmt, nullptr, CAT_ELT_BWD));
+        RUN(CAT_GEMM_WGRAD, conv_flops(B.c2, B.g),
+            conv_gemm_wgrad(prec, B.a1, B.dz2, G(pb + P_C2_W), net->wgrad_scratch, B.c2, s));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c2, B.g), conv_gemm_dgrad(prec, B.dz2, B.pk2, B.da1, B.c2, s));
+        FSB_TRY(bn_backward(net, s, B.da1, nullptr, B.z1, B.g, B.bn1, P[P_PRELU1], kNoRes, kNoDrop, G(pb + P_BN1_W),
+                            G(pb + P_BN1_B), G(pb + P_PRELU1), B.dz1, fmt, nullptr, CAT_ELT_BWD));
+        RUN(CAT_GEMM_WGRAD, conv_flops(B.c1, B.g),
+            conv_gemm_wgrad(prec, B.r0, B.dz1, G(pb + P_C1_W), net->wgrad_scratch, B.c1, s));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c1, B.g), conv_gemm_dgrad(prec, B.dz1, B.pk1, B.dr0a, B.c1, s));
+        // r0 = prelu_a(bn_a(zp)) ; gradient = conv1 dgrad + residual branch
+        FSB_TRY(bn_backward(net, s, B.dr0a, B.dr0b, B.zp, B.g, B.bn_a, P[P_PRELUA], kNoRes, kNoDrop, G(pb + P_BNA_W),
+                            G(pb + P_BNA_B), G(pb + P_PRELUA), B.dzp, FMT_F32, nullptr, CAT_ELT_BWD));
+        if (c.two_d && k == 0) {
+            RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
+                conv0_backward(net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift, B.bn_in.mean,
+                               B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, B.g, G(pb + P_CONV_W),
+                               G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->wgrad_scratch, s));
+        } else {
+            RUN(CAT_ELT_BWD, 0, maxpool_backward(B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt, s));
+            RUN(CAT_GEMM_WGRAD, conv_flops(B.entry, B.g_in),
+                conv_gemm_wgrad(prec, B.u, B.dzf, G(pb + P_CONV_W), net->wgrad_scratch, B.entry, s));
+            RUN(CAT_GEMM_DGRAD, conv_flops(B.entry, B.g_in), conv_gemm_dgrad(prec, B.dzf, B.pk_entry, B.du, B.entry, s));
+            float* dprev = k > 0 ? net->blocks[k - 1].d_out : nullptr;
+            FSB_TRY(bn_backward(net, s, B.du, nullptr, B.x_in, B.g_in, B.bn_in, nullptr, kNoRes, kNoDrop,
+                                G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, FMT_F32, nullptr, CAT_ELT_BWD));
+        }
+    }
+    return 0;
+}
+
+// =================================================================================================
+extern "C" int fsb_net_read_activation(fsb_net* net, int which, float* dst, long long cap, long long* numel,
+                                       void* workspace, void* stream) {
+    FSB_REQUIRE(net && dst && numel, "read_activation: null argument");
+    if (!net->fwd_done || net->ws != workspace) {
+        set_error("read_activation: no forward on this workspace");
+        return FSB_E_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const fsb_net_config& c = net->cfg;
+    if (which == 0) {
+        long long cnt = (long long)net->N * c.n_features * net->frames;
+        FSB_REQUIRE(cap >= cnt, "read_activation: destination too small");
+        *numel = cnt;
+        if (c.two_d) {
+            FSB_CUDA(cudaMemcpyAsync(dst, net->feat, cnt * 4, cudaMemcpyDeviceToDevice, s));
+            return 0;
+        }
+        return pf_to_nchw(net->blocks[0].x_in, net->blocks[0].g_in, dst, s);
+    }
+    if (which == 100) {
+        long long cnt = (long long)net->N * net->D;
+        FSB_REQUIRE(cap >= cnt, "read_activation: destination too small");
+        *numel = cnt;
+        return copy2d(net->feats, net->N, net->D, net->Ds, dst, net->D, s);
+    }
+    int k = which - 1;
+    FSB_REQUIRE(k >= 0 && k < c.num_blocks, "read_activation: unknown tensor %d", which);
+    const BlockPlan& B = net->blocks[k];
+    long long cnt = B.g.pixels * B.g.C;
+    FSB_REQUIRE(cap >= cnt, "read_activation: destination too small");
+    *numel = cnt;
+    return pf_to_nchw(B.out, B.g, dst, s);
+}
+
+extern "C" int fsb_net_set_profiling(fsb_net* net, int on) {
+    net->profiling = on != 0;
+    return 0;
+}
+
+extern "C" int fsb_net_get_timings(fsb_net* net, int cap, const char** names, float* ms, double* flops, int* count) {
+    FSB_REQUIRE(cap >= CAT_COUNT, "get_timings: capacity must be >= %d", (int)CAT_COUNT);
+    for (int i = 0; i < CAT_COUNT; ++i) { names[i] = kCatNames[i]; ms[i] = 0.f; flops[i] = 0.0; }
+    for (const fsb_net::Rec& r : net->recs) {
+        float t = 0.f;
+        FSB_CUDA(cudaEventSynchronize(net->ev_pool[r.e1]));
+        FSB_CUDA(cudaEventElapsedTime(&t, net->ev_pool[r.e0], net->ev_pool[r.e1]));
+        ms[r.cat] += t;
+        flops[r.cat] += r.flops;
+    }
+    *count = CAT_COUNT;
+    return 0;
+}
+
+// =================================================================================================
+// unit-level conv entry points (NCHW in / out) over the same PF pipeline
+extern "C" size_t fsb_conv_workspace_bytes(int n, int cin, int cout, int h, int w, int kh, int kw) {
+    Geo gi = make_geo(n, h, w, cin, kh == 3 ? 1 : 0, kw == 3 ? 1 : 0);
+    Geo go = make_geo(n, h, w, cout, gi.padH, gi.padW);
+    ConvGeom c = make_conv_geom(gi, cin, cout, kh, kw);
+    size_t pk = std::max(packed_weight_bytes(0, c), packed_weight_bytes(1, c));
+    size_t wg = std::max(wgrad_scratch_bytes(0, c), wgrad_scratch_bytes(1, c));
+    return 2 * plane_bytes(gi) + 2 * plane_bytes(go) + pk + wg + 4096;
+}
+
+static int conv_unit_setup(int n, int cin, int cout, int h, int w, int kh, int kw, Geo& gi, Geo& go, ConvGeom& c) {
+    FSB_REQUIRE((kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv: kernel must be 1 or 3 per dimension");
+    gi = make_geo(n, h, w, cin, kh == 3 ? 1 : 0, kw == 3 ? 1 : 0);
+    go = make_geo(n, h, w, cout, gi.padH, gi.padW);
+    c = make_conv_geom(gi, cin, cout, kh, kw);
+    return 0;
+}
+
+extern "C" int fsb_conv_forward(const float* x, const float* w, const float* b, int n, int cin, int cout, int h,
+                                int wd, int kh, int kw, int precision, float* y, void* workspace, size_t ws_bytes,
+                                void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    Geo gi, go;
+    ConvGeom c;
+    FSB_TRY(conv_unit_setup(n, cin, cout, h, wd, kh, kw, gi, go, c));
+    FSB_REQUIRE(ws_bytes >= fsb_conv_workspace_bytes(n, cin, cout, h, wd, kh, kw), "conv: workspace too small");
+    FSB_TRY(fsb_device_ok());
+    Bump bump{(char*)workspace, 0};
+    void* A = bump.take_bytes(plane_bytes(gi));
+    float* Z = (float*)bump.take_bytes(plane_bytes(go));
+    void* pk = bump.take_bytes(packed_weight_bytes(precision, c));
+    int fmt = act_fmt(precision);
+    FSB_CUDA(cudaMemsetAsync(A, 0, plane_bytes(gi), s));
+    FSB_TRY(nchw_to_pf(x, gi, A, fmt, s));
+    FSB_TRY(pack_weights(precision, w, b, c, pk, s));
+    FSB_TRY(conv_gemm_fwd(precision, A, pk, Z, c, s));
+    return pf_to_nchw(Z, go, y, s);
+}
+
+extern "C" int fsb_conv_backward(const float* x, const float* w, const float* dy, int n, int cin, int cout, int h,
+                                 int wd, int kh, int kw, int precision, float* dx, float* dw, float* db,
+                                 void* workspace, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    Geo gi, go;
+    ConvGeom c;
+    FSB_TRY(conv_unit_setup(n, cin, cout, h, wd, kh, kw, gi, go, c));
+    FSB_REQUIRE(ws_bytes >= fsb_conv_workspace_bytes(n, cin, cout, h, wd, kh, kw), "conv: workspace too small");
+    FSB_TRY(fsb_device_ok());
+    Bump bump{(char*)workspace, 0};
+    void* A = bump.take_bytes(plane_bytes(gi));
+    void* dZ = bump.take_bytes(plane_bytes(go));
+    float* dA = (float*)bump.take_bytes(plane_bytes(gi));
+    void* pk = bump.take_bytes(packed_weight_bytes(precision, c));
+    void* scratch = bump.take_bytes(wgrad_scratch_bytes(precision, c));
+    int fmt = act_fmt(precision);
+    FSB_CUDA(cudaMemsetAsync(A, 0, plane_bytes(gi), s));
+    FSB_CUDA(cudaMemsetAsync(dZ, 0, plane_bytes(go), s));
+    FSB_TRY(nchw_to_pf(x, gi, A, fmt, s));
+    FSB_TRY(nchw_to_pf(dy, go, dZ, fmt, s));
+    FSB_TRY(pack_weights(precision, w, nullptr, c, pk, s));
+    FSB_TRY(conv_gemm_dgrad(precision, dZ, pk, dA, c, s));
+    FSB_TRY(pf_to_nchw(dA, gi, dx, s));
+    FSB_TRY(conv_gemm_wgrad(precision, A, dZ, dw, scratch, c, s));
+    // bias gradient: sum of dy over (n, h, w) -- dy is NCHW here
+    if (db) {
+        float* dyf = (float*)dZ;
+        if (fmt != FMT_F32) {
+            FSB_CUDA(cudaMemsetAsync(dZ, 0, plane_bytes(go), s));
+            FSB_TRY(nchw_to_pf(dy, go, dZ, FMT_F32, s));
+        }
+        FSB_TRY(colsum(dyf, go.rows, cout, go.Cs, db, s));
+    }
+    return 0;
+}

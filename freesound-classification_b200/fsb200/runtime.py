@@ -1,0 +1,355 @@
+"""Host-side runtime over libfsb200: device-buffer ownership (torch tensors), stream hand-off and
+autograd wiring.  PyTorch is plumbing here (memory, streams, autograd tape); all arithmetic is in
+the CUDA library.  Nothing in this module computes on the CPU and nothing falls back."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NetConfig, check, lib
+
+PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+
+def default_precision():
+    """GEMM back end: `FSB200_PRECISION` = fp32 (CUDA cores) | bf16x3 (tcgen05, fp32-grade) | bf16."""
+    return os.environ.get("FSB200_PRECISION", "fp32")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def require_cuda(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError("%s must be a CUDA tensor: this package has no CPU path" % name)
+
+
+# ----------------------------------------------------------------------------------------------
+# filterbank: dense (n_mel, n_bins) -> banded (vals, off, start, len)
+# ----------------------------------------------------------------------------------------------
+def band_filterbank(fb):
+    fb = np.asarray(fb, dtype=np.float32)
+    vals, off, start, length = [], [], [], []
+    for row in fb:
+        nz = np.flatnonzero(row)
+        if nz.size == 0:
+            s, e = 0, 1
+        else:
+            s, e = int(nz[0]), int(nz[-1]) + 1
+        off.append(len(vals))
+        start.append(s)
+        length.append(e - s)
+        vals.extend(row[s:e].tolist())
+    return (np.asarray(vals, np.float32), np.asarray(off, np.int32), np.asarray(start, np.int32),
+            np.asarray(length, np.int32))
+
+
+class FeatureExtractor:
+    """Stand-alone K-feat launcher (used by `ops.utils.compute_torch_stft` and tests)."""
+
+    _tables = {}
+
+    def __init__(self, n_fft, hop, filterbank=None, device="cuda"):
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        self.device = torch.device(device)
+        key = (self.n_fft, str(self.device))
+        if key not in FeatureExtractor._tables:
+            nbytes = lib().fsb_feat_table_bytes(self.n_fft)
+            tab = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                check(lib().fsb_feat_init_tables(self.n_fft, _ptr(tab), _stream()), "feat_init_tables")
+            FeatureExtractor._tables[key] = tab
+        self.tables = FeatureExtractor._tables[key]
+        self.fb = None
+        if filterbank is not None:
+            vals, off, start, length = band_filterbank(filterbank)
+            self.n_mel = len(off)
+            self.fb = tuple(torch.from_numpy(a).to(self.device) for a in (vals, off, start, length))
+
+    def __call__(self, audio, mode):
+        """audio (N, T) float32 CUDA -> (N, F, frames); mode 0 |STFT|, 1 log|STFT|, 2 log-mel."""
+        require_cuda(audio, "audio")
+        if audio.dim() != 2:
+            raise ValueError("audio must be (N, T)")
+        audio = audio.float()
+        if audio.stride(1) != 1:
+            audio = audio.contiguous()
+        n, t = audio.shape
+        frames = 1 + t // self.hop
+        f_out = self.n_mel if mode == 2 else self.n_fft // 2 + 1
+        if mode == 2 and self.fb is None:
+            raise ValueError("mel mode needs a filterbank")
+        out = torch.empty((n, f_out, frames), dtype=torch.float32, device=audio.device)
+        fb = self.fb if mode == 2 else (None, None, None, None)
+        with torch.cuda.device(audio.device):
+            check(lib().fsb_feat_forward(_ptr(audio), n, audio.stride(0), t, self.n_fft, self.hop, mode, 1e-4,
+                                         self.n_mel if mode == 2 else 0, _ptr(fb[0]), _ptr(fb[1]), _ptr(fb[2]),
+                                         _ptr(fb[3]), _ptr(self.tables), _ptr(out), f_out * frames, frames, 1,
+                                         _stream()), "feat_forward")
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# LSEP
+# ----------------------------------------------------------------------------------------------
+class _LsepFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, targets):
+        require_cuda(scores, "input")
+        s = scores.contiguous().float()
+        t = targets.contiguous().float()
+        n, c = s.shape
+        loss = torch.empty(n, dtype=torch.float32, device=s.device)
+        with torch.cuda.device(s.device):
+            check(lib().fsb_lsep_forward(_ptr(s), _ptr(t), n, c, _ptr(loss), _stream()), "lsep_forward")
+        ctx.save_for_backward(s, t)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        s, t = ctx.saved_tensors
+        n, c = s.shape
+        dloss = dloss.contiguous().float()
+        ds = torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            check(lib().fsb_lsep_backward(_ptr(s), _ptr(t), _ptr(dloss), n, c, _ptr(ds), _stream()), "lsep_backward")
+        return ds, None
+
+
+def lsep_per_sample(scores, targets):
+    return _LsepFunction.apply(scores, targets)
+
+
+# ----------------------------------------------------------------------------------------------
+# network plan
+# ----------------------------------------------------------------------------------------------
+BLOCK_PARAM_SUFFIXES = (
+    "0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias", "4.weight",
+    "5.conv1.weight", "5.conv1.bias", "5.bn1.weight", "5.bn1.bias",
+    "5.conv2.weight", "5.conv2.bias", "5.bn2.weight", "5.bn2.bias",
+    "5.conv3.weight", "5.conv3.bias", "5.bn3.weight", "5.bn3.bias",
+    "5.prelu1.weight", "5.prelu2.weight", "5.prelu3.weight")
+HEAD_PARAM_NAMES = ("0.weight", "0.bias", "1.weight", "1.bias", "2.weight", "2.bias", "3.weight",
+                    "5.weight", "5.bias")
+BLOCK_BN_PREFIXES = ("0", "3", "5.bn1", "5.bn2", "5.bn3")
+HEAD_BN_PREFIXES = ("0", "2")
+
+
+def canonical_param_names(num_blocks):
+    names = []
+    for k in range(num_blocks):
+        names += ["conv_modules.%d.%s" % (k, s) for s in BLOCK_PARAM_SUFFIXES]
+    names += ["output_transform.%s" % s for s in HEAD_PARAM_NAMES]
+    return names
+
+
+def canonical_bn_prefixes(num_blocks):
+    names = []
+    for k in range(num_blocks):
+        names += ["conv_modules.%d.%s" % (k, s) for s in BLOCK_BN_PREFIXES]
+    names += ["output_transform.%s" % s for s in HEAD_BN_PREFIXES]
+    return names
+
+
+class NetPlan:
+    """Owns an `fsb_net` handle plus its workspace tensor."""
+
+    def __init__(self, two_d, features, depths, start_deep_supervision_on, n_classes, dropout_p, filterbank=None,
+                 precision=None, device="cuda"):
+        parts = features.split("_")
+        if parts[0] not in ("mel", "stft"):
+            raise ValueError("unsupported feature descriptor %r (mel_* / stft_* only)" % features)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("freesound-classification_b200 runs on CUDA (sm_100a) only; got device %r" % (device,))
+        self.precision = precision or default_precision()
+        cfg = NetConfig()
+        cfg.two_d = 1 if two_d else 0
+        cfg.feat_mode = 2 if parts[0] == "mel" else 1
+        cfg.n_fft, cfg.hop = int(parts[1]), int(parts[2])
+        cfg.n_features = int(parts[3]) if parts[0] == "mel" else cfg.n_fft // 2 + 1
+        cfg.num_blocks = len(depths)
+        for i, d in enumerate(depths):
+            cfg.depth[i] = int(d)
+        cfg.start_deep_supervision_on = int(start_deep_supervision_on)
+        cfg.n_classes = int(n_classes)
+        cfg.dropout_p = float(dropout_p)
+        cfg.precision = PRECISIONS[self.precision]
+        self.cfg = cfg
+        handle = ctypes.c_void_p()
+        if cfg.feat_mode == 2:
+            vals, off, start, length = band_filterbank(filterbank)
+            self._fb_keep = (vals, off, start, length)
+            check(lib().fsb_net_create(ctypes.byref(cfg), vals.ctypes.data, off.ctypes.data, start.ctypes.data,
+                                       length.ctypes.data, len(vals), ctypes.byref(handle)), "net_create")
+        else:
+            check(lib().fsb_net_create(ctypes.byref(cfg), None, None, None, None, 0, ctypes.byref(handle)),
+                  "net_create")
+        self.handle = handle
+        self.num_params = lib().fsb_net_num_params(handle)
+        self.num_bn = lib().fsb_net_num_bn(handle)
+        self.param_numel = [lib().fsb_net_param_numel(handle, i) for i in range(self.num_params)]
+        self.total_params = sum(self.param_numel)
+        self.workspace = None
+        self._ws_key = None
+        self._param_ptrs = (ctypes.c_void_p * self.num_params)()
+        self._mean_ptrs = (ctypes.c_void_p * self.num_bn)()
+        self._var_ptrs = (ctypes.c_void_p * self.num_bn)()
+        self._cnt_ptrs = (ctypes.c_void_p * self.num_bn)()
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().fsb_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _ensure_workspace(self, n, t, training):
+        key = (n, t, bool(training))
+        if key != self._ws_key:
+            need = lib().fsb_net_workspace_bytes(self.handle, n, t, 1 if training else 0)
+            if need == 0:
+                check(-1, "net_workspace_bytes")
+            if self.workspace is None or self.workspace.numel() < need:
+                self.workspace = None          # release before growing
+                self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        return self.workspace
+
+    def set_pointers(self, params, bn_means, bn_vars, bn_counts):
+        for i, p in enumerate(params):
+            if p.numel() != self.param_numel[i] or not p.is_contiguous() or p.dtype != torch.float32:
+                raise RuntimeError("parameter %d: expected %d contiguous float32 elements" % (i, self.param_numel[i]))
+            self._param_ptrs[i] = p.data_ptr()
+        for i in range(self.num_bn):
+            self._mean_ptrs[i] = bn_means[i].data_ptr()
+            self._var_ptrs[i] = bn_vars[i].data_ptr()
+            self._cnt_ptrs[i] = bn_counts[i].data_ptr()
+
+    def forward(self, signal, training, dropout_seed=0):
+        """signal (N, T) float32 CUDA; pointers must have been set.  Returns logits (N, C)."""
+        require_cuda(signal, "signal")
+        if signal.stride(1) != 1 or signal.dtype != torch.float32:
+            signal = signal.float().contiguous()
+        n, t = signal.shape
+        ws = self._ensure_workspace(n, t, training)
+        logits = torch.empty((n, self.cfg.n_classes), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().fsb_net_forward(self.handle, _ptr(signal), n, t, signal.stride(0), self._param_ptrs,
+                                        self._mean_ptrs, self._var_ptrs, self._cnt_ptrs, 1 if training else 0,
+                                        int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(ws), ws.numel(), _ptr(logits),
+                                        _stream()), "net_forward")
+        return logits
+
+    def backward(self, dlogits):
+        dlogits = dlogits.contiguous().float()
+        grads = torch.empty(self.total_params, dtype=torch.float32, device=self.device)
+        ws = self.workspace
+        with torch.cuda.device(self.device):
+            check(lib().fsb_net_backward(self.handle, _ptr(dlogits), self._param_ptrs, _ptr(grads), _ptr(ws),
+                                         ws.numel(), _stream()), "net_backward")
+        return grads
+
+    def read_activation(self, which, shape):
+        dst = torch.empty(shape, dtype=torch.float32, device=self.device)
+        numel = ctypes.c_longlong(0)
+        with torch.cuda.device(self.device):
+            check(lib().fsb_net_read_activation(self.handle, which, _ptr(dst), dst.numel(), ctypes.byref(numel),
+                                                _ptr(self.workspace), _stream()), "net_read_activation")
+        if numel.value != dst.numel():
+            raise RuntimeError("activation %d has %d elements, expected shape %r" % (which, numel.value, shape))
+        return dst
+
+    def set_profiling(self, on):
+        lib().fsb_net_set_profiling(self.handle, 1 if on else 0)
+
+    def timings(self):
+        cap = 16
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_float * cap)()
+        flops = (ctypes.c_double * cap)()
+        count = ctypes.c_int(0)
+        check(lib().fsb_net_get_timings(self.handle, cap, names, ms, flops, ctypes.byref(count)), "net_get_timings")
+        return {names[i].decode(): (ms[i], flops[i]) for i in range(count.value)}
+
+
+class _NetFunction(torch.autograd.Function):
+    """logits = net(signal; params): the whole forward/backward is two library calls."""
+
+    @staticmethod
+    def forward(ctx, plan, signal, dropout_seed, *params):
+        ctx.plan = plan
+        ctx.shapes = [p.shape for p in params]
+        return plan.forward(signal, True, dropout_seed)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        plan = ctx.plan
+        flat = plan.backward(dlogits)
+        plan.last_flat_grad = flat
+        grads, off = [], 0
+        for shape, n in zip(ctx.shapes, plan.param_numel):
+            grads.append(flat[off:off + n].view(shape))
+            off += n
+        return (None, None, None) + tuple(grads)
+
+
+def net_apply(plan, signal, dropout_seed, params):
+    return _NetFunction.apply(plan, signal, dropout_seed, *params)
+
+
+# ----------------------------------------------------------------------------------------------
+# unit-level conv (tests)
+# ----------------------------------------------------------------------------------------------
+def conv_forward(x, w, b, precision="fp32"):
+    require_cuda(x, "x")
+    n, cin, h, wd = x.shape
+    cout, _, kh, kw = w.shape
+    nbytes = lib().fsb_conv_workspace_bytes(n, cin, cout, h, wd, kh, kw)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().fsb_conv_forward(_ptr(x.contiguous()), _ptr(w.contiguous()), _ptr(b), n, cin, cout, h, wd, kh, kw,
+                                     PRECISIONS[precision], _ptr(y), _ptr(ws), nbytes, _stream()), "conv_forward")
+    return y
+
+
+def conv_backward(x, w, dy, precision="fp32"):
+    n, cin, h, wd = x.shape
+    cout, _, kh, kw = w.shape
+    nbytes = lib().fsb_conv_workspace_bytes(n, cin, cout, h, wd, kh, kw)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    dx = torch.empty_like(x)
+    dw = torch.empty_like(w)
+    db = torch.empty(cout, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().fsb_conv_backward(_ptr(x.contiguous()), _ptr(w.contiguous()), _ptr(dy.contiguous()), n, cin, cout,
+                                      h, wd, kh, kw, PRECISIONS[precision], _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
+                                      nbytes, _stream()), "conv_backward")
+    return dx, dw, db
+
+
+def mixup_equal(pcm, labels, partner):
+    """On-device MixUp (equal-length branch): pcm (N, T), labels (N, C), partner (N) int32 (-1 = keep)."""
+    require_cuda(pcm, "pcm")
+    pcm = pcm.contiguous().float()
+    labels = labels.contiguous().float()
+    partner = partner.to(device=pcm.device, dtype=torch.int32).contiguous()
+    out = torch.empty_like(pcm)
+    lout = torch.empty_like(labels)
+    with torch.cuda.device(pcm.device):
+        check(lib().fsb_mixup_equal(_ptr(pcm), _ptr(labels), _ptr(partner), pcm.shape[0], pcm.shape[1],
+                                    labels.shape[1], _ptr(out), _ptr(lout), _stream()), "mixup_equal")
+    return out, lout
+
+
+def launch_count(reset=False):
+    return lib().fsb_launch_count(1 if reset else 0)
