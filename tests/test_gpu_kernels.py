@@ -107,8 +107,10 @@ def test_lsep_general_targets_and_overflow_like_reference():
     big[0, 0], big[0, 1] = -100.0, 100.0
     tb = torch.zeros(1, 80)
     tb[0, 0] = 1.0
-    assert torch.isinf(lsep_loss(big.cuda(), tb.cuda(), average=False)).all()   # no max-shift, like the reference
-    assert torch.isinf(restate.lsep_loss(big, tb, average=False)).all()
+    # no max-shift, like the reference: exp(200) overflows.  The reference's masked product turns the
+    # overflow into inf * 0 = nan for the masked pairs; the factorised kernel reports +inf (never finite).
+    assert torch.isinf(lsep_loss(big.cuda(), tb.cuda(), average=False)).all()
+    assert not torch.isfinite(restate.lsep_loss(big, tb, average=False)).any()
 
 
 # ------------------------------------------------------------------------------------------ Adam
