@@ -76,12 +76,13 @@ __host__ __device__ inline long long geo_row(const Geo& g, int n, int y, int x) 
     return ((long long)n * g.Hp + (y + g.padH)) * g.Wp + (x + g.padW);
 }
 
-// interior pixel index q in [0, N*H*W) -> padded row
+// interior pixel index q in [0, N*H*W) -> padded row (32-bit divisions: N*H*W < 2^32 is checked on the host)
 __device__ __forceinline__ long long geo_q_to_row(const Geo& g, long long q) {
-    int x = (int)(q % g.W);
-    long long t = q / g.W;
-    int y = (int)(t % g.H);
-    int n = (int)(t / g.H);
+    const unsigned uq = (unsigned)q;
+    const unsigned t = uq / (unsigned)g.W;
+    const unsigned x = uq - t * (unsigned)g.W;
+    const unsigned n = t / (unsigned)g.H;
+    const unsigned y = t - n * (unsigned)g.H;
     return ((long long)n * g.Hp + (y + g.padH)) * g.Wp + (x + g.padW);
 }
 

@@ -179,12 +179,45 @@ int pf_stats(const float* x, const Geo& g, double* partials, cudaStream_t s) {
     return 0;
 }
 
-__global__ void bn_finalize_kernel(const double* partials, int nblk, long long count, const float* gamma,
-                                   const float* beta, float* run_mean, float* run_var, long long* bn_count,
-                                   int training, int C, int Cs, float* scale, float* shift, float* mean,
-                                   float* invstd) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cs) return;
+// Fixed-order parallel reduction of per-block partial sums: 32 channels x 8 slices per CTA; every slice
+// walks the blocks b = slice, slice + 8, ... and the 8 slice totals are added in slice order, so the
+// result does not depend on scheduling (deterministic).
+template <int K>
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int nblk, int Cs, int c,
+                                                double (&out)[K]) {
+    __shared__ double red[K][8][32];
+    const int slice = threadIdx.x >> 5, cl = threadIdx.x & 31;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    if (c < Cs) {
+#pragma unroll 4
+        for (int b = slice; b < nblk; b += 8) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += partials[((long long)b * K + k) * Cs + c];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[k][slice][cl] = acc[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += red[k][j][cl];
+        out[k] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* partials, int nblk, long long count, const float* gamma,
+                   const float* beta, float* run_mean, float* run_var, long long* bn_count,
+                   int training, int C, int Cs, float* scale, float* shift, float* mean,
+                   float* invstd) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double tot[2] = {0.0, 0.0};
+    if (training) reduce_partials<2>(partials, nblk, Cs, c, tot);
+    if (threadIdx.x >= 32 || c >= Cs) return;
     if (c >= C) {
         scale[c] = 0.f; shift[c] = 0.f;
         if (mean) mean[c] = 0.f;
@@ -194,13 +227,8 @@ __global__ void bn_finalize_kernel(const double* partials, int nblk, long long c
     const float eps = 1e-5f, momentum = 0.1f;
     float m, istd;
     if (training) {
-        double s = 0.0, ss = 0.0;
-        for (int b = 0; b < nblk; ++b) {
-            s += partials[((long long)b * 2 + 0) * Cs + c];
-            ss += partials[((long long)b * 2 + 1) * Cs + c];
-        }
-        double mu = s / (double)count;
-        double var = ss / (double)count - mu * mu;
+        double mu = tot[0] / (double)count;
+        double var = tot[1] / (double)count - mu * mu;
         if (var < 0.0) var = 0.0;
         m = (float)mu;
         istd = (float)(1.0 / sqrt(var + (double)eps));
@@ -224,9 +252,9 @@ __global__ void bn_finalize_kernel(const double* partials, int nblk, long long c
 int bn_finalize(const double* partials, int nblk, long long count, const float* gamma, const float* beta,
                 float* run_mean, float* run_var, long long* bn_count, int training, int C, int Cs,
                 float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
-    bn_finalize_kernel<<<(Cs + 127) / 128, 128, 0, s>>>(partials, nblk, count, gamma, beta, run_mean,
-                                                       run_var, bn_count, training, C, Cs, scale, shift,
-                                                       mean, invstd);
+    bn_finalize_kernel<<<(Cs + 31) / 32, 256, 0, s>>>(partials, nblk, count, gamma, beta, run_mean,
+                                                     run_var, bn_count, training, C, Cs, scale, shift,
+                                                     mean, invstd);
     FSB_LAUNCHED();
     return 0;
 }
@@ -331,10 +359,11 @@ maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int p
     EW_PROLOGUE
     if (!cok) return;
     EW_PIXEL_LOOP {
-        int x = (int)(q % g.W);
-        long long t = q / g.W;
-        int y = (int)(t % g.H);
-        int n = (int)(t / g.H);
+        const unsigned uq = (unsigned)q;
+        const unsigned tq = uq / (unsigned)g.W;
+        const int x = (int)(uq - tq * (unsigned)g.W);
+        const int n = (int)(tq / (unsigned)g.H);
+        const int y = (int)(tq - (unsigned)n * (unsigned)g.H);
         long long r00 = geo_row(gf, n, y * pool_h, 2 * x);
         float4 m = max4(ld4(zf + r00 * gf.Cs + c0), ld4(zf + (r00 + 1) * gf.Cs + c0));
         if (pool_h == 2) {
@@ -360,10 +389,11 @@ maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restric
     if (!cok) return;
     const long long plane = g.rows * g.Cs;
     EW_PIXEL_LOOP {
-        int x = (int)(q % g.W);
-        long long t = q / g.W;
-        int y = (int)(t % g.H);
-        int n = (int)(t / g.H);
+        const unsigned uq = (unsigned)q;
+        const unsigned tq = uq / (unsigned)g.W;
+        const int x = (int)(uq - tq * (unsigned)g.W);
+        const int n = (int)(tq / (unsigned)g.H);
+        const int y = (int)(tq - (unsigned)n * (unsigned)g.H);
         long long row = geo_row(g, n, y, x);
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         int py = y / pool_h, px = x / 2;
@@ -556,28 +586,25 @@ int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const 
     return 0;
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs,
-                                       float* dgamma, float* dbeta, float* dslope, float* c1, float* c2) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cs) return;
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs,
+                       float* dgamma, float* dbeta, float* dslope, float* c1, float* c2) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double tot[3];
+    reduce_partials<3>(partials, nblk, Cs, c, tot);
+    if (threadIdx.x >= 32 || c >= Cs) return;
     if (c >= C) { c1[c] = 0.f; c2[c] = 0.f; return; }
-    double s0 = 0, s1 = 0, s2 = 0;
-    for (int b = 0; b < nblk; ++b) {
-        s0 += partials[((long long)b * 3 + 0) * Cs + c];
-        s1 += partials[((long long)b * 3 + 1) * Cs + c];
-        s2 += partials[((long long)b * 3 + 2) * Cs + c];
-    }
-    if (dbeta) dbeta[c] = (float)s0;
-    if (dgamma) dgamma[c] = (float)s1;
-    if (dslope) dslope[c] = (float)s2;
-    c1[c] = (float)(s0 / (double)count);
-    c2[c] = (float)(s1 / (double)count);
+    if (dbeta) dbeta[c] = (float)tot[0];
+    if (dgamma) dgamma[c] = (float)tot[1];
+    if (dslope) dslope[c] = (float)tot[2];
+    c1[c] = (float)(tot[0] / (double)count);
+    c2[c] = (float)(tot[1] / (double)count);
 }
 
 int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, float* dgamma, float* dbeta,
                     float* dslope, float* c1, float* c2, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<(Cs + 127) / 128, 128, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
-                                                           c1, c2);
+    bn_bwd_finalize_kernel<<<(Cs + 31) / 32, 256, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
+                                                         c1, c2);
     FSB_LAUNCHED();
     return 0;
 }

@@ -1,25 +1,761 @@
-// tcgen05 / TMEM / TMA back end of the row-shifted GEMM (precision 1 and 2).
+// tcgen05 / TMEM / TMA back end of the row-shifted GEMM (precision 1 = bf16x3 split, 2 = single bf16).
+//
+// Every convolution of the network is a sum of row-shifted GEMMs over padded-flat NHWC tensors
+// (gemm.cuh).  Activations arrive as two bf16 planes (hi, lo with x ~= hi + lo, common.cuh); weights are
+// packed once per step into K-major bf16 hi/lo tiles.  Products are formed on the 5th-generation tensor
+// cores as   hi*hi + hi*lo + lo*hi   with float32 accumulation in TMEM (each product keeps ~2^-16
+// relative error), or hi*hi only in precision 2.
+//
+//   conv_tc_kernel  (forward and dgrad)   D[r, n] = sum_t sum_k A[r + off_t, k] * W_t[n, k]
+//       persistent, warp specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+//       warps 2..5 = epilogue (TMEM -> registers -> global).  Two smem rings: an A ring whose stage is
+//       a (128 + 8)-row x 64-channel SWIZZLE_128B box shared by the three dx taps of one dy (the tap
+//       shift is a 128-byte start-address offset of the UMMA descriptor), and a W ring with one
+//       (BN x 64) tile per tap.  Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i
+//       overlap the main loop of tile i + 1.
+//   wgrad_tc_kernel                       dW_t[co, ci] = sum_r dZ[r, co] * A[r + off_t, ci]
+//       both operands MN-major (channels contiguous, the reduction runs over pixel rows); one CTA owns a
+//       128(co) x 128(ci) tile for the three dx taps of one dy (3 x 128 TMEM columns) over a slice of
+//       the rows; partial sums go to scratch and are reduced in a fixed order (deterministic).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace fsb {
 
-size_t tc_packed_weight_bytes(const ConvGeom& c) { return simt_packed_weight_bytes(c); }
-int tc_pack_weights(const float*, const float*, const ConvGeom&, void*, cudaStream_t) {
-    set_error("tcgen05 back end not built yet");
-    return FSB_E_INVALID;
+int wgrad_finalize(const float* P, int splits, const ConvGeom& c, float* dw, cudaStream_t s);
+
+namespace {
+
+constexpr int BM = 128;            // UMMA M (cta_group::1)
+constexpr int BK = 64;             // channels per smem row: 64 bf16 = 128 bytes = one swizzle span
+constexpr int A_HALO = 8;          // extra rows of the A box (row shifts 0..2 used)
+constexpr int TC_THREADS = 192;    // 6 warps
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int WG_R = 64;           // wgrad: pixel rows per pipeline stage
+constexpr int WG_BN = 128;         // wgrad: input channels per tile
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-int tc_fwd(int, const void*, const void*, float*, const ConvGeom&, cudaStream_t) {
-    set_error("tcgen05 back end not built yet");
-    return FSB_E_INVALID;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-int tc_dgrad(int, const void*, const void*, float*, const ConvGeom&, cudaStream_t) {
-    set_error("tcgen05 back end not built yet");
-    return FSB_E_INVALID;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-size_t tc_wgrad_scratch_bytes(const ConvGeom& c) { return simt_wgrad_scratch_bytes(c); }
-int tc_wgrad(int, const void*, const void*, float*, void*, const ConvGeom&, cudaStream_t) {
-    set_error("tcgen05 back end not built yet");
-    return FSB_E_INVALID;
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, f32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// mbarrier arrives once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (SWIZZLE_128B; sm_100 descriptor version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7u) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D = f32, A = B = bf16, M x N, majors: 0 = K-major, 1 = MN-major
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------------------------
+struct ConvTcParams {
+    long long rows;        // rows of the output (and of each activation plane)
+    int m_tiles, n_tiles;
+    int BN;                // output channels per tile (multiple of 16, <= 256)
+    int K;                 // padded input channels CsIn (multiple of 16)
+    int ngroups, tpg;      // A boxes per k-chunk sweep, taps sharing one box
+    int goff[9];           // row offset of the box origin relative to the tile's first row
+    int wrow[9][3];        // first row of tap (group, shift) in the packed weight matrix (hi plane)
+    int w_lo_row;          // row offset of the lo plane in the packed weight matrix
+    int a_box_rows;        // 128 (tpg == 1) or 136
+    int nA, nW;            // ring depths
+    int planes;            // 2 = bf16x3, 1 = bf16 (hi only)
+    int base_off_mode;     // 1: descriptor base_offset = row shift, 0: always 0
+    float* Z;
+    int ldz;               // CsOut
+    const float* bias;     // CsOut entries or nullptr
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: [A ring][W ring][barriers]
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_plane = (uint32_t)p.a_box_rows * 128u;
+    const uint32_t a_stage = a_plane * 2u;
+    const uint32_t w_plane = (uint32_t)p.BN * 128u;
+    const uint32_t w_stage = w_plane * 2u;
+    const uint32_t a_ring = smem_base;
+    const uint32_t w_ring = a_ring + a_stage * p.nA;
+    const uint32_t bars = w_ring + w_stage * p.nW;         // 8-byte mbarriers
+    // barrier layout: A_full[nA] A_empty[nA] W_full[nW] W_empty[nW] T_full[2] T_empty[2], then tmem ptr
+    const uint32_t bA_full = bars, bA_empty = bA_full + 8u * p.nA;
+    const uint32_t bW_full = bA_empty + 8u * p.nA, bW_empty = bW_full + 8u * p.nW;
+    const uint32_t bT_full = bW_empty + 8u * p.nW, bT_empty = bT_full + 16u;
+    const uint32_t tmem_slot = bT_empty + 16u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int kchunks = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nA; ++i) { mbar_init(bA_full + 8u * i, 1); mbar_init(bA_empty + 8u * i, 1); }
+        for (int i = 0; i < p.nW; ++i) { mbar_init(bW_full + 8u * i, 1); mbar_init(bW_empty + 8u * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bT_full + 8u * i, 1); mbar_init(bT_empty + 8u * i, 128); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int r0 = mt * BM;
+                for (int g = 0; g < p.ngroups; ++g) {
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(bA_empty + 8u * sa, pa ^ 1u);
+                        mbar_expect_tx(bA_full + 8u * sa, a_plane * p.planes);
+                        const uint32_t dst = a_ring + a_stage * sa;
+                        tma_load_3d(dst, &tmA, kc * BK, r0 + p.goff[g], 0, bA_full + 8u * sa);
+                        if (p.planes == 2) tma_load_3d(dst + a_plane, &tmA, kc * BK, r0 + p.goff[g], 1, bA_full + 8u * sa);
+                        if (++sa == (uint32_t)p.nA) { sa = 0; pa ^= 1u; }
+                        for (int s = 0; s < p.tpg; ++s) {
+                            mbar_wait(bW_empty + 8u * sw, pw ^ 1u);
+                            mbar_expect_tx(bW_full + 8u * sw, w_plane * p.planes);
+                            const uint32_t wd = w_ring + w_stage * sw;
+                            const int wr = p.wrow[g][s] + nt * p.BN;
+                            tma_load_2d(wd, &tmW, kc * BK, wr, bW_full + 8u * sw);
+                            if (p.planes == 2) tma_load_2d(wd + w_plane, &tmW, kc * BK, p.w_lo_row + wr, bW_full + 8u * sw);
+                            if (++sw == (uint32_t)p.nW) { sw = 0; pw ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BM, p.BN, 0, 0);
+            uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t buf = it & 1u, use = it >> 1;
+                mbar_wait(bT_empty + 8u * buf, (use & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256u;
+                uint32_t acc = 0;
+                for (int g = 0; g < p.ngroups; ++g) {
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(bA_full + 8u * sa, pa);
+                        tc_fence_after();
+                        const uint32_t a_base = a_ring + a_stage * sa;
+                        int ksteps = (p.K - kc * BK + 15) / 16;
+                        if (ksteps > BK / 16) ksteps = BK / 16;
+                        for (int s = 0; s < p.tpg; ++s) {
+                            mbar_wait(bW_full + 8u * sw, pw);
+                            tc_fence_after();
+                            const uint32_t w_base = w_ring + w_stage * sw;
+                            const uint32_t boff = p.base_off_mode ? (uint32_t)s : 0u;
+                            for (int k = 0; k < ksteps; ++k) {
+                                const uint64_t a_hi = make_desc(a_base + s * 128u + k * 32u, 16, 1024, boff);
+                                const uint64_t b_hi = make_desc(w_base + k * 32u, 16, 1024, 0);
+                                if (p.planes == 2) {
+                                    const uint64_t a_lo = make_desc(a_base + a_plane + s * 128u + k * 32u, 16, 1024, boff);
+                                    const uint64_t b_lo = make_desc(w_base + w_plane + k * 32u, 16, 1024, 0);
+                                    umma_bf16(d_tmem, a_lo, b_hi, idesc, acc);
+                                    umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                                    umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+                                } else {
+                                    umma_bf16(d_tmem, a_hi, b_hi, idesc, acc);
+                                }
+                                acc = 1u;
+                            }
+                            umma_commit(bW_empty + 8u * sw);
+                            if (++sw == (uint32_t)p.nW) { sw = 0; pw ^= 1u; }
+                        }
+                        umma_commit(bA_empty + 8u * sa);
+                        if (++sa == (uint32_t)p.nA) { sa = 0; pa ^= 1u; }
+                    }
+                }
+                umma_commit(bT_full + 8u * buf);
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const uint32_t buf = it & 1u, use = it >> 1;
+            mbar_wait(bT_full + 8u * buf, use & 1u);
+            tc_fence_after();
+            const long long row = (long long)mt * BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+            float* zrow = p.Z + row * p.ldz;
+            for (int c = 0; c < p.BN; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c, v);
+                const int n = nt * p.BN + c;
+                if (row < p.rows && n < p.ldz) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(zrow + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bT_empty + 8u * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad kernel
+// ---------------------------------------------------------------------------------------------
+struct WgradTcParams {
+    long long rows;
+    long long rows_per_split;   // multiple of WG_R
+    int splits;
+    int co_tiles, ci_tiles, ngroups, tpg;
+    int goff[9];                // row offset of the A box origin per group
+    int tap_of[9][3];           // torch tap index of (group, shift)
+    int ntaps;
+    int CsIn, CsOut;
+    int nstages;
+    int planes;
+    int base_off_mode;
+    float* P;                   // [split][tap][CsIn][CsOut]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmA, const WgradTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t dz_box = WG_R * 128u;                  // one 64-channel box of dZ
+    constexpr uint32_t a_box = (WG_R + A_HALO) * 128u;        // one 64-channel box of A (with halo rows)
+    constexpr uint32_t dz_plane = 2u * dz_box;                // 128 output channels
+    constexpr uint32_t a_plane = 2u * a_box;                  // 128 input channels
+    const uint32_t stage_bytes = (dz_plane + a_plane) * 2u;   // hi + lo (lo unused when planes == 1)
+    const uint32_t ring = smem_base;
+    const uint32_t bars = ring + stage_bytes * p.nstages;
+    const uint32_t b_full = bars, b_empty = b_full + 8u * p.nstages, b_done = b_empty + 8u * p.nstages;
+    const uint32_t tmem_slot = b_done + 8u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // work item
+    int item = blockIdx.x;
+    const int sp = item % p.splits; item /= p.splits;
+    const int cit = item % p.ci_tiles; item /= p.ci_tiles;
+    const int cot = item % p.co_tiles; item /= p.co_tiles;
+    const int g = item;
+    const int co0 = cot * 128, ci0 = cit * WG_BN;
+    int bn = p.CsIn - ci0;
+    if (bn > WG_BN) bn = WG_BN;
+    const long long rb = (long long)sp * p.rows_per_split;
+    long long re = rb + p.rows_per_split;
+    if (re > p.rows) re = p.rows;
+    const int nchunks = re > rb ? (int)((re - rb + WG_R - 1) / WG_R) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nstages; ++i) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
+        mbar_init(b_done, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmDZ);
+        tma_prefetch_desc(&tmA);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int r = (int)(rb + (long long)ch * WG_R);
+                mbar_wait(b_empty + 8u * st, ph ^ 1u);
+                mbar_expect_tx(b_full + 8u * st, (dz_plane + a_plane) * p.planes);
+                const uint32_t base = ring + stage_bytes * st;
+                for (int pl = 0; pl < p.planes; ++pl) {
+                    const uint32_t dzd = base + pl * dz_plane;
+                    const uint32_t ad = base + 2u * dz_plane + pl * a_plane;
+                    tma_load_3d(dzd, &tmDZ, co0, r, pl, b_full + 8u * st);
+                    tma_load_3d(dzd + dz_box, &tmDZ, co0 + 64, r, pl, b_full + 8u * st);
+                    tma_load_3d(ad, &tmA, ci0, r + p.goff[g], pl, b_full + 8u * st);
+                    tma_load_3d(ad + a_box, &tmA, ci0 + 64, r + p.goff[g], pl, b_full + 8u * st);
+                }
+                if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, bn, 1, 1);
+            uint32_t st = 0, ph = 0;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                mbar_wait(b_full + 8u * st, ph);
+                tc_fence_after();
+                const uint32_t base = ring + stage_bytes * st;
+                const uint32_t dz_hi = base, dz_lo = base + dz_plane;
+                const uint32_t a_hi = base + 2u * dz_plane, a_lo = a_hi + a_plane;
+                for (int s = 0; s < p.tpg; ++s) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)s * WG_BN;
+                    const uint32_t boff = p.base_off_mode ? (uint32_t)s : 0u;
+                    for (int k = 0; k < WG_R / 16; ++k) {
+                        const uint32_t acc = (ch > 0 || k > 0) ? 1u : 0u;
+                        const uint64_t m_hi = make_desc(dz_hi + k * 2048u, dz_box, 1024, 0);
+                        const uint64_t n_hi = make_desc(a_hi + s * 128u + k * 2048u, a_box, 1024, boff);
+                        if (p.planes == 2) {
+                            const uint64_t m_lo = make_desc(dz_lo + k * 2048u, dz_box, 1024, 0);
+                            const uint64_t n_lo = make_desc(a_lo + s * 128u + k * 2048u, a_box, 1024, boff);
+                            umma_bf16(d_tmem, m_lo, n_hi, idesc, acc);
+                            umma_bf16(d_tmem, m_hi, n_lo, idesc, 1u);
+                            umma_bf16(d_tmem, m_hi, n_hi, idesc, 1u);
+                        } else {
+                            umma_bf16(d_tmem, m_hi, n_hi, idesc, acc);
+                        }
+                    }
+                }
+                umma_commit(b_empty + 8u * st);
+                if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1u; }
+            }
+            umma_commit(b_done);
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        if (nchunks > 0) {
+            mbar_wait(b_done, 0);
+            tc_fence_after();
+        }
+        for (int s = 0; s < p.tpg; ++s) {
+            const int t = p.tap_of[g][s];
+            float* Pt = p.P + ((long long)sp * p.ntaps + t) * p.CsIn * p.CsOut;
+            const uint32_t taddr = tmem_base + (uint32_t)s * WG_BN + ((uint32_t)(q * 32) << 16);
+            for (int c = 0; c < bn; c += 16) {
+                float v[16];
+                if (nchunks > 0) {
+                    tmem_ld16(taddr + (uint32_t)c, v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+                if (co < p.CsOut) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) Pt[(long long)(ci0 + c + i) * p.CsOut + co] = v[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: torch (Cout, Cin, taps) float32 -> bf16 hi/lo K-major tiles for forward and dgrad
+// ---------------------------------------------------------------------------------------------
+struct TcPackLayout {
+    int bn_f, nt_f, npad_f, kpad_f;      // forward : N = Cout, K = Cin
+    int bn_d, nt_d, npad_d, kpad_d;      // dgrad   : N = Cin,  K = Cout
+    size_t fwd_elems, dgr_elems;         // elements per plane
+    size_t off_fwd, off_dgr, off_bias, total;
+};
+
+void split_n(int cs, int& bn, int& nt) {
+    nt = (cs + 255) / 256;
+    bn = round_up((cs + nt - 1) / nt, 16);
+}
+
+TcPackLayout pack_layout(const ConvGeom& c) {
+    TcPackLayout L;
+    split_n(c.CsOut, L.bn_f, L.nt_f);
+    split_n(c.CsIn, L.bn_d, L.nt_d);
+    L.npad_f = L.bn_f * L.nt_f; L.kpad_f = round_up(c.CsIn, BK);
+    L.npad_d = L.bn_d * L.nt_d; L.kpad_d = round_up(c.CsOut, BK);
+    L.fwd_elems = (size_t)c.ntaps * L.npad_f * L.kpad_f;
+    L.dgr_elems = (size_t)c.ntaps * L.npad_d * L.kpad_d;
+    L.off_fwd = 0;
+    L.off_dgr = align_up(L.off_fwd + 2 * L.fwd_elems * 2, 1024);
+    L.off_bias = align_up(L.off_dgr + 2 * L.dgr_elems * 2, 1024);
+    L.total = L.off_bias + (size_t)c.CsOut * 4;
+    return L;
+}
+
+__global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, ConvGeom c, TcPackLayout L,
+                               __nv_bfloat16* fwd, __nv_bfloat16* dgr, float* pb) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long i = i0; i < (long long)L.fwd_elems; i += stride) {
+        int k = (int)(i % L.kpad_f);
+        long long u = i / L.kpad_f;
+        int n = (int)(u % L.npad_f);
+        int t = (int)(u / L.npad_f);
+        float v = (n < c.Cout && k < c.Cin) ? w[((long long)n * c.Cin + k) * c.ntaps + t] : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        fwd[i] = hi;
+        fwd[L.fwd_elems + i] = lo;
+    }
+    for (long long i = i0; i < (long long)L.dgr_elems; i += stride) {
+        int k = (int)(i % L.kpad_d);           // output channel
+        long long u = i / L.kpad_d;
+        int n = (int)(u % L.npad_d);           // input channel
+        int t = (int)(u / L.npad_d);
+        float v = (k < c.Cout && n < c.Cin) ? w[((long long)k * c.Cin + n) * c.ntaps + t] : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        dgr[i] = hi;
+        dgr[L.dgr_elems + i] = lo;
+    }
+    for (long long i = i0; i < c.CsOut; i += stride) pb[i] = (bias && i < c.Cout) ? bias[i] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps
+// ---------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+    }
+    return fn;
+}
+
+// activation planes: (C, rows, 2 planes) bf16, box (64, box_rows, 1)
+int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int box_rows) {
+    auto fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return FSB_E_NODEVICE;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)Cs, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)Cs * 2, (cuuint64_t)rows * Cs * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(act rows=%lld Cs=%d box=%d) failed: %d", rows, Cs, box_rows, (int)r);
+        return FSB_E_INVALID;
+    }
+    return 0;
+}
+
+// packed weights: (Kpad, total_rows) bf16, box (64, box_rows)
+int make_w_map(CUtensorMap* m, const void* base, long long total_rows, int kpad, int box_rows) {
+    auto fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return FSB_E_NODEVICE;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)total_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weights rows=%lld kpad=%d box=%d) failed: %d", total_rows, kpad, box_rows, (int)r);
+        return FSB_E_INVALID;
+    }
+    return 0;
+}
+
+int tc_mode() {
+    // debugging switches: bit 0 = one TMA box per tap (no dx sharing), bit 1 = set the descriptor base_offset to
+    // the row shift (measured on B200: the swizzle is a function of the absolute smem address, so a
+    // 128-byte-shifted start address needs base_offset 0; base_offset = shift gives wrong results)
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("FSB200_TC_MODE");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Groups taps that differ only in their column shift (consecutive row offsets base-1, base, base+1).
+// sign = +1: forward offsets; -1: dgrad (negated).  Fills goff / tap index per (group, shift).
+void group_taps(const ConvGeom& c, int sign, bool share, int& ngroups, int& tpg, int goff[9], int tap_of[9][3]) {
+    const bool triple = share && (c.ntaps == 3 || c.ntaps == 9);
+    if (!triple) {
+        ngroups = c.ntaps;
+        tpg = 1;
+        for (int t = 0; t < c.ntaps; ++t) {
+            goff[t] = sign * c.offs[t];
+            tap_of[t][0] = t;
+            tap_of[t][1] = tap_of[t][2] = 0;
+        }
+        return;
+    }
+    ngroups = c.ntaps / 3;
+    tpg = 3;
+    for (int g = 0; g < ngroups; ++g) {
+        // taps 3g, 3g+1, 3g+2 have offsets o-1, o, o+1 (dx = -1, 0, +1)
+        const int centre = sign * c.offs[3 * g + 1];
+        goff[g] = centre - 1;
+        for (int s = 0; s < 3; ++s) tap_of[g][s] = sign > 0 ? 3 * g + s : 3 * g + (2 - s);
+    }
+}
+
+int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
+                   const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
+                   cudaStream_t s) {
+    ConvTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows;
+    p.m_tiles = (int)((rows + BM - 1) / BM);
+    p.n_tiles = nt;
+    p.BN = bn;
+    p.K = K;
+    int tap_of[9][3];
+    group_taps(c, sign, !(tc_mode() & 1), p.ngroups, p.tpg, p.goff, tap_of);
+    for (int g = 0; g < p.ngroups; ++g)
+        for (int t = 0; t < p.tpg; ++t) p.wrow[g][t] = tap_of[g][t] * w_npad;
+    p.w_lo_row = c.ntaps * w_npad;
+    p.a_box_rows = p.tpg == 1 ? BM : BM + A_HALO;
+    p.planes = precision == 1 ? 2 : 1;
+    p.base_off_mode = (tc_mode() & 2) ? 1 : 0;
+    p.Z = Z;
+    p.ldz = ldz;
+    p.bias = bias;
+    const size_t a_stage = (size_t)p.a_box_rows * 128 * 2, w_stage = (size_t)bn * 128 * 2;
+    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/;
+    // ring depths: at least 2 each; give W the stages it needs to cover one A stage, then grow both
+    p.nA = 2; p.nW = 2;
+    for (;;) {
+        bool grown = false;
+        if (p.nW < 6 && fixed + a_stage * p.nA + w_stage * (p.nW + 1) <= SMEM_LIMIT) { ++p.nW; grown = true; }
+        if (p.nA < 4 && p.nA * p.tpg < p.nW + 1 && fixed + a_stage * (p.nA + 1) + w_stage * p.nW <= SMEM_LIMIT) { ++p.nA; grown = true; }
+        if (!grown) break;
+    }
+    const size_t smem = fixed + a_stage * p.nA + w_stage * p.nW;
+    FSB_REQUIRE(smem <= SMEM_LIMIT, "conv_tc: shared memory %zu exceeds the limit (BN=%d)", smem, bn);
+    CUtensorMap tmA, tmW;
+    FSB_TRY(make_act_map(&tmA, A, rows, K, p.a_box_rows));
+    FSB_TRY(make_w_map(&tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn));
+    static bool attr_set = false;
+    if (!attr_set) {
+        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_set = true;
+    }
+    int grid = p.m_tiles * p.n_tiles;
+    if (grid > num_sms()) grid = num_sms();
+    conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmW, p);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// back-end entry points
+// ---------------------------------------------------------------------------------------------
+size_t tc_packed_weight_bytes(const ConvGeom& c) { return pack_layout(c).total + 1024; }
+
+static char* tc_pack_base(const void* packed) { return (char*)align_up((size_t)packed, 1024); }
+
+int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s) {
+    TcPackLayout L = pack_layout(c);
+    char* base = tc_pack_base(packed);
+    size_t total = L.fwd_elems > L.dgr_elems ? L.fwd_elems : L.dgr_elems;
+    int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+    tc_pack_kernel<<<blocks, 256, 0, s>>>(w, bias, c, L, (__nv_bfloat16*)(base + L.off_fwd),
+                                          (__nv_bfloat16*)(base + L.off_dgr), (float*)(base + L.off_bias));
+    FSB_LAUNCHED();
+    return 0;
+}
+
+int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s) {
+    TcPackLayout L = pack_layout(c);
+    const char* base = tc_pack_base(packed);
+    return launch_conv_tc(precision, A, base + L.off_fwd, L.kpad_f, L.npad_f, L.bn_f, L.nt_f,
+                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, s);
+}
+
+int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s) {
+    TcPackLayout L = pack_layout(c);
+    const char* base = tc_pack_base(packed);
+    return launch_conv_tc(precision, dZ, base + L.off_dgr, L.kpad_d, L.npad_d, L.bn_d, L.nt_d, nullptr, dA, c.rows,
+                          c.CsOut, c.CsIn, c, -1, s);
+}
+
+static void wgrad_shape(const ConvGeom& c, int& ngroups, int& tpg, int& co_tiles, int& ci_tiles, int& splits,
+                        long long& rows_per_split) {
+    int goff[9], tap_of[9][3];
+    group_taps(c, +1, !(tc_mode() & 1), ngroups, tpg, goff, tap_of);
+    co_tiles = (c.CsOut + 127) / 128;
+    ci_tiles = (c.CsIn + WG_BN - 1) / WG_BN;
+    const int items = ngroups * co_tiles * ci_tiles;
+    long long chunks = (c.rows + WG_R - 1) / WG_R;
+    int want = (2 * 148 + items - 1) / items;           // about two waves of CTAs
+    if (want > chunks) want = (int)chunks;
+    if (want > 128) want = 128;
+    if (want < 1) want = 1;
+    splits = want;
+    rows_per_split = (chunks + splits - 1) / splits * WG_R;
+}
+
+size_t tc_wgrad_scratch_bytes(const ConvGeom& c) {
+    int ng, tpg, cot, cit, splits;
+    long long rps;
+    wgrad_shape(c, ng, tpg, cot, cit, splits, rps);
+    // both tap groupings (debug switch) need the same bound: splits <= 128
+    return (size_t)splits * c.ntaps * c.CsIn * c.CsOut * sizeof(float);
+}
+
+int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c, cudaStream_t s) {
+    WgradTcParams p;
+    memset(&p, 0, sizeof(p));
+    wgrad_shape(c, p.ngroups, p.tpg, p.co_tiles, p.ci_tiles, p.splits, p.rows_per_split);
+    group_taps(c, +1, !(tc_mode() & 1), p.ngroups, p.tpg, p.goff, p.tap_of);
+    p.rows = c.rows;
+    p.ntaps = c.ntaps;
+    p.CsIn = c.CsIn;
+    p.CsOut = c.CsOut;
+    p.planes = precision == 1 ? 2 : 1;
+    p.base_off_mode = (tc_mode() & 2) ? 1 : 0;
+    p.P = (float*)scratch;
+    const size_t stage = (size_t)(2 * WG_R * 128 + 2 * (WG_R + A_HALO) * 128) * 2;
+    p.nstages = (int)((SMEM_LIMIT - 1024 - 256) / stage);
+    if (p.nstages > 4) p.nstages = 4;
+    const size_t smem = 1024 + 256 + stage * p.nstages;
+    CUtensorMap tmDZ, tmA;
+    FSB_TRY(make_act_map(&tmDZ, dZ, c.rows, c.CsOut, WG_R));
+    FSB_TRY(make_act_map(&tmA, A, c.rows, c.CsIn, WG_R + A_HALO));
+    static bool attr_set = false;
+    if (!attr_set) {
+        FSB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_set = true;
+    }
+    const int grid = p.ngroups * p.co_tiles * p.ci_tiles * p.splits;
+    wgrad_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmDZ, tmA, p);
+    FSB_LAUNCHED();
+    return wgrad_finalize((const float*)scratch, p.splits, c, dw, s);
 }
 
 }  // namespace fsb

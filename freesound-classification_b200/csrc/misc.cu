@@ -134,14 +134,27 @@ extern "C" int fsb_version(void) { return 100; }
 extern "C" const char* fsb_last_error(void) { return g_err; }
 
 extern "C" int fsb_device_ok(void) {
+    // cached per device: cudaGetDeviceProperties costs milliseconds and this sits on the per-step path
+    static int cached[64];       // 0 = unknown, 1 = ok, 2 = wrong architecture
+    static int cached_major[64], cached_minor[64];
     int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
         set_error("no CUDA device");
         return FSB_E_NODEVICE;
     }
-    if (prop.major != 10) {
-        set_error("libfsb200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (!cached[dev]) {
+        int major = 0, minor = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+            set_error("no CUDA device");
+            return FSB_E_NODEVICE;
+        }
+        cached_major[dev] = major; cached_minor[dev] = minor;
+        cached[dev] = major == 10 ? 1 : 2;
+    }
+    if (cached[dev] != 1) {
+        set_error("libfsb200 is built for sm_100a only; device is sm_%d%d", cached_major[dev], cached_minor[dev]);
         return FSB_E_NODEVICE;
     }
     return 0;

@@ -358,6 +358,8 @@ static int check_shape(const fsb_net* net, int n, int t) {
     const fsb_net_config& c = net->cfg;
     FSB_REQUIRE(n >= 1 && t > c.n_fft / 2, "net: need N >= 1 and T > n_fft/2 (N=%d, T=%d)", n, t);
     int frames = 1 + t / c.hop;
+    FSB_REQUIRE((long long)n * (c.two_d ? c.n_features : 1) * frames < (1ll << 31),
+                "net: batch too large for 32-bit pixel indices (N=%d, frames=%d)", n, frames);
     int w = frames, h = c.two_d ? c.n_features : 1;
     for (int k = 0; k < c.num_blocks; ++k) {
         w /= 2;
@@ -621,6 +623,19 @@ extern "C" int fsb_net_read_activation(fsb_net* net, int which, float* dst, long
         FSB_REQUIRE(cap >= cnt, "read_activation: destination too small");
         *numel = cnt;
         return copy2d(net->feats, net->N, net->D, net->Ds, dst, net->D, s);
+    }
+    if (which >= 300) {
+        // debugging taps (float32 back end only): 300 + 10*block + {0 zp, 1 r0, 2 z1, 3 dz1, 4 dr0a, 5 dr0b, 6 da1, 7 dzp}
+        FSB_REQUIRE(c.precision == 0, "read_activation: internal taps need the float32 back end");
+        int kb = (which - 300) / 10, j = (which - 300) % 10;
+        FSB_REQUIRE(kb >= 0 && kb < c.num_blocks && j <= 7, "read_activation: unknown tap %d", which);
+        const BlockPlan& Bk = net->blocks[kb];
+        const float* src[8] = {Bk.zp, (const float*)Bk.r0, Bk.z1, (const float*)Bk.dz1, Bk.dr0a, Bk.dr0b, Bk.da1, Bk.dzp};
+        FSB_REQUIRE(src[j] != nullptr, "read_activation: tap %d not available (training only)", which);
+        long long cnt = Bk.g.pixels * Bk.g.C;
+        FSB_REQUIRE(cap >= cnt, "read_activation: destination too small");
+        *numel = cnt;
+        return pf_to_nchw(src[j], Bk.g, dst, s);
     }
     int k = which - 1;
     FSB_REQUIRE(k >= 0 && k < c.num_blocks, "read_activation: unknown tensor %d", which);

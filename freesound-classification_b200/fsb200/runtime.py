@@ -199,6 +199,8 @@ class NetPlan:
         self.total_params = sum(self.param_numel)
         self.workspace = None
         self._ws_key = None
+        self.grad_flat = None
+        self.grad_views = None
         self._param_ptrs = (ctypes.c_void_p * self.num_params)()
         self._mean_ptrs = (ctypes.c_void_p * self.num_bn)()
         self._var_ptrs = (ctypes.c_void_p * self.num_bn)()
@@ -249,9 +251,18 @@ class NetPlan:
                                         _stream()), "net_forward")
         return logits
 
-    def backward(self, dlogits):
+    def backward(self, dlogits, fresh=False):
+        """Runs the backward plan; returns the flat gradient (canonical parameter order).  The plan owns ONE
+        persistent flat buffer (stable pointers keep the fused-Adam table and NCCL buffers cached); `fresh`
+        asks for a temporary buffer instead (gradient accumulation into existing `.grad`)."""
         dlogits = dlogits.contiguous().float()
-        grads = torch.empty(self.total_params, dtype=torch.float32, device=self.device)
+        if fresh:
+            grads = torch.empty(self.total_params, dtype=torch.float32, device=self.device)
+        else:
+            if self.grad_flat is None:
+                self.grad_flat = torch.empty(self.total_params, dtype=torch.float32, device=self.device)
+                self.grad_views = None
+            grads = self.grad_flat
         ws = self.workspace
         with torch.cuda.device(self.device):
             check(lib().fsb_net_backward(self.handle, _ptr(dlogits), self._param_ptrs, _ptr(grads), _ptr(ws),
@@ -282,24 +293,44 @@ class NetPlan:
 
 
 class _NetFunction(torch.autograd.Function):
-    """logits = net(signal; params): the whole forward/backward is two library calls."""
+    """logits = net(signal; params): the whole forward/backward is two library calls.
+
+    backward() writes every parameter gradient into the plan's persistent flat buffer and installs views of
+    it as `p.grad` directly (autograd's AccumulateGrad would clone each of the ~120 views); when a parameter
+    already holds a gradient (accumulation_steps > 1) the step's gradient goes to a temporary buffer and
+    is added."""
 
     @staticmethod
     def forward(ctx, plan, signal, dropout_seed, *params):
         ctx.plan = plan
-        ctx.shapes = [p.shape for p in params]
+        ctx.params = params
         return plan.forward(signal, True, dropout_seed)
 
     @staticmethod
     def backward(ctx, dlogits):
-        plan = ctx.plan
-        flat = plan.backward(dlogits)
-        plan.last_flat_grad = flat
-        grads, off = [], 0
-        for shape, n in zip(ctx.shapes, plan.param_numel):
-            grads.append(flat[off:off + n].view(shape))
-            off += n
-        return (None, None, None) + tuple(grads)
+        plan, params = ctx.plan, ctx.params
+        accumulate = any(p.grad is not None for p in params)
+        flat = plan.backward(dlogits, fresh=accumulate)
+        if accumulate:
+            off = 0
+            for p, n in zip(params, plan.param_numel):
+                g = flat[off:off + n].view(p.shape)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.add_(g)
+                off += n
+        else:
+            if plan.grad_views is None or len(plan.grad_views) != len(params):
+                views, off = [], 0
+                for p, n in zip(params, plan.param_numel):
+                    views.append(flat[off:off + n].view(p.shape))
+                    off += n
+                plan.grad_views = views
+            for p, g in zip(params, plan.grad_views):
+                p.grad = g
+            plan.last_flat_grad = flat
+        return (None, None, None) + (None,) * len(params)
 
 
 def net_apply(plan, signal, dropout_seed, params):

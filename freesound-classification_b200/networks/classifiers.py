@@ -205,11 +205,18 @@ class _AcceleratedCNN(nn.Module):
         writer.add_histogram("losses", np.array(losses), global_step=global_step)
 
     def add_image_summaries(self, signal, global_step, writer, to_plot=8):
+        """Reference :621-631 (image grid of the first raw signals).  A summary that the installed
+        tensorboard/PIL cannot encode must not stop training, so failures are reported once and skipped."""
         import torchvision.utils
         if len(signal) > to_plot:
             signal = signal[:to_plot]
-        image_grid = torchvision.utils.make_grid(signal.data.cpu().unsqueeze(1), normalize=True, scale_each=True)
-        writer.add_image("signal", image_grid, global_step)
+        try:
+            image_grid = torchvision.utils.make_grid(signal.data.cpu().unsqueeze(1), normalize=True, scale_each=True)
+            writer.add_image("signal", image_grid, global_step)
+        except Exception as exc:       # noqa: BLE001
+            if not getattr(self, "_image_summary_warned", False):
+                print("image summary skipped: %s" % exc)
+                self._image_summary_warned = True
 
     def _loss(self, class_logits, labels, average):
         return lsep_loss(class_logits, labels, average=average)
@@ -300,7 +307,7 @@ class _AcceleratedCNN(nn.Module):
                     ev = torch.cuda.Event()
                     ev.record()
                 item = (ev, losses_h, loss_h, probs_h, labels_h, batch_idx, self.global_step,
-                        signal.squeeze(-1) if batch_idx == 0 else None)
+                        signal if batch_idx == 0 else None)
                 if pending is not None:
                     resolve(pending, pb)
                 pending = item
