@@ -59,6 +59,7 @@ struct Geo {
     int N, H, W, C, Cs, padH, padW, Hp, Wp;
     long long rows;      // N * Hp * Wp
     long long pixels;    // N * H * W (interior)
+    const unsigned char* mask;   // device: mask[row] = 1 for interior rows; nullptr = no border (all interior)
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -69,6 +70,7 @@ inline Geo make_geo(int N, int H, int W, int C, int padH, int padW) {
     g.padH = padH; g.padW = padW; g.Hp = H + 2 * padH; g.Wp = W + 2 * padW;
     g.rows = (long long)N * g.Hp * g.Wp;
     g.pixels = (long long)N * H * W;
+    g.mask = nullptr;
     return g;
 }
 

@@ -20,7 +20,7 @@ static EwShape ew_shape(const Geo& g) {
     int bx = cv < 64 ? cv : 64;
     int by = 256 / bx;
     if (by < 1) by = 1;
-    long long need = (g.pixels + by * 4 - 1) / (by * 4);
+    long long need = (g.rows + by * 4 - 1) / (by * 4);
     int gx = (int)(need < 1 ? 1 : (need > EW_MAX_BLOCKS ? EW_MAX_BLOCKS : need));
     EwShape s;
     s.block = dim3(bx, by);
@@ -30,14 +30,37 @@ static EwShape ew_shape(const Geo& g) {
 
 int ew_num_blocks(const Geo& g) { return (int)ew_shape(g).grid.x; }
 
+#define EW_CHECK(g) \
+    FSB_REQUIRE(((g).padH == 0 && (g).padW == 0) || (g).mask != nullptr, "element-wise kernel: geometry has a border but no interior mask")
+
 #define EW_PROLOGUE                                                        \
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;                  \
     const bool cok = cv < g.Cs / 4;                                        \
     const int c0 = cv * 4;
 
-#define EW_PIXEL_LOOP                                                      \
-    for (long long q = (long long)blockIdx.x * blockDim.y + threadIdx.y; q < g.pixels; \
-         q += (long long)gridDim.x * blockDim.y)
+// Grid-stride loop over the PADDED rows (consecutive rows -> consecutive memory, no divisions); border rows
+// are skipped through the geometry's byte mask (1 = interior pixel; nullptr = every row is interior).
+#define EW_PIXEL_LOOP                                                                        \
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < g.rows;     \
+         row += (long long)gridDim.x * blockDim.y)                                            \
+        if (g.mask == nullptr || g.mask[row])
+
+// interior mask of a padded-flat geometry
+__global__ void interior_mask_kernel(Geo g, unsigned char* mask) {
+    for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < g.rows;
+         row += (long long)gridDim.x * blockDim.x) {
+        int rr = (int)(row % ((long long)g.Hp * g.Wp));
+        int yy = rr / g.Wp, xx = rr - yy * g.Wp;
+        mask[row] = (yy >= g.padH && yy < g.padH + g.H && xx >= g.padW && xx < g.padW + g.W) ? 1 : 0;
+    }
+}
+
+int pf_build_mask(const Geo& g, unsigned char* mask, cudaStream_t s) {
+    int blocks = (int)((g.rows + 255) / 256 > 1184 ? 1184 : (g.rows + 255) / 256);
+    interior_mask_kernel<<<blocks, 256, 0, s>>>(g, mask);
+    FSB_LAUNCHED();
+    return 0;
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -157,14 +180,13 @@ int pf_zero_all(void* buf, int fmt, const Geo& g, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ x, Geo g, double* partials) {
+__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ xin, Geo g, double* partials) {
     EW_PROLOGUE
     Acc4 acc[2];
     acc[0].init(); acc[1].init();
     if (cok) {
         EW_PIXEL_LOOP {
-            long long row = geo_q_to_row(g, q);
-            float4 v = ld4(x + row * g.Cs + c0);
+            float4 v = ld4(xin + row * g.Cs + c0);
             acc[0].add(v);
             acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
         }
@@ -173,6 +195,7 @@ __global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ x,
 }
 
 int pf_stats(const float* x, const Geo& g, double* partials, cudaStream_t s) {
+    EW_CHECK(g);
     EwShape sh = ew_shape(g);
     stats_kernel<<<sh.grid, sh.block, 0, s>>>(x, g, partials);
     FSB_LAUNCHED();
@@ -313,38 +336,51 @@ __device__ __forceinline__ Coef4 load_coef(const float* scale, const float* shif
     return c;
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr, void* a_mma,
-                  int fmt, float* a_f32) {
+                  int fmt, float* a_f32, double* out_stats) {
     EW_PROLOGUE
-    if (!cok) return;
-    Coef4 cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
-    Coef4 cr;
-    if (res.zr) cr = load_coef(res.scale, res.shift, res.slope, c0);
-    const long long plane = g.rows * g.Cs;
-    EW_PIXEL_LOOP {
-        long long row = geo_q_to_row(g, q);
-        long long idx = row * g.Cs + c0;
-        float4 y = affine4(ld4(z + idx), cb.sc, cb.sh);
-        if (res.zr) {
-            float4 r = affine4(ld4(res.zr + idx), cr.sc, cr.sh);
-            if (cr.has_sl) r = prelu4(r, cr.sl);
-            y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+    if (!STATS && !cok) return;
+    Acc4 acc[2];
+    if (STATS) { acc[0].init(); acc[1].init(); }
+    if (cok) {
+        Coef4 cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
+        Coef4 cr;
+        if (res.zr) cr = load_coef(res.scale, res.shift, res.slope, c0);
+        const long long plane = g.rows * g.Cs;
+        EW_PIXEL_LOOP {
+            long long idx = row * g.Cs + c0;
+            float4 v = affine4(ld4(z + idx), cb.sc, cb.sh);
+            if (res.zr) {
+                float4 r = affine4(ld4(res.zr + idx), cr.sc, cr.sh);
+                if (cr.has_sl) r = prelu4(r, cr.sl);
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            if (cb.has_sl) v = prelu4(v, cb.sl);
+            if (dr.p > 0.f) {
+                v.x *= keep_scale(dr, idx); v.y *= keep_scale(dr, idx + 1);
+                v.z *= keep_scale(dr, idx + 2); v.w *= keep_scale(dr, idx + 3);
+            }
+            if (a_f32) st4(a_f32 + idx, v);
+            if (a_mma) store_fmt(a_mma, fmt, plane, idx, v);
+            if (STATS) {
+                acc[0].add(v);
+                acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
+            }
         }
-        if (cb.has_sl) y = prelu4(y, cb.sl);
-        if (dr.p > 0.f) {
-            y.x *= keep_scale(dr, idx); y.y *= keep_scale(dr, idx + 1);
-            y.z *= keep_scale(dr, idx + 2); y.w *= keep_scale(dr, idx + 3);
-        }
-        if (a_f32) st4(a_f32 + idx, y);
-        if (a_mma) store_fmt(a_mma, fmt, plane, idx, y);
     }
+    if (STATS) block_reduce_store<2>(acc, out_stats, g.Cs, c0, cok);
 }
 
 int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropout dr, void* a_mma, int fmt,
-                   float* a_f32, cudaStream_t s) {
+                   float* a_f32, double* out_stats, cudaStream_t s) {
+    EW_CHECK(g);
     EwShape sh = ew_shape(g);
-    bn_act_fwd_kernel<<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32);
+    if (out_stats)
+        bn_act_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, out_stats);
+    else
+        bn_act_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, nullptr);
     FSB_LAUNCHED();
     return 0;
 }
@@ -354,29 +390,43 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int pool_h) {
+maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int pool_h, double* out_stats) {
     EW_PROLOGUE
-    if (!cok) return;
-    EW_PIXEL_LOOP {
-        const unsigned uq = (unsigned)q;
-        const unsigned tq = uq / (unsigned)g.W;
-        const int x = (int)(uq - tq * (unsigned)g.W);
-        const int n = (int)(tq / (unsigned)g.H);
-        const int y = (int)(tq - (unsigned)n * (unsigned)g.H);
-        long long r00 = geo_row(gf, n, y * pool_h, 2 * x);
-        float4 m = max4(ld4(zf + r00 * gf.Cs + c0), ld4(zf + (r00 + 1) * gf.Cs + c0));
-        if (pool_h == 2) {
-            long long r10 = r00 + gf.Wp;
-            m = max4(m, max4(ld4(zf + r10 * gf.Cs + c0), ld4(zf + (r10 + 1) * gf.Cs + c0)));
+    if (!STATS && !cok) return;
+    Acc4 acc[2];
+    if (STATS) { acc[0].init(); acc[1].init(); }
+    if (cok) {
+        EW_PIXEL_LOOP {
+            const unsigned img = (unsigned)(g.Hp * g.Wp);
+            const int n = (int)((unsigned long long)row / img);
+            const unsigned rr = (unsigned)(row - (long long)n * img);
+            const int y = (int)(rr / (unsigned)g.Wp) - g.padH, x = (int)(rr % (unsigned)g.Wp) - g.padW;
+            long long r00 = geo_row(gf, n, y * pool_h, 2 * x);
+            float4 m = max4(ld4(zf + r00 * gf.Cs + c0), ld4(zf + (r00 + 1) * gf.Cs + c0));
+            if (pool_h == 2) {
+                long long r10 = r00 + gf.Wp;
+                m = max4(m, max4(ld4(zf + r10 * gf.Cs + c0), ld4(zf + (r10 + 1) * gf.Cs + c0)));
+            }
+            st4(zp + row * g.Cs + c0, m);
+            if (STATS) {
+                acc[0].add(m);
+                acc[1].add(make_float4(m.x * m.x, m.y * m.y, m.z * m.z, m.w * m.w));
+            }
         }
-        st4(zp + geo_row(g, n, y, x) * g.Cs + c0, m);
     }
+    if (STATS) block_reduce_store<2>(acc, out_stats, g.Cs, c0, cok);
 }
 
-int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, cudaStream_t s) {
+int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, double* out_stats,
+                    cudaStream_t s) {
+    EW_CHECK(gp);
     EwShape sh = ew_shape(gp);
-    maxpool_fwd_kernel<<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h);
+    if (out_stats)
+        maxpool_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, out_stats);
+    else
+        maxpool_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr);
     FSB_LAUNCHED();
     return 0;
 }
@@ -389,12 +439,10 @@ maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restric
     if (!cok) return;
     const long long plane = g.rows * g.Cs;
     EW_PIXEL_LOOP {
-        const unsigned uq = (unsigned)q;
-        const unsigned tq = uq / (unsigned)g.W;
-        const int x = (int)(uq - tq * (unsigned)g.W);
-        const int n = (int)(tq / (unsigned)g.H);
-        const int y = (int)(tq - (unsigned)n * (unsigned)g.H);
-        long long row = geo_row(g, n, y, x);
+        const unsigned img = (unsigned)(g.Hp * g.Wp);
+        const int n = (int)((unsigned long long)row / img);
+        const unsigned rr = (unsigned)(row - (long long)n * img);
+        const int y = (int)(rr / (unsigned)g.Wp) - g.padH, x = (int)(rr % (unsigned)g.Wp) - g.padW;
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         int py = y / pool_h, px = x / 2;
         if (py < gp.H && px < gp.W) {
@@ -427,6 +475,7 @@ maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restric
 
 int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h, void* dzf,
                      int fmt, cudaStream_t s) {
+    EW_CHECK(gf);
     EwShape sh = ew_shape(gf);
     maxpool_bwd_kernel<<<sh.grid, sh.block, 0, s>>>(dzp, gp, zf, gf, pool_h, dzf, fmt);
     FSB_LAUNCHED();
@@ -567,7 +616,7 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict_
     if (cok) {
         BwdCoef k = load_bwd(bn, res, c0);
         EW_PIXEL_LOOP {
-            long long idx = geo_q_to_row(g, q) * g.Cs + c0;
+            long long idx = row * g.Cs + c0;
             float4 dy, zh, dsl;
             bwd_point(dA1, dA2, z, res, k, dr, idx, dy, zh, dsl);
             acc[0].add(dy);
@@ -580,6 +629,7 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict_
 
 int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
                       Dropout dr, double* partials, cudaStream_t s) {
+    EW_CHECK(g);
     EwShape sh = ew_shape(g);
     bn_act_bwd_reduce_kernel<<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
     FSB_LAUNCHED();
@@ -619,7 +669,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__
     float4 m1 = ld4(c1 + c0), m2 = ld4(c2 + c0);
     const long long plane = g.rows * g.Cs;
     EW_PIXEL_LOOP {
-        long long idx = geo_q_to_row(g, q) * g.Cs + c0;
+        long long idx = row * g.Cs + c0;
         float4 dy, zh, dsl;
         bwd_point(dA1, dA2, z, res, k, dr, idx, dy, zh, dsl);
         float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
@@ -631,6 +681,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__
 
 int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
                      Dropout dr, const float* c1, const float* c2, void* dz, int fmt, float* dres, cudaStream_t s) {
+    EW_CHECK(g);
     EwShape sh = ew_shape(g);
     bn_act_bwd_apply_kernel<<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
     FSB_LAUNCHED();

@@ -31,6 +31,8 @@ struct Dropout {           // keep mask = hash(seed, element) >= p ; scale 1/(1-
 // number of pixel-blocks an element-wise reduction over `g` uses (partials are [nblk][K][Cs] doubles)
 int ew_num_blocks(const Geo& g);
 
+// fills mask[row] = 1 for interior rows of g, 0 for border rows (g.rows bytes)
+int pf_build_mask(const Geo& g, unsigned char* mask, cudaStream_t s);
 int pf_zero_border(void* buf, int fmt, const Geo& g, cudaStream_t s);
 int pf_zero_all(void* buf, int fmt, const Geo& g, cudaStream_t s);
 
@@ -48,12 +50,16 @@ int bn_finalize(const double* partials, int nblk, long long count, const float* 
 // appends channel 1 to a 2-channel partial record [1][2][16] (count = N*H*W)
 int freq_encoding_stats(int H, long long n_times_w, double* partials16, cudaStream_t s);
 
-// a = act(BN(z) [+ residual]) ; writes any of: GEMM-format plane(s) `a_mma` (fmt), float32 `a_f32`
+// a = act(BN(z) [+ residual]) ; writes any of: GEMM-format plane(s) `a_mma` (fmt), float32 `a_f32`;
+// out_stats (optional): per-block partial sum / sum of squares of `a` ([ew_num_blocks(g)][2][Cs] doubles),
+// i.e. the batch statistics of the NEXT BatchNorm, gathered while the data is in registers
 int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropout dr, void* a_mma,
-                   int fmt, float* a_f32, cudaStream_t s);
+                   int fmt, float* a_f32, double* out_stats, cudaStream_t s);
 
 // 2x2 (pool_h = 2) or 1x2 (pool_h = 1) max pool, floor mode: zf (gf) -> zp (gp)
-int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, cudaStream_t s);
+// out_stats (optional): partial sum / sum of squares of zp, [ew_num_blocks(gp)][2][Cs] doubles
+int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, double* out_stats,
+                    cudaStream_t s);
 // dzf (fmt planes, full-res geometry) <- dzp routed to the first maximum of every window
 int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h,
                      void* dzf, int fmt, cudaStream_t s);

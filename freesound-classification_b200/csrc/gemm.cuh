@@ -39,7 +39,16 @@ size_t packed_weight_bytes(int precision, const ConvGeom& c);
 // w: torch layout (Cout, Cin, taps) float32; bias: Cout or nullptr
 int pack_weights(int precision, const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s);
 
-int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s);
+// Optional fused BatchNorm statistics of the forward output: per-CTA partial sum / sum of squares over
+// interior pixels, partials[*nblk][2][CsOut] doubles (the tcgen05 epilogue reduces the tile while it is in
+// registers; the float32 back end runs the stand-alone statistics pass).  g = geometry of Z.
+struct FwdStats {
+    double* partials;
+    const Geo* g;
+    int* nblk;
+};
+int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
+                  cudaStream_t s);
 int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
 
 size_t wgrad_scratch_bytes(int precision, const ConvGeom& c);
@@ -57,7 +66,9 @@ int simt_wgrad(const float* A, const float* dZ, float* dw, void* scratch, const 
 
 size_t tc_packed_weight_bytes(const ConvGeom& c);
 int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s);
-int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s);
+int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
+           cudaStream_t s);
+int tc_max_ctas();
 int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
 size_t tc_wgrad_scratch_bytes(const ConvGeom& c);
 int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,

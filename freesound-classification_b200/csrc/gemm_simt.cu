@@ -2,6 +2,7 @@
 // float32 path (used for the FC head in every precision mode, and as the on-device cross-check of
 // the tcgen05 back end at sizes the CPU oracle cannot reach).
 #include "gemm.cuh"
+#include "eltwise.cuh"
 
 namespace fsb {
 
@@ -253,8 +254,15 @@ size_t packed_weight_bytes(int precision, const ConvGeom& c) {
 int pack_weights(int precision, const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s) {
     return precision == 0 ? simt_pack_weights(w, bias, c, packed, s) : tc_pack_weights(w, bias, c, packed, s);
 }
-int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s) {
-    return precision == 0 ? simt_fwd((const float*)A, packed, Z, c, s) : tc_fwd(precision, A, packed, Z, c, s);
+int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
+                  cudaStream_t s) {
+    if (precision != 0) return tc_fwd(precision, A, packed, Z, c, st, s);
+    FSB_TRY(simt_fwd((const float*)A, packed, Z, c, s));
+    if (st) {
+        FSB_TRY(pf_stats(Z, *st->g, st->partials, s));
+        *st->nblk = ew_num_blocks(*st->g);
+    }
+    return 0;
 }
 int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s) {
     return precision == 0 ? simt_dgrad((const float*)dZ, packed, dA, c, s) : tc_dgrad(precision, dZ, packed, dA, c, s);

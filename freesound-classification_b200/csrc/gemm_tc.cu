@@ -139,6 +139,31 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Column sums of a 32 x 16 register tile (one row per lane, 16 columns per lane) by recursive halving:
+// 16 shuffles; afterwards lanes 2j and 2j+1 both hold the total of column j = (lane >> 1) & 15.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h8 ? a[i] : a[i + 4], keep = h8 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h4 ? b[i] : b[i + 2], keep = h4 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = h2 ? c[0] : c[1], keep = h2 ? c[1] : c[0];
+    const float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ---------------------------------------------------------------------------------------------
@@ -158,6 +183,9 @@ struct ConvTcParams {
     float* Z;
     int ldz;               // CsOut
     const float* bias;     // CsOut entries or nullptr
+    // optional fused BatchNorm statistics of Z over interior pixels: partials[blockIdx.x][2][ldz] (doubles)
+    double* stats;
+    int Hp, Wp, H, W, padH, padW;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -177,9 +205,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bW_full = bA_empty + 8u * p.nA, bW_empty = bW_full + 8u * p.nW;
     const uint32_t bT_full = bW_empty + 8u * p.nW, bT_empty = bT_full + 16u;
     const uint32_t tmem_slot = bT_empty + 16u;
+    double* stat_acc = reinterpret_cast<double*>(smem_raw + (bars - smem_u32(smem_raw)) + 256u);   // [2][ldz]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    if (p.stats)
+        for (int i = threadIdx.x; i < 2 * p.ldz; i += TC_THREADS) stat_acc[i] = 0.0;
     const int kchunks = (p.K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
@@ -285,22 +316,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long row = (long long)mt * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
             float* zrow = p.Z + row * p.ldz;
+            float interior = 0.f;
+            if (p.stats && row < p.rows) {
+                const int rr = (int)(row % ((long long)p.Hp * p.Wp));
+                const int yy = rr / p.Wp, xx = rr - yy * p.Wp;
+                interior = (yy >= p.padH && yy < p.padH + p.H && xx >= p.padW && xx < p.padW + p.W) ? 1.f : 0.f;
+            }
             for (int c = 0; c < p.BN; c += 16) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)c, v);
                 const int n = nt * p.BN + c;
-                if (row < p.rows && n < p.ldz) {
+                if (n < p.ldz) {                       // warp-uniform
                     if (p.bias) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
                     }
+                    if (row < p.rows) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4*>(zrow + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(zrow + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                    if (p.stats) {
+                        float sq[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { v[i] *= interior; sq[i] = v[i] * v[i]; }
+                        const float s1 = warp_colsum16(v, lane), s2 = warp_colsum16(sq, lane);
+                        if ((lane & 1) == 0) {
+                            const int col = n + ((lane >> 1) & 15);
+                            atomicAdd(stat_acc + col, (double)s1);
+                            atomicAdd(stat_acc + p.ldz + col, (double)s2);
+                        }
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive(bT_empty + 8u * buf);
+        }
+        if (p.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+            double* o = p.stats + (long long)blockIdx.x * 2 * p.ldz;
+            for (int i = threadIdx.x - 64; i < 2 * p.ldz; i += 128) o[i] = stat_acc[i];
         }
     }
     tc_fence_before();
@@ -624,7 +679,7 @@ void group_taps(const ConvGeom& c, int sign, bool share, int& ngroups, int& tpg,
 
 int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
                    const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
-                   cudaStream_t s) {
+                   const FwdStats* st, cudaStream_t s) {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
     p.rows = rows;
@@ -644,7 +699,13 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     p.ldz = ldz;
     p.bias = bias;
     const size_t a_stage = (size_t)p.a_box_rows * 128 * 2, w_stage = (size_t)bn * 128 * 2;
-    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/;
+    if (st) {
+        const Geo& g = *st->g;
+        FSB_REQUIRE(g.rows == rows && g.Cs == ldz, "conv_tc: statistics geometry does not match the output");
+        p.stats = st->partials;
+        p.Hp = g.Hp; p.Wp = g.Wp; p.H = g.H; p.W = g.W; p.padH = g.padH; p.padW = g.padW;
+    }
+    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (st ? (size_t)16 * ldz : 0) /*statistics*/;
     // ring depths: at least 2 each; give W the stages it needs to cover one A stage, then grow both
     p.nA = 2; p.nW = 2;
     for (;;) {
@@ -667,6 +728,7 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     if (grid > num_sms()) grid = num_sms();
     conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmW, p);
     FSB_LAUNCHED();
+    if (st) *st->nblk = grid;
     return 0;
 }
 
@@ -690,18 +752,21 @@ int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* 
     return 0;
 }
 
-int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s) {
+int tc_max_ctas() { return num_sms(); }
+
+int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
+           cudaStream_t s) {
     TcPackLayout L = pack_layout(c);
     const char* base = tc_pack_base(packed);
     return launch_conv_tc(precision, A, base + L.off_fwd, L.kpad_f, L.npad_f, L.bn_f, L.nt_f,
-                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, s);
+                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, st, s);
 }
 
 int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s) {
     TcPackLayout L = pack_layout(c);
     const char* base = tc_pack_base(packed);
     return launch_conv_tc(precision, dZ, base + L.off_dgr, L.kpad_d, L.npad_d, L.bn_d, L.nt_d, nullptr, dA, c.rows,
-                          c.CsOut, c.CsIn, c, -1, s);
+                          c.CsOut, c.CsIn, c, -1, nullptr, s);
 }
 
 static void wgrad_shape(const ConvGeom& c, int& ngroups, int& tpg, int& co_tiles, int& ci_tiles, int& splits,

@@ -63,6 +63,7 @@ struct BlockPlan {
     float *zf, *zp, *z1, *z2, *z3, *out;
     void *r0, *a1, *a2;
     int* argrow;
+    unsigned char *mask, *mask_in;
     int head_off;        // column offset in the concatenated head input, -1 if no head
     // backward
     float *d_out, *da2, *da1, *dr0a, *dr0b, *dzp, *du;
@@ -188,6 +189,12 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
         carve_bn(b, B.bn2, B.C);
         carve_bn(b, B.bn3, B.C);
         bool direct0 = c.two_d && k == 0;
+        // interior masks of the two geometries (element-wise kernels skip border rows through them)
+        B.mask = b.take<unsigned char>((size_t)B.g.rows);
+        B.mask_in = direct0 ? nullptr : b.take<unsigned char>((size_t)B.g_in.rows);
+        B.g.mask = B.mask;
+        B.g_in.mask = B.mask_in;
+        B.g_full.mask = B.mask_in;
         B.pk_entry = direct0 ? nullptr : b.take_bytes(packed_weight_bytes(prec, B.entry));
         B.pk1 = b.take_bytes(packed_weight_bytes(prec, B.c1));
         B.pk2 = b.take_bytes(packed_weight_bytes(prec, B.c2));
@@ -265,6 +272,8 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
         max_wgrad = std::max(max_wgrad, simt_wgrad_scratch_bytes(net->lin5));
     }
     max_partials = std::max(max_partials, (size_t)ew_num_blocks(net->g_head) * 3 * net->g_head.Cs);
+    for (int k = 0; k < c.num_blocks; ++k)
+        max_partials = std::max(max_partials, (size_t)256 * 2 * net->blocks[k].g.Cs);   // one record per GEMM CTA
     net->partials = b.take<double>(max_partials);
     net->wgrad_scratch = b.take_bytes(max_wgrad + 256);
     return align_up(b.off, 256);
@@ -304,12 +313,20 @@ double conv_flops(const ConvGeom& c, const Geo& g) { return 2.0 * c.Cin * c.Cout
 const Residual kNoRes = {nullptr, nullptr, nullptr, nullptr};
 const Dropout kNoDrop = {0.f, 0ull};
 
+// finalize a BatchNorm from `nblk` partial records already sitting in net->partials (training) or from the
+// running statistics (eval)
+int bn_finalize_from(fsb_net* net, cudaStream_t s, int nblk, const Geo& g, BnBuf& bn, const float* gamma,
+                     const float* beta, float* rm, float* rv, long long* cnt, int training, int cat) {
+    RUN(cat, 0, bn_finalize(net->partials, nblk, g.pixels, gamma, beta, rm, rv, cnt, training, bn.C, bn.Cs, bn.scale,
+                            bn.shift, bn.mean, bn.invstd, s));
+    return 0;
+}
+
+// stand-alone statistics pass + finalize
 int bn_forward_stats(fsb_net* net, cudaStream_t s, const float* x, const Geo& g, BnBuf& bn, const float* gamma,
                      const float* beta, float* rm, float* rv, long long* cnt, int training, int cat) {
     if (training) RUN(cat, 0, pf_stats(x, g, net->partials, s));
-    RUN(cat, 0, bn_finalize(net->partials, ew_num_blocks(g), g.pixels, gamma, beta, rm, rv, cnt, training, bn.C,
-                            bn.Cs, bn.scale, bn.shift, bn.mean, bn.invstd, s));
-    return 0;
+    return bn_finalize_from(net, s, ew_num_blocks(g), g, bn, gamma, beta, rm, rv, cnt, training, cat);
 }
 
 }  // namespace
@@ -392,6 +409,10 @@ static int bind(fsb_net* net, void* ws, size_t ws_bytes, int n, int t, int train
     // kernels (interior-only writers) then preserve for the lifetime of the binding
     FSB_CUDA(cudaMemsetAsync(ws, 0, need, s));
     const fsb_net_config& c = net->cfg;
+    for (BlockPlan& B : net->blocks) {
+        FSB_TRY(pf_build_mask(B.g, B.mask, s));
+        if (B.mask_in) FSB_TRY(pf_build_mask(B.g_in, B.mask_in, s));
+    }
     FSB_TRY(fsb_feat_init_tables(c.n_fft, net->feat_tables, s));
     if (c.feat_mode == 2) {
         FSB_CUDA(cudaMemcpyAsync(net->d_fb_vals, net->fb_vals.data(), net->fb_vals.size() * 4, cudaMemcpyHostToDevice, s));
@@ -416,9 +437,11 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
     net->ev_used = 0;
     net->dropout_seed = dropout_seed;
     const int frames = net->frames;
+    int carried_nblk = 0;      // partial records left in net->partials by the previous block's last pass
 
     for (int k = 0; k < c.num_blocks; ++k) {
         BlockPlan& B = net->blocks[k];
+        bool zp_stats_ready = false;
         const float* const* P = params + (size_t)k * P_PER_BLOCK;
         float* const* RM = bn_mean + (size_t)k * B_PER_BLOCK;
         float* const* RV = bn_var + (size_t)k * B_PER_BLOCK;
@@ -449,36 +472,57 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
                                                   c.n_features, net->d_fb_vals, net->d_fb_off, net->d_fb_start,
                                                   net->d_fb_len, net->feat_tables, dst,
                                                   (long long)B.g_in.Hp * B.g_in.Wp * B.g_in.Cs, 1, B.g_in.Cs, s));
+                FSB_TRY(bn_forward_stats(net, s, B.x_in, B.g_in, B.bn_in, P[P_BNIN_W], P[P_BNIN_B], RM[B_IN], RV[B_IN],
+                                         cnt(B_IN), training, CAT_ELT_FWD));
+            } else {
+                // statistics of the block input were gathered by the previous block's last element-wise pass
+                FSB_TRY(bn_finalize_from(net, s, carried_nblk, B.g_in, B.bn_in, P[P_BNIN_W], P[P_BNIN_B], RM[B_IN],
+                                         RV[B_IN], cnt(B_IN), training, CAT_ELT_FWD));
             }
-            FSB_TRY(bn_forward_stats(net, s, B.x_in, B.g_in, B.bn_in, P[P_BNIN_W], P[P_BNIN_B], RM[B_IN], RV[B_IN],
-                                     cnt(B_IN), training, CAT_ELT_FWD));
             RUN(CAT_ELT_FWD, 0, bn_act_forward(B.x_in, B.g_in, B.bn_in.coef(nullptr), kNoRes, kNoDrop, B.u, fmt,
-                                               nullptr, s));
+                                               nullptr, nullptr, s));
             RUN(CAT_PACK, 0, pack_weights(prec, P[P_CONV_W], P[P_CONV_B], B.entry, B.pk_entry, s));
-            RUN(CAT_GEMM_FWD, conv_flops(B.entry, B.g_in), conv_gemm_fwd(prec, B.u, B.pk_entry, B.zf, B.entry, s));
-            RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1, s));
+            RUN(CAT_GEMM_FWD, conv_flops(B.entry, B.g_in),
+                conv_gemm_fwd(prec, B.u, B.pk_entry, B.zf, B.entry, nullptr, s));
+            RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1,
+                                                training ? net->partials : nullptr, s));
+            zp_stats_ready = true;
         }
         // BN_a + PReLU_a -> r0
-        FSB_TRY(bn_forward_stats(net, s, B.zp, B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A], cnt(B_A),
-                                 training, CAT_ELT_FWD));
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.zp, B.g, B.bn_a.coef(P[P_PRELUA]), kNoRes, kNoDrop, B.r0, fmt, nullptr, s));
-        // resnet block
+        if (zp_stats_ready)
+            FSB_TRY(bn_finalize_from(net, s, ew_num_blocks(B.g), B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A],
+                                     cnt(B_A), training, CAT_ELT_FWD));
+        else
+            FSB_TRY(bn_forward_stats(net, s, B.zp, B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A], cnt(B_A),
+                                     training, CAT_ELT_FWD));
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.zp, B.g, B.bn_a.coef(P[P_PRELUA]), kNoRes, kNoDrop, B.r0, fmt, nullptr,
+                                           nullptr, s));
+        // resnet block: every conv GEMM gathers the batch statistics of its output in the epilogue
         RUN(CAT_PACK, 0, pack_weights(prec, P[P_C1_W], P[P_C1_B], B.c1, B.pk1, s));
         RUN(CAT_PACK, 0, pack_weights(prec, P[P_C2_W], P[P_C2_B], B.c2, B.pk2, s));
         RUN(CAT_PACK, 0, pack_weights(prec, P[P_C3_W], P[P_C3_B], B.c3, B.pk3, s));
-        RUN(CAT_GEMM_FWD, conv_flops(B.c1, B.g), conv_gemm_fwd(prec, B.r0, B.pk1, B.z1, B.c1, s));
-        FSB_TRY(bn_forward_stats(net, s, B.z1, B.g, B.bn1, P[P_BN1_W], P[P_BN1_B], RM[B_1], RV[B_1], cnt(B_1),
-                                 training, CAT_ELT_FWD));
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z1, B.g, B.bn1.coef(P[P_PRELU1]), kNoRes, kNoDrop, B.a1, fmt, nullptr, s));
-        RUN(CAT_GEMM_FWD, conv_flops(B.c2, B.g), conv_gemm_fwd(prec, B.a1, B.pk2, B.z2, B.c2, s));
-        FSB_TRY(bn_forward_stats(net, s, B.z2, B.g, B.bn2, P[P_BN2_W], P[P_BN2_B], RM[B_2], RV[B_2], cnt(B_2),
-                                 training, CAT_ELT_FWD));
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z2, B.g, B.bn2.coef(P[P_PRELU2]), kNoRes, kNoDrop, B.a2, fmt, nullptr, s));
-        RUN(CAT_GEMM_FWD, conv_flops(B.c3, B.g), conv_gemm_fwd(prec, B.a2, B.pk3, B.z3, B.c3, s));
-        FSB_TRY(bn_forward_stats(net, s, B.z3, B.g, B.bn3, P[P_BN3_W], P[P_BN3_B], RM[B_3], RV[B_3], cnt(B_3),
-                                 training, CAT_ELT_FWD));
+        int nblk = 0;
+        FwdStats st = {net->partials, &B.g, &nblk};
+        const FwdStats* stp = training ? &st : nullptr;
+        RUN(CAT_GEMM_FWD, conv_flops(B.c1, B.g), conv_gemm_fwd(prec, B.r0, B.pk1, B.z1, B.c1, stp, s));
+        FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn1, P[P_BN1_W], P[P_BN1_B], RM[B_1], RV[B_1], cnt(B_1), training,
+                                 CAT_ELT_FWD));
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z1, B.g, B.bn1.coef(P[P_PRELU1]), kNoRes, kNoDrop, B.a1, fmt, nullptr,
+                                           nullptr, s));
+        RUN(CAT_GEMM_FWD, conv_flops(B.c2, B.g), conv_gemm_fwd(prec, B.a1, B.pk2, B.z2, B.c2, stp, s));
+        FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn2, P[P_BN2_W], P[P_BN2_B], RM[B_2], RV[B_2], cnt(B_2), training,
+                                 CAT_ELT_FWD));
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z2, B.g, B.bn2.coef(P[P_PRELU2]), kNoRes, kNoDrop, B.a2, fmt, nullptr,
+                                           nullptr, s));
+        RUN(CAT_GEMM_FWD, conv_flops(B.c3, B.g), conv_gemm_fwd(prec, B.a2, B.pk3, B.z3, B.c3, stp, s));
+        FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn3, P[P_BN3_W], P[P_BN3_B], RM[B_3], RV[B_3], cnt(B_3), training,
+                                 CAT_ELT_FWD));
         Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z3, B.g, B.bn3.coef(P[P_PRELU3]), res, kNoDrop, nullptr, fmt, B.out, s));
+        // the block output feeds the next block's input BatchNorm: gather its statistics here
+        const bool next_stats = training && k + 1 < c.num_blocks;
+        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z3, B.g, B.bn3.coef(P[P_PRELU3]), res, kNoDrop, nullptr, fmt, B.out,
+                                           next_stats ? net->partials : nullptr, s));
+        carried_nblk = ew_num_blocks(B.g);
         if (B.head_off >= 0)
             RUN(CAT_ELT_FWD, 0, gmax_forward(B.out, B.g, net->feats, net->Ds, B.head_off, B.argrow, s));
     }
@@ -492,7 +536,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
         FSB_TRY(bn_forward_stats(net, s, net->feats, net->g_head, net->hbn0, P[H_BN0_W], P[H_BN0_B], RM[0], RV[0],
                                  CT ? CT[0] : nullptr, training, CAT_HEAD));
         RUN(CAT_HEAD, 0, bn_act_forward(net->feats, net->g_head, net->hbn0.coef(nullptr), kNoRes, kNoDrop, nullptr,
-                                        FMT_F32, net->h0, s));
+                                        FMT_F32, net->h0, nullptr, s));
         RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L1_W], P[H_L1_B], net->lin1, net->pk_l1, s));
         RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L5_W], P[H_L5_B], net->lin5, net->pk_l5, s));
         RUN(CAT_HEAD, 0, simt_fwd(net->h0, net->pk_l1, net->z1h, net->lin1, s));
@@ -500,7 +544,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
                                  CT ? CT[1] : nullptr, training, CAT_HEAD));
         Dropout dr = {training ? c.dropout_p : 0.f, dropout_seed};
         RUN(CAT_HEAD, 0, bn_act_forward(net->z1h, net->g_head, net->hbn2.coef(P[H_PRELU]), kNoRes, dr, nullptr,
-                                        FMT_F32, net->h1, s));
+                                        FMT_F32, net->h1, nullptr, s));
         RUN(CAT_HEAD, 0, simt_fwd(net->h1, net->pk_l5, net->zl, net->lin5, s));
         RUN(CAT_HEAD, 0, copy2d(net->zl, n, c.n_classes, net->CsCls, logits, c.n_classes, s));
     }
@@ -701,7 +745,7 @@ extern "C" int fsb_conv_forward(const float* x, const float* w, const float* b, 
     FSB_CUDA(cudaMemsetAsync(A, 0, plane_bytes(gi), s));
     FSB_TRY(nchw_to_pf(x, gi, A, fmt, s));
     FSB_TRY(pack_weights(precision, w, b, c, pk, s));
-    FSB_TRY(conv_gemm_fwd(precision, A, pk, Z, c, s));
+    FSB_TRY(conv_gemm_fwd(precision, A, pk, Z, c, nullptr, s));
     return pf_to_nchw(Z, go, y, s);
 }
 
