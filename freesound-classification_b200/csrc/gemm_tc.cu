@@ -122,6 +122,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // shared-memory matrix descriptor (SWIZZLE_128B; sm_100 descriptor version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
     uint64_t d = 0;
@@ -137,31 +152,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// Column sums of a 32 x 16 register tile (one row per lane, 16 columns per lane) by recursive halving:
-// 16 shuffles; afterwards lanes 2j and 2j+1 both hold the total of column j = (lane >> 1) & 15.
-__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
-    float a[8], b[4], c[2];
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
-        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h8 ? a[i] : a[i + 4], keep = h8 ? a[i + 4] : a[i];
-        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h4 ? b[i] : b[i + 2], keep = h4 ? b[i + 2] : b[i];
-        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    const float send = h2 ? c[0] : c[1], keep = h2 ? c[1] : c[0];
-    const float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    return d + __shfl_xor_sync(0xffffffffu, d, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -205,7 +195,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bW_full = bA_empty + 8u * p.nA, bW_empty = bW_full + 8u * p.nW;
     const uint32_t bT_full = bW_empty + 8u * p.nW, bT_empty = bT_full + 16u;
     const uint32_t tmem_slot = bT_empty + 16u;
-    double* stat_acc = reinterpret_cast<double*>(smem_raw + (bars - smem_u32(smem_raw)) + 256u);   // [2][ldz]
+    // epilogue scratch after the barriers: staging panel [128 rows][32 floats] (16-byte chunks XOR-swizzled
+    // by row & 7), interior bits of the tile's rows, bias [ldz], statistics accumulators [2][ldz] doubles
+    unsigned char* epi = smem_raw + (bars - smem_u32(smem_raw)) + 256u;
+    float4* stg = reinterpret_cast<float4*>(epi);
+    uint32_t* tile_mask = reinterpret_cast<uint32_t*>(epi + 16384);
+    float* bias_s = reinterpret_cast<float*>(epi + 16384 + 16);
+    double* stat_acc = reinterpret_cast<double*>(epi + 16384 + 16 + (((size_t)p.ldz * 4 + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < p.ldz; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
@@ -305,52 +302,94 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> global =====================
+        // ============ epilogue: TMEM -> registers -> swizzled smem panel -> coalesced global stores ============
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int rl = q * 32 + lane;              // this thread's row within the tile
+        const int npanels = (p.BN + 31) / 32;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const uint32_t buf = it & 1u, use = it >> 1;
+            const long long m0 = (long long)mt * BM;
+            if (p.stats) {
+                const long long row = m0 + rl;
+                bool interior = false;
+                if (row < p.rows) {
+                    const int rr = (int)(row % ((long long)p.Hp * p.Wp));
+                    const int yy = rr / p.Wp, xx = rr - yy * p.Wp;
+                    interior = yy >= p.padH && yy < p.padH + p.H && xx >= p.padW && xx < p.padW + p.W;
+                }
+                const uint32_t bits = __ballot_sync(0xffffffffu, interior);
+                if (lane == 0) tile_mask[q] = bits;
+            }
             mbar_wait(bT_full + 8u * buf, use & 1u);
             tc_fence_after();
-            const long long row = (long long)mt * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
-            float* zrow = p.Z + row * p.ldz;
-            float interior = 0.f;
-            if (p.stats && row < p.rows) {
-                const int rr = (int)(row % ((long long)p.Hp * p.Wp));
-                const int yy = rr / p.Wp, xx = rr - yy * p.Wp;
-                interior = (yy >= p.padH && yy < p.padH + p.H && xx >= p.padW && xx < p.padW + p.W) ? 1.f : 0.f;
-            }
-            for (int c = 0; c < p.BN; c += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)c, v);
-                const int n = nt * p.BN + c;
-                if (n < p.ldz) {                       // warp-uniform
-                    if (p.bias) {
+            for (int pn = 0; pn < npanels; ++pn) {
+                const int cols = p.BN - pn * 32 >= 32 ? 32 : 16;       // BN is a multiple of 16
+                const int n = nt * p.BN + pn * 32;                      // first global column of the panel
+                float v[32];
+                if (cols == 32) {
+                    tmem_ld32(taddr + (uint32_t)(pn * 32), v);
+                } else {
+                    tmem_ld16(taddr + (uint32_t)(pn * 32), v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
-                    }
-                    if (row < p.rows) {
+                    for (int i = 16; i < 32; ++i) v[i] = 0.f;
+                }
+                if (pn == npanels - 1) {           // accumulator drained: hand the TMEM buffer back early
+                    tc_fence_before();
+                    mbar_arrive(bT_empty + 8u * buf);
+                }
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(zrow + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int j = 0; j < 8; ++j) {
+                    const int cg = n + 4 * j;
+                    float4 o;
+                    if (cg < p.ldz && 4 * j < cols) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cg);
+                        o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+                    } else {
+                        o = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    if (p.stats) {
-                        float sq[16];
+                    stg[rl * 8 + (j ^ (rl & 7))] = o;
+                }
+                if (p.stats) asm volatile("bar.sync 1, 128;" ::: "memory");
+                else __syncwarp();
+                // this warp's 32 rows, 4 rows x 128 contiguous bytes per store instruction
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { v[i] *= interior; sq[i] = v[i] * v[i]; }
-                        const float s1 = warp_colsum16(v, lane), s2 = warp_colsum16(sq, lane);
-                        if ((lane & 1) == 0) {
-                            const int col = n + ((lane >> 1) & 15);
-                            atomicAdd(stat_acc + col, (double)s1);
-                            atomicAdd(stat_acc + p.ldz + col, (double)s2);
-                        }
+                for (int i = 0; i < 8; ++i) {
+                    const int r = q * 32 + 4 * i + (lane >> 3), j = lane & 7;
+                    const float4 o = stg[r * 8 + (j ^ (r & 7))];
+                    const long long grow = m0 + r;
+                    const int cg = n + 4 * j;
+                    if (grow < p.rows && cg < p.ldz && 4 * j < cols) *reinterpret_cast<float4*>(p.Z + grow * p.ldz + cg) = o;
+                }
+                if (p.stats) {
+                    // column sums over the 128 rows: warp q owns columns 8q..8q+7, lane>>3 selects a 32-row quarter
+                    const int cl = 8 * q + (lane & 7), rq = lane >> 3;
+                    const uint32_t bits = tile_mask[rq];
+                    const float* stf = reinterpret_cast<const float*>(stg);
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) {
+                        const int rr = (i + 2 * rq) & 31;              // staggered: conflict-free across quarters
+                        const int r = 32 * rq + rr;
+                        const float x = stf[r * 32 + (((cl >> 2) ^ (r & 7)) << 2) + (cl & 3)];
+                        if ((bits >> rr) & 1u) { s1 += x; s2 = fmaf(x, x, s2); }
                     }
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                    const int cg = n + cl;
+                    if (lane < 8 && cg < p.ldz && cl < cols) {          // unique owner of this column: no atomics
+                        stat_acc[cg] += (double)s1;
+                        stat_acc[p.ldz + cg] += (double)s2;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");     // panel fully consumed
+                } else {
+                    __syncwarp();
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bT_empty + 8u * buf);
         }
         if (p.stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
@@ -705,7 +744,8 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
         p.stats = st->partials;
         p.Hp = g.Hp; p.Wp = g.Wp; p.H = g.H; p.W = g.W; p.padH = g.padH; p.padW = g.padW;
     }
-    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (st ? (size_t)16 * ldz : 0) /*statistics*/;
+    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + 16384 + 16 /*staging panel, tile mask*/ +
+                         (((size_t)ldz * 4 + 15) & ~(size_t)15) /*bias*/ + (size_t)16 * ldz /*statistics*/;
     // ring depths: at least 2 each; give W the stages it needs to cover one A stage, then grow both
     p.nA = 2; p.nW = 2;
     for (;;) {
@@ -777,7 +817,7 @@ static void wgrad_shape(const ConvGeom& c, int& ngroups, int& tpg, int& co_tiles
     ci_tiles = (c.CsIn + WG_BN - 1) / WG_BN;
     const int items = ngroups * co_tiles * ci_tiles;
     long long chunks = (c.rows + WG_R - 1) / WG_R;
-    int want = (2 * 148 + items - 1) / items;           // about two waves of CTAs
+    int want = (2 * num_sms()) / items;                 // at most two full waves (one CTA per SM at a time)
     if (want > chunks) want = (int)chunks;
     if (want > 128) want = 128;
     if (want < 1) want = 1;
