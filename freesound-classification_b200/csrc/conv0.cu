@@ -207,39 +207,39 @@ conv0_bwd_kernel(const float* __restrict__ feat, int N, int H, int W, const floa
     }
 }
 
-__global__ void conv0_bwd_finalize_kernel(const float* partials, int nblk, Geo gp, float* dw, float* db) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int ndw = gp.C * 18;
-    if (i < ndw) {
-        int c = i / 18, k = i % 18;
-        double s = 0.0;
-        for (int b = 0; b < nblk; ++b) s += partials[((long long)b * C0B_REC + k) * gp.Cs + c];
-        dw[i] = (float)s;
-    } else if (i < ndw + gp.C) {
-        db[i - ndw] = 0.f;   // conv bias feeds a batch-statistics BN: analytically zero gradient
-    }
-}
-
-// one block per BN_in term (dgamma[0], dgamma[1], dbeta[0], dbeta[1]): sum over blocks and channels
-__global__ void __launch_bounds__(256)
-conv0_bwd_bn_kernel(const float* partials, int nblk, Geo gp, float* dgamma_in, float* dbeta_in) {
-    const int k = 18 + blockIdx.x;
-    double s = 0.0;
-    long long total = (long long)nblk * gp.C;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-        int b = (int)(e / gp.C), c = (int)(e % gp.C);
-        s += partials[((long long)b * C0B_REC + k) * gp.Cs + c];
-    }
-    __shared__ double red[256];
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int st = 128; st > 0; st >>= 1) {
-        if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+// One CTA per record k (18 dW taps, 2 dgamma terms, 2 dbeta terms): 32 channels x 32 slices of the per-block
+// partials are summed at a time in a fixed order (deterministic); records 18..21 are then summed over channels.
+__global__ void __launch_bounds__(1024)
+conv0_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, Geo gp, float* dw, float* db, float* dgamma_in,
+                          float* dbeta_in) {
+    __shared__ double red[32][33];
+    __shared__ double tot[512];
+    const int k = blockIdx.x;
+    const int slice = threadIdx.x >> 5, cl = threadIdx.x & 31;
+    for (int c0 = 0; c0 < gp.Cs; c0 += 32) {
+        const int c = c0 + cl;
+        double acc = 0.0;
+        if (c < gp.C) {
+#pragma unroll 8
+            for (int b = slice; b < nblk; b += 32) acc += (double)partials[((long long)b * C0B_REC + k) * gp.Cs + c];
+        }
+        red[slice][cl] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t += red[j][cl];
+            if (c < 512) tot[c] = t;
+            if (k < 18 && c < gp.C) dw[c * 18 + k] = (float)t;
+            if (k == 0 && c < gp.C) db[c] = 0.f;   // conv bias feeds a batch-statistics BN: analytically zero gradient
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        if (blockIdx.x < 2) dgamma_in[blockIdx.x] = (float)red[0];
-        else dbeta_in[blockIdx.x - 2] = (float)red[0];
+    if (k >= 18 && threadIdx.x == 0) {
+        double t = 0.0;
+        for (int c = 0; c < gp.C; ++c) t += tot[c];
+        if (k < 20) dgamma_in[k - 18] = (float)t;
+        else dbeta_in[k - 20] = (float)t;
     }
 }
 
@@ -249,10 +249,8 @@ int conv0_backward(const float* feat, int N, int H, int W, const float* scale, c
     conv0_bwd_kernel<<<C0B_BLOCKS, C0_THREADS, 0, s>>>(feat, N, H, W, scale, shift, mean, invstd, w, b, dzp, gp,
                                                        (float*)scratch);
     FSB_LAUNCHED();
-    int total = gp.C * 18 + gp.C;
-    conv0_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>((const float*)scratch, C0B_BLOCKS, gp, dw, db);
-    FSB_LAUNCHED();
-    conv0_bwd_bn_kernel<<<4, 256, 0, s>>>((const float*)scratch, C0B_BLOCKS, gp, dgamma_in, dbeta_in);
+    FSB_REQUIRE(gp.Cs <= 512, "conv0: at most 512 output channels");
+    conv0_bwd_finalize_kernel<<<C0B_REC, 1024, 0, s>>>((const float*)scratch, C0B_BLOCKS, gp, dw, db, dgamma_in, dbeta_in);
     FSB_LAUNCHED();
     return 0;
 }

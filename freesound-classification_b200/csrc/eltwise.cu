@@ -45,6 +45,18 @@ int ew_num_blocks(const Geo& g) { return (int)ew_shape(g).grid.x; }
          row += (long long)gridDim.x * blockDim.y)                                            \
         if (g.mask == nullptr || g.mask[row])
 
+// Same walk, two rows per iteration: the loads of both rows are issued before either is consumed (twice the
+// bytes in flight per thread; the streaming kernels are latency-bound otherwise).  okA / okB: row is interior.
+#define EW_PIXEL_LOOP2                                                                                  \
+    const long long ew_stride = (long long)gridDim.x * blockDim.y;                                      \
+    for (long long rowA = (long long)blockIdx.x * blockDim.y + threadIdx.y; rowA < g.rows;              \
+         rowA += 2 * ew_stride)                                                                          \
+        for (bool ew_once = true; ew_once;)                                                              \
+            for (const long long rowB = rowA + ew_stride; ew_once;)                                      \
+                for (const bool okA = g.mask == nullptr || g.mask[rowA],                                 \
+                                okB = rowB < g.rows && (g.mask == nullptr || g.mask[rowB]);              \
+                     ew_once; ew_once = false)
+
 // interior mask of a padded-flat geometry
 __global__ void interior_mask_kernel(Geo g, unsigned char* mask) {
     for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < g.rows;
@@ -202,20 +214,23 @@ int pf_stats(const float* x, const Geo& g, double* partials, cudaStream_t s) {
     return 0;
 }
 
-// Fixed-order parallel reduction of per-block partial sums: 32 channels x 8 slices per CTA; every slice
-// walks the blocks b = slice, slice + 8, ... and the 8 slice totals are added in slice order, so the
+// Fixed-order parallel reduction of per-block partial sums: 32 channels x 32 slices per CTA (1024 threads); every
+// slice walks the blocks b = slice, slice + 32, ... and the 32 slice totals are added in slice order, so the
 // result does not depend on scheduling (deterministic).
+constexpr int FIN_SLICES = 32;
+constexpr int FIN_THREADS = 32 * FIN_SLICES;
+
 template <int K>
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int nblk, int Cs, int c,
                                                 double (&out)[K]) {
-    __shared__ double red[K][8][32];
+    __shared__ double red[K][FIN_SLICES][32];
     const int slice = threadIdx.x >> 5, cl = threadIdx.x & 31;
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
     if (c < Cs) {
-#pragma unroll 4
-        for (int b = slice; b < nblk; b += 8) {
+#pragma unroll 8
+        for (int b = slice; b < nblk; b += FIN_SLICES) {
 #pragma unroll
             for (int k = 0; k < K; ++k) acc[k] += partials[((long long)b * K + k) * Cs + c];
         }
@@ -226,13 +241,15 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double t = 0.0;
+        if (threadIdx.x < 32) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t += red[k][j][cl];
+            for (int j = 0; j < FIN_SLICES; ++j) t += red[k][j][cl];
+        }
         out[k] = t;
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FIN_THREADS)
 bn_finalize_kernel(const double* partials, int nblk, long long count, const float* gamma,
                    const float* beta, float* run_mean, float* run_var, long long* bn_count,
                    int training, int C, int Cs, float* scale, float* shift, float* mean,
@@ -275,7 +292,7 @@ bn_finalize_kernel(const double* partials, int nblk, long long count, const floa
 int bn_finalize(const double* partials, int nblk, long long count, const float* gamma, const float* beta,
                 float* run_mean, float* run_var, long long* bn_count, int training, int C, int Cs,
                 float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
-    bn_finalize_kernel<<<(Cs + 31) / 32, 256, 0, s>>>(partials, nblk, count, gamma, beta, run_mean,
+    bn_finalize_kernel<<<(Cs + 31) / 32, FIN_THREADS, 0, s>>>(partials, nblk, count, gamma, beta, run_mean,
                                                      run_var, bn_count, training, C, Cs, scale, shift,
                                                      mean, invstd);
     FSB_LAUNCHED();
@@ -336,6 +353,33 @@ __device__ __forceinline__ Coef4 load_coef(const float* scale, const float* shif
     return c;
 }
 
+struct FwdIn {
+    float4 z, r;
+};
+
+__device__ __forceinline__ FwdIn fwd_load(const float* z, const float* zr, long long idx) {
+    FwdIn in;
+    in.z = ld4(z + idx);
+    in.r = zr ? ld4(zr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return in;
+}
+
+__device__ __forceinline__ float4 fwd_compute(const FwdIn& in, const Coef4& cb, const Coef4& cr, bool has_res,
+                                              const Dropout& dr, long long idx) {
+    float4 v = affine4(in.z, cb.sc, cb.sh);
+    if (has_res) {
+        float4 r = affine4(in.r, cr.sc, cr.sh);
+        if (cr.has_sl) r = prelu4(r, cr.sl);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (cb.has_sl) v = prelu4(v, cb.sl);
+    if (dr.p > 0.f) {
+        v.x *= keep_scale(dr, idx); v.y *= keep_scale(dr, idx + 1);
+        v.z *= keep_scale(dr, idx + 2); v.w *= keep_scale(dr, idx + 3);
+    }
+    return v;
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr, void* a_mma,
@@ -346,27 +390,32 @@ bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, D
     if (STATS) { acc[0].init(); acc[1].init(); }
     if (cok) {
         Coef4 cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
-        Coef4 cr;
-        if (res.zr) cr = load_coef(res.scale, res.shift, res.slope, c0);
+        Coef4 cr = cb;
+        const bool has_res = res.zr != nullptr;
+        if (has_res) cr = load_coef(res.scale, res.shift, res.slope, c0);
         const long long plane = g.rows * g.Cs;
-        EW_PIXEL_LOOP {
-            long long idx = row * g.Cs + c0;
-            float4 v = affine4(ld4(z + idx), cb.sc, cb.sh);
-            if (res.zr) {
-                float4 r = affine4(ld4(res.zr + idx), cr.sc, cr.sh);
-                if (cr.has_sl) r = prelu4(r, cr.sl);
-                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        EW_PIXEL_LOOP2 {
+            const long long idxA = rowA * g.Cs + c0, idxB = rowB * g.Cs + c0;
+            FwdIn inA, inB;
+            if (okA) inA = fwd_load(z, res.zr, idxA);
+            if (okB) inB = fwd_load(z, res.zr, idxB);
+            if (okA) {
+                float4 v = fwd_compute(inA, cb, cr, has_res, dr, idxA);
+                if (a_f32) st4(a_f32 + idxA, v);
+                if (a_mma) store_fmt(a_mma, fmt, plane, idxA, v);
+                if (STATS) {
+                    acc[0].add(v);
+                    acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
+                }
             }
-            if (cb.has_sl) v = prelu4(v, cb.sl);
-            if (dr.p > 0.f) {
-                v.x *= keep_scale(dr, idx); v.y *= keep_scale(dr, idx + 1);
-                v.z *= keep_scale(dr, idx + 2); v.w *= keep_scale(dr, idx + 3);
-            }
-            if (a_f32) st4(a_f32 + idx, v);
-            if (a_mma) store_fmt(a_mma, fmt, plane, idx, v);
-            if (STATS) {
-                acc[0].add(v);
-                acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
+            if (okB) {
+                float4 v = fwd_compute(inB, cb, cr, has_res, dr, idxB);
+                if (a_f32) st4(a_f32 + idxB, v);
+                if (a_mma) store_fmt(a_mma, fmt, plane, idxB, v);
+                if (STATS) {
+                    acc[0].add(v);
+                    acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
+                }
             }
         }
     }
@@ -483,9 +532,18 @@ int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo
 }
 
 // ---------------------------------------------------------------------------------------------
-// global max: grid (channel chunks, N); block (bx cvec, by pixels)
+// global max: grid (channel chunks, N, pixel slices); block (bx cvec, by pixels).  Every CTA reduces its slice of
+// the image and merges into packed[n][c] with a 64-bit atomicMax of (ordered value bits << 32 | ~row): the winner is
+// the largest value and, among equal values, the smallest row -- the first maximum in scan order, independent
+// of scheduling.  A second tiny kernel unpacks value and row.
+__device__ __forceinline__ unsigned long long gmax_pack(float v, int row) {
+    unsigned u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
+}
+
 __global__ void __launch_bounds__(256)
-gmax_fwd_kernel(const float* __restrict__ x, Geo g, float* feat, int feat_stride, int feat_off, int* argrow) {
+gmax_fwd_kernel(const float* __restrict__ x, Geo g, unsigned long long* packed) {
     const int cv = blockIdx.x * blockDim.x + threadIdx.x;
     const bool cok = cv < g.Cs / 4;
     const int c0 = cv * 4;
@@ -493,8 +551,10 @@ gmax_fwd_kernel(const float* __restrict__ x, Geo g, float* feat, int feat_stride
     float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int bi[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
     const int hw = g.H * g.W;
+    const int per = (hw + gridDim.z - 1) / gridDim.z;
+    const int p_begin = blockIdx.z * per, p_end = min(hw, p_begin + per);
     if (cok) {
-        for (int p = threadIdx.y; p < hw; p += blockDim.y) {
+        for (int p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
             int yy = p / g.W, xx = p - yy * g.W;
             long long row = geo_row(g, n, yy, xx);
             float4 v4 = ld4(x + row * g.Cs + c0);
@@ -520,21 +580,44 @@ gmax_fwd_kernel(const float* __restrict__ x, Geo g, float* feat, int feat_stride
                 if (sv[tt] > b || (sv[tt] == b && si[tt] < r)) { b = sv[tt]; r = si[tt]; }
             }
             int c = c0 + i;
-            if (c < g.C) {
-                feat[(long long)n * feat_stride + feat_off + c] = b;
-                argrow[(long long)n * g.C + c] = r;
-            }
+            if (c < g.C && r != 0x7fffffff) atomicMax(packed + (long long)n * g.Cs + c, gmax_pack(b, r));
         }
     }
 }
 
-int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int feat_off, int* argrow,
+__global__ void gmax_unpack_kernel(const unsigned long long* __restrict__ packed, Geo g, float* feat, int feat_stride,
+                                   int feat_off, int* argrow) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)g.N * g.C) return;
+    int n = (int)(i / g.C), c = (int)(i % g.C);
+    unsigned long long pk = packed[(long long)n * g.Cs + c];
+    unsigned u = (unsigned)(pk >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    feat[(long long)n * feat_stride + feat_off + c] = __uint_as_float(u);
+    argrow[i] = (int)(0xFFFFFFFFu - (unsigned)(pk & 0xFFFFFFFFull));
+}
+
+size_t gmax_scratch_bytes(const Geo& g) { return (size_t)g.N * g.Cs * sizeof(unsigned long long); }
+
+int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int feat_off, int* argrow, void* scratch,
                  cudaStream_t s) {
     int cv = g.Cs / 4;
     int bx = cv < 32 ? cv : 32;
     int by = 256 / bx;
-    dim3 grid((cv + bx - 1) / bx, g.N);
-    gmax_fwd_kernel<<<grid, dim3(bx, by), 0, s>>>(x, g, feat, feat_stride, feat_off, argrow);
+    int chunks = (cv + bx - 1) / bx;
+    // enough pixel slices for ~4 CTAs per SM, at least `by` pixels per slice
+    int hw = g.H * g.W;
+    int slices = (4 * 148 + chunks * g.N - 1) / (chunks * g.N);
+    if (slices > (hw + 4 * by - 1) / (4 * by)) slices = (hw + 4 * by - 1) / (4 * by);
+    if (slices < 1) slices = 1;
+    if (slices > 65535) slices = 65535;
+    FSB_CUDA(cudaMemsetAsync(scratch, 0, gmax_scratch_bytes(g), s));
+    dim3 grid(chunks, g.N, slices);
+    gmax_fwd_kernel<<<grid, dim3(bx, by), 0, s>>>(x, g, (unsigned long long*)scratch);
+    FSB_LAUNCHED();
+    long long total = (long long)g.N * g.C;
+    gmax_unpack_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>((const unsigned long long*)scratch, g, feat, feat_stride,
+                                                                  feat_off, argrow);
     FSB_LAUNCHED();
     return 0;
 }
@@ -564,21 +647,34 @@ struct BwdCoef {
     bool has_res;
 };
 
-__device__ __forceinline__ void bwd_point(const float* dA1, const float* dA2, const float* z, const Residual& res,
-                                          const BwdCoef& k, const Dropout& dr, long long idx, float4& dy,
-                                          float4& zhat, float4& dsl) {
-    float4 zz = ld4(z + idx);
+struct BwdIn {
+    float4 z, r, g, g2;
+};
+
+// RES: the activation has a residual branch (res.zr); DA2: the incoming gradient is dA1 + dA2
+template <bool RES, bool DA2>
+__device__ __forceinline__ BwdIn bwd_load(const float* dA1, const float* dA2, const float* z, const float* zr,
+                                          long long idx) {
+    BwdIn in;
+    in.z = ld4(z + idx);
+    in.g = ld4(dA1 + idx);
+    if (RES) in.r = ld4(zr + idx);
+    if (DA2) in.g2 = ld4(dA2 + idx);
+    return in;
+}
+
+template <bool RES, bool DA2>
+__device__ __forceinline__ void bwd_compute(const BwdIn& in, const BwdCoef& k, const Dropout& dr, long long idx,
+                                            float4& dy, float4& zhat, float4& dsl) {
+    const float4 zz = in.z;
     float4 y = affine4(zz, k.cb.sc, k.cb.sh);
-    if (k.has_res) {
-        float4 r = affine4(ld4(res.zr + idx), k.cr.sc, k.cr.sh);
+    if (RES) {
+        float4 r = affine4(in.r, k.cr.sc, k.cr.sh);
         if (k.cr.has_sl) r = prelu4(r, k.cr.sl);
         y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
     }
-    float4 g = ld4(dA1 + idx);
-    if (dA2) {
-        float4 g2 = ld4(dA2 + idx);
-        g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
-    }
+    float4 g = in.g;
+    if (DA2) { g.x += in.g2.x; g.y += in.g2.y; g.z += in.g2.z; g.w += in.g2.w; }
     if (dr.p > 0.f) {
         g.x *= keep_scale(dr, idx); g.y *= keep_scale(dr, idx + 1);
         g.z *= keep_scale(dr, idx + 2); g.w *= keep_scale(dr, idx + 3);
@@ -596,47 +692,71 @@ __device__ __forceinline__ void bwd_point(const float* dA1, const float* dA2, co
                        (zz.z - k.mean.z) * k.invstd.z, (zz.w - k.mean.w) * k.invstd.w);
 }
 
+template <bool RES>
 __device__ __forceinline__ BwdCoef load_bwd(const BnCoef& bn, const Residual& res, int c0) {
     BwdCoef k;
     k.cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
-    k.has_res = res.zr != nullptr;
-    if (k.has_res) k.cr = load_coef(res.scale, res.shift, res.slope, c0);
+    k.has_res = RES;
+    if (RES) k.cr = load_coef(res.scale, res.shift, res.slope, c0);
     k.mean = ld4(bn.mean + c0);
     k.invstd = ld4(bn.invstd + c0);
     return k;
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void fma4(float4& a, const float4& b, const float4& c) {
+    a.x = fmaf(b.x, c.x, a.x); a.y = fmaf(b.y, c.y, a.y); a.z = fmaf(b.z, c.z, a.z); a.w = fmaf(b.w, c.w, a.w);
+}
+
+// Per-thread float32 partial sums (a thread visits rows / (gridDim.x * blockDim.y) ~ 10^2 pixels); the cross-thread
+// and cross-block reductions run in double.
+template <bool RES, bool DA2>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2,
                          const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr,
                          double* partials) {
     EW_PROLOGUE
-    Acc4 acc[3];
-    acc[0].init(); acc[1].init(); acc[2].init();
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
     if (cok) {
-        BwdCoef k = load_bwd(bn, res, c0);
-        EW_PIXEL_LOOP {
-            long long idx = row * g.Cs + c0;
+        BwdCoef k = load_bwd<RES>(bn, res, c0);
+        EW_PIXEL_LOOP2 {
+            const long long idxA = rowA * g.Cs + c0, idxB = rowB * g.Cs + c0;
+            BwdIn inA, inB;
+            if (okA) inA = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxA);
+            if (okB) inB = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxB);
             float4 dy, zh, dsl;
-            bwd_point(dA1, dA2, z, res, k, dr, idx, dy, zh, dsl);
-            acc[0].add(dy);
-            acc[1].add(make_float4(dy.x * zh.x, dy.y * zh.y, dy.z * zh.z, dy.w * zh.w));
-            acc[2].add(dsl);
+            if (okA) {
+                bwd_compute<RES, DA2>(inA, k, dr, idxA, dy, zh, dsl);
+                add4(s0, dy); fma4(s1, dy, zh); add4(s2, dsl);
+            }
+            if (okB) {
+                bwd_compute<RES, DA2>(inB, k, dr, idxB, dy, zh, dsl);
+                add4(s0, dy); fma4(s1, dy, zh); add4(s2, dsl);
+            }
         }
     }
+    Acc4 acc[3];
+    acc[0].init(); acc[1].init(); acc[2].init();
+    acc[0].f = s0; acc[1].f = s1; acc[2].f = s2;
     block_reduce_store<3>(acc, partials, g.Cs, c0, cok);
 }
 
 int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
                       Dropout dr, double* partials, cudaStream_t s) {
     EW_CHECK(g);
+    FSB_REQUIRE(!(res.zr && dA2), "bn_act_bwd: residual and second gradient are mutually exclusive");
     EwShape sh = ew_shape(g);
-    bn_act_bwd_reduce_kernel<<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
+    if (res.zr)
+        bn_act_bwd_reduce_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
+    else if (dA2)
+        bn_act_bwd_reduce_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
+    else
+        bn_act_bwd_reduce_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
     FSB_LAUNCHED();
     return 0;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FIN_THREADS)
 bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs,
                        float* dgamma, float* dbeta, float* dslope, float* c1, float* c2) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -653,37 +773,57 @@ bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C,
 
 int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, float* dgamma, float* dbeta,
                     float* dslope, float* c1, float* c2, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<(Cs + 31) / 32, 256, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
+    bn_bwd_finalize_kernel<<<(Cs + 31) / 32, FIN_THREADS, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
                                                          c1, c2);
     FSB_LAUNCHED();
     return 0;
 }
 
-__global__ void __launch_bounds__(256)
+template <bool RES, bool DA2>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2, const float* __restrict__ z,
                         Geo g, BnCoef bn, Residual res, Dropout dr, const float* c1, const float* c2, void* dz,
                         int fmt, float* dres) {
     EW_PROLOGUE
     if (!cok) return;
-    BwdCoef k = load_bwd(bn, res, c0);
+    BwdCoef k = load_bwd<RES>(bn, res, c0);
     float4 m1 = ld4(c1 + c0), m2 = ld4(c2 + c0);
     const long long plane = g.rows * g.Cs;
-    EW_PIXEL_LOOP {
-        long long idx = row * g.Cs + c0;
+    EW_PIXEL_LOOP2 {
+        const long long idxA = rowA * g.Cs + c0, idxB = rowB * g.Cs + c0;
+        BwdIn inA, inB;
+        if (okA) inA = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxA);
+        if (okB) inB = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxB);
         float4 dy, zh, dsl;
-        bwd_point(dA1, dA2, z, res, k, dr, idx, dy, zh, dsl);
-        float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
-                               k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
-        store_fmt(dz, fmt, plane, idx, o);
-        if (dres) st4(dres + idx, dy);
+        if (okA) {
+            bwd_compute<RES, DA2>(inA, k, dr, idxA, dy, zh, dsl);
+            float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
+                                   k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
+            store_fmt(dz, fmt, plane, idxA, o);
+            if (RES && dres) st4(dres + idxA, dy);
+        }
+        if (okB) {
+            bwd_compute<RES, DA2>(inB, k, dr, idxB, dy, zh, dsl);
+            float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
+                                   k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
+            store_fmt(dz, fmt, plane, idxB, o);
+            if (RES && dres) st4(dres + idxB, dy);
+        }
     }
 }
 
 int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
                      Dropout dr, const float* c1, const float* c2, void* dz, int fmt, float* dres, cudaStream_t s) {
     EW_CHECK(g);
+    FSB_REQUIRE(!(res.zr && dA2), "bn_act_bwd: residual and second gradient are mutually exclusive");
+    FSB_REQUIRE(res.zr || !dres, "bn_act_bwd: dres needs a residual branch");
     EwShape sh = ew_shape(g);
-    bn_act_bwd_apply_kernel<<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
+    if (res.zr)
+        bn_act_bwd_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
+    else if (dA2)
+        bn_act_bwd_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
+    else
+        bn_act_bwd_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
     FSB_LAUNCHED();
     return 0;
 }

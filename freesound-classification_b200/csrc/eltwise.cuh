@@ -65,7 +65,9 @@ int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo
                      void* dzf, int fmt, cudaStream_t s);
 
 // global max over (H, W) per (n, c): feat[n*feat_stride + feat_off + c], argrow[n*C + c] (padded row)
-int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int feat_off, int* argrow,
+// scratch: gmax_scratch_bytes(g) bytes (packed per-(n, c) atomic-max slots)
+size_t gmax_scratch_bytes(const Geo& g);
+int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int feat_off, int* argrow, void* scratch,
                  cudaStream_t s);
 // dx[argrow, c] += dfeat[n*feat_stride + feat_off + c]
 int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* argrow, const Geo& g,

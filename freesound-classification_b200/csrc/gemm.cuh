@@ -61,6 +61,10 @@ size_t simt_packed_weight_bytes(const ConvGeom& c);
 int simt_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s);
 int simt_fwd(const float* A, const void* packed, float* Z, const ConvGeom& c, cudaStream_t s);
 int simt_dgrad(const float* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
+// split-K variants for linear layers with few rows (the FC head); scratch >= simt_skinny_scratch_bytes(c)
+size_t simt_skinny_scratch_bytes(const ConvGeom& c);
+int simt_skinny_fwd(const float* A, const void* packed, float* Z, const ConvGeom& c, void* scratch, cudaStream_t s);
+int simt_skinny_dgrad(const float* dZ, const void* packed, float* dA, const ConvGeom& c, void* scratch, cudaStream_t s);
 size_t simt_wgrad_scratch_bytes(const ConvGeom& c);
 int simt_wgrad(const float* A, const float* dZ, float* dw, void* scratch, const ConvGeom& c, cudaStream_t s);
 

@@ -47,7 +47,7 @@ struct Taps {
 // Z[r, n] = bias[n] + sum_t sum_k A[r + off_t, k] * W[t][k][n];   128 x 64 tile, 8 x 4 per thread
 __global__ void __launch_bounds__(256)
 simt_gemm_kernel(const float* __restrict__ A, long long rows, int K, Taps taps, const float* __restrict__ W,
-                 const float* __restrict__ bias, float* __restrict__ Z, int Nn) {
+                 const float* __restrict__ bias, float* __restrict__ Z, int Nn, int k_per_split) {
     __shared__ __align__(16) float As[16][132];
     __shared__ __align__(16) float Bs[16][64];
     const int tid = threadIdx.x;
@@ -63,7 +63,9 @@ simt_gemm_kernel(const float* __restrict__ A, long long rows, int K, Taps taps, 
     for (int t = 0; t < taps.n; ++t) {
         const long long off = taps.off[t];
         const float* Wt = W + (long long)t * K * Nn;
-        for (int k0 = 0; k0 < K; k0 += 16) {
+        // split-K (skinny problems): slice blockIdx.z of the reduction goes to plane blockIdx.z of Z
+        const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+        for (int k0 = k_begin; k0 < k_end; k0 += 16) {
 #pragma unroll
             for (int l = 0; l < 2; ++l) {
                 int idx = tid + l * 256;
@@ -102,6 +104,7 @@ simt_gemm_kernel(const float* __restrict__ A, long long rows, int K, Taps taps, 
         }
     }
     const int n = n0 + tx * 4;
+    Z += (long long)blockIdx.z * rows * Nn;
     if (n < Nn) {
         float4 bv = bias ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -121,7 +124,7 @@ int simt_fwd(const float* A, const void* packed, float* Z, const ConvGeom& c, cu
     t.n = c.ntaps;
     for (int i = 0; i < 9; ++i) t.off[i] = c.offs[i];
     dim3 grid((unsigned)((c.rows + 127) / 128), (c.CsOut + 63) / 64);
-    simt_gemm_kernel<<<grid, 256, 0, s>>>(A, c.rows, c.CsIn, t, fwd, pb, Z, c.CsOut);
+    simt_gemm_kernel<<<grid, 256, 0, s>>>(A, c.rows, c.CsIn, t, fwd, pb, Z, c.CsOut, c.CsIn);
     FSB_LAUNCHED();
     return 0;
 }
@@ -132,9 +135,61 @@ int simt_dgrad(const float* dZ, const void* packed, float* dA, const ConvGeom& c
     t.n = c.ntaps;
     for (int i = 0; i < 9; ++i) t.off[i] = -c.offs[i];
     dim3 grid((unsigned)((c.rows + 127) / 128), (c.CsIn + 63) / 64);
-    simt_gemm_kernel<<<grid, 256, 0, s>>>(dZ, c.rows, c.CsOut, t, dgr, nullptr, dA, c.CsIn);
+    simt_gemm_kernel<<<grid, 256, 0, s>>>(dZ, c.rows, c.CsOut, t, dgr, nullptr, dA, c.CsIn, c.CsOut);
     FSB_LAUNCHED();
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// skinny (few rows, e.g. the FC head: rows = batch) linear layers: split-K over gridDim.z, partial planes in
+// scratch, summed in split order together with the bias (deterministic)
+static const int SKINNY_SPLITS = 16;
+
+size_t simt_skinny_scratch_bytes(const ConvGeom& c) {
+    int cs = c.CsIn > c.CsOut ? c.CsIn : c.CsOut;
+    return (size_t)SKINNY_SPLITS * c.rows * cs * sizeof(float);
+}
+
+__global__ void __launch_bounds__(256)
+skinny_finalize_kernel(const float* __restrict__ P, int splits, long long plane, int Nn, const float* __restrict__ bias,
+                       float* __restrict__ Z) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.x * blockDim.x) {
+        float s = bias ? bias[i % Nn] : 0.f;
+#pragma unroll 4
+        for (int sp = 0; sp < splits; ++sp) s += P[sp * plane + i];
+        Z[i] = s;
+    }
+}
+
+static int skinny_gemm(const float* A, long long rows, int K, const float* W, const float* bias, float* Z, int Nn,
+                       float* scratch, cudaStream_t s) {
+    FSB_REQUIRE(K % 16 == 0, "skinny_gemm: K must be a multiple of 16");
+    int k_per_split = ((K / 16 + SKINNY_SPLITS - 1) / SKINNY_SPLITS) * 16;
+    int splits = (K + k_per_split - 1) / k_per_split;
+    Taps t;
+    t.n = 1;
+    for (int i = 0; i < 9; ++i) t.off[i] = 0;
+    dim3 grid((unsigned)((rows + 127) / 128), (Nn + 63) / 64, splits);
+    simt_gemm_kernel<<<grid, 256, 0, s>>>(A, rows, K, t, W, nullptr, scratch, Nn, k_per_split);
+    FSB_LAUNCHED();
+    long long plane = rows * Nn;
+    int blocks = (int)((plane + 255) / 256 > 1184 ? 1184 : (plane + 255) / 256);
+    skinny_finalize_kernel<<<blocks, 256, 0, s>>>(scratch, splits, plane, Nn, bias, Z);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+int simt_skinny_fwd(const float* A, const void* packed, float* Z, const ConvGeom& c, void* scratch, cudaStream_t s) {
+    FSB_REQUIRE(c.ntaps == 1, "skinny GEMM: linear layers only");
+    const float* fwd = (const float*)packed;
+    const float* pb = fwd + (size_t)2 * c.CsIn * c.CsOut;
+    return skinny_gemm(A, c.rows, c.CsIn, fwd, pb, Z, c.CsOut, (float*)scratch, s);
+}
+
+int simt_skinny_dgrad(const float* dZ, const void* packed, float* dA, const ConvGeom& c, void* scratch, cudaStream_t s) {
+    FSB_REQUIRE(c.ntaps == 1, "skinny GEMM: linear layers only");
+    const float* dgr = (const float*)packed + (size_t)c.CsIn * c.CsOut;
+    return skinny_gemm(dZ, c.rows, c.CsOut, dgr, nullptr, dA, c.CsIn, (float*)scratch, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,26 +263,27 @@ simt_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dZ, lon
     }
 }
 
-// dw[co][ci][t] = sum_split P[split][t][ci][co]   (fixed order: deterministic)
-__global__ void wgrad_finalize_kernel(const float* P, int splits, ConvGeom c, float* dw) {
-    long long total = (long long)c.Cout * c.Cin * c.ntaps;
-    long long plane = (long long)c.ntaps * c.CsIn * c.CsOut;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+// dw[co][ci][t] = sum_split P[split][t][ci][co]   (fixed order: deterministic).  Threads walk P in its own
+// order (co fastest) so every split plane is read coalesced; the `splits` loads of a thread are independent.
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ P, int splits, ConvGeom c, float* dw) {
+    const long long plane = (long long)c.ntaps * c.CsIn * c.CsOut;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane;
          i += (long long)gridDim.x * blockDim.x) {
-        int t = (int)(i % c.ntaps);
-        long long u = i / c.ntaps;
-        int ci = (int)(u % c.Cin);
-        int co = (int)(u / c.Cin);
-        long long src = ((long long)t * c.CsIn + ci) * c.CsOut + co;
+        const int co = (int)(i % c.CsOut);
+        const long long u = i / c.CsOut;
+        const int ci = (int)(u % c.CsIn);
+        const int t = (int)(u / c.CsIn);
+        if (co >= c.Cout || ci >= c.Cin) continue;
         float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += P[sp * plane + src];
-        dw[i] = s;
+#pragma unroll 8
+        for (int sp = 0; sp < splits; ++sp) s += P[sp * plane + i];
+        dw[((long long)co * c.Cin + ci) * c.ntaps + t] = s;
     }
 }
 
 int wgrad_finalize(const float* P, int splits, const ConvGeom& c, float* dw, cudaStream_t s) {
-    long long total = (long long)c.Cout * c.Cin * c.ntaps;
-    int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+    long long total = (long long)c.ntaps * c.CsIn * c.CsOut;
+    int blocks = (int)((total + 255) / 256 > 2368 ? 2368 : (total + 255) / 256);
     wgrad_finalize_kernel<<<blocks, 256, 0, s>>>(P, splits, c, dw);
     FSB_LAUNCHED();
     return 0;

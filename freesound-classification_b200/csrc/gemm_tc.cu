@@ -8,7 +8,9 @@
 //
 //   conv_tc_kernel  (forward and dgrad)   D[r, n] = sum_t sum_k A[r + off_t, k] * W_t[n, k]
 //       persistent, warp specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-//       warps 2..5 = epilogue (TMEM -> registers -> global).  Two smem rings: an A ring whose stage is
+//       warps 2..5 = epilogue (TMEM -> registers -> swizzled smem panel -> TMA store, one 32-row x 32-column box
+//       per warp, double buffered; BatchNorm column statistics by a register shuffle-transpose reduction).
+//       Two smem rings: an A ring whose stage is
 //       a (128 + 8)-row x 64-channel SWIZZLE_128B box shared by the three dx taps of one dy (the tap
 //       shift is a 128-byte start-address offset of the UMMA descriptor), and a W ring with one
 //       (BN x 64) tile per tap.  Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i
@@ -85,6 +87,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
+}
+// smem tile -> global (bulk async group of the issuing thread); out-of-range rows / columns are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -169,19 +185,38 @@ struct ConvTcParams {
     int a_box_rows;        // 128 (tpg == 1) or 136
     int nA, nW;            // ring depths
     int planes;            // 2 = bf16x3, 1 = bf16 (hi only)
+    int nstg;              // epilogue staging buffers per warp: 2 (double buffered) or 1 (wide tiles: smem is tight)
     int base_off_mode;     // 1: descriptor base_offset = row shift, 0: always 0
     float* Z;
     int ldz;               // CsOut
     const float* bias;     // CsOut entries or nullptr
     // optional fused BatchNorm statistics of Z over interior pixels: partials[blockIdx.x][2][ldz] (doubles)
     double* stats;
-    int Hp, Wp, H, W, padH, padW;
+    const unsigned char* mask;   // interior mask of the output geometry (nullptr = every row is interior)
 };
 
+constexpr int EPI_BOX_BYTES = 4096;             // one staged box: 32 rows x 128 bytes; 4 epilogue warps x nstg boxes
+
+// Sum over the 32 lanes of a warp of v[j], for every j: afterwards lane l holds the total of column l in v[0].
+// Butterfly transpose-reduction: 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmZ32, const __grid_constant__ CUtensorMap tmZ16, const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: [A ring][W ring][barriers]
+    // carve: [A ring][W ring][epilogue staging][barriers][bias][statistics]   (every ring stage is a multiple of 1 KB)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_plane = (uint32_t)p.a_box_rows * 128u;
     const uint32_t a_stage = a_plane * 2u;
@@ -189,25 +224,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t w_stage = w_plane * 2u;
     const uint32_t a_ring = smem_base;
     const uint32_t w_ring = a_ring + a_stage * p.nA;
-    const uint32_t bars = w_ring + w_stage * p.nW;         // 8-byte mbarriers
+    const uint32_t epi_stage = w_ring + w_stage * p.nW;     // 1 KB aligned: SWIZZLE_128B boxes
+    const uint32_t bars = epi_stage + 4u * p.nstg * EPI_BOX_BYTES;      // 8-byte mbarriers
     // barrier layout: A_full[nA] A_empty[nA] W_full[nW] W_empty[nW] T_full[2] T_empty[2], then tmem ptr
     const uint32_t bA_full = bars, bA_empty = bA_full + 8u * p.nA;
     const uint32_t bW_full = bA_empty + 8u * p.nA, bW_empty = bW_full + 8u * p.nW;
     const uint32_t bT_full = bW_empty + 8u * p.nW, bT_empty = bT_full + 16u;
     const uint32_t tmem_slot = bT_empty + 16u;
-    // epilogue scratch after the barriers: staging panel [128 rows][32 floats] (16-byte chunks XOR-swizzled
-    // by row & 7), interior bits of the tile's rows, bias [ldz], statistics accumulators [2][ldz] doubles
-    unsigned char* epi = smem_raw + (bars - smem_u32(smem_raw)) + 256u;
-    float4* stg = reinterpret_cast<float4*>(epi);
-    uint32_t* tile_mask = reinterpret_cast<uint32_t*>(epi + 16384);
-    float* bias_s = reinterpret_cast<float*>(epi + 16384 + 16);
-    double* stat_acc = reinterpret_cast<double*>(epi + 16384 + 16 + (((size_t)p.ldz * 4 + 15) & ~(size_t)15));
+    unsigned char* tail = smem_raw + (bars - smem_u32(smem_raw)) + 256u;
+    float* bias_s = reinterpret_cast<float*>(tail);
+    double* stat_acc = reinterpret_cast<double*>(tail + (((size_t)p.ldz * 4 + 15) & ~(size_t)15));
     for (int i = threadIdx.x; i < p.ldz; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
     if (p.stats)
         for (int i = threadIdx.x; i < 2 * p.ldz; i += TC_THREADS) stat_acc[i] = 0.0;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile schedule: a CTA keeps one column tile nt for its whole life (its statistics then cover one column range)
+    const int nt = blockIdx.x % p.n_tiles;
+    const int mt0 = blockIdx.x / p.n_tiles, mt_step = gridDim.x / p.n_tiles;
     const int kchunks = (p.K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
@@ -217,6 +251,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmZ32);
+        tma_prefetch_desc(&tmZ16);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -229,8 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
                 const int r0 = mt * BM;
                 for (int g = 0; g < p.ngroups; ++g) {
                     for (int kc = 0; kc < kchunks; ++kc) {
@@ -259,7 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = make_idesc(BM, p.BN, 0, 0);
             uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
                 const uint32_t buf = it & 1u, use = it >> 1;
                 mbar_wait(bT_empty + 8u * buf, (use & 1u) ^ 1u);
                 tc_fence_after();
@@ -302,97 +337,109 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ============ epilogue: TMEM -> registers -> swizzled smem panel -> coalesced global stores ============
+        // ====== epilogue: TMEM -> registers (+bias) -> swizzled smem box -> TMA store; column statistics by shuffles ======
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
         const int rl = q * 32 + lane;              // this thread's row within the tile
-        const int npanels = (p.BN + 31) / 32;
+        const uint32_t stg0 = epi_stage + (uint32_t)(q * p.nstg) * EPI_BOX_BYTES;
+        uint32_t sb = 0;                           // staging buffer toggle
+        double acc1[8], acc2[8];                   // lane l: column 32*pn + l of this CTA's column tile
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc1[i] = 0.0; acc2[i] = 0.0; }
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
             const long long m0 = (long long)mt * BM;
+            bool interior = false;
             if (p.stats) {
                 const long long row = m0 + rl;
-                bool interior = false;
-                if (row < p.rows) {
-                    const int rr = (int)(row % ((long long)p.Hp * p.Wp));
-                    const int yy = rr / p.Wp, xx = rr - yy * p.Wp;
-                    interior = yy >= p.padH && yy < p.padH + p.H && xx >= p.padW && xx < p.padW + p.W;
-                }
-                const uint32_t bits = __ballot_sync(0xffffffffu, interior);
-                if (lane == 0) tile_mask[q] = bits;
+                interior = row < p.rows && (p.mask == nullptr || p.mask[row] != 0);
             }
             mbar_wait(bT_full + 8u * buf, use & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
-            for (int pn = 0; pn < npanels; ++pn) {
-                const int cols = p.BN - pn * 32 >= 32 ? 32 : 16;       // BN is a multiple of 16
-                const int n = nt * p.BN + pn * 32;                      // first global column of the panel
-                float v[32];
-                if (cols == 32) {
-                    tmem_ld32(taddr + (uint32_t)(pn * 32), v);
-                } else {
-                    tmem_ld16(taddr + (uint32_t)(pn * 32), v);
 #pragma unroll
-                    for (int i = 16; i < 32; ++i) v[i] = 0.f;
-                }
-                if (pn == npanels - 1) {           // accumulator drained: hand the TMEM buffer back early
-                    tc_fence_before();
-                    mbar_arrive(bT_empty + 8u * buf);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int cg = n + 4 * j;
-                    float4 o;
-                    if (cg < p.ldz && 4 * j < cols) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cg);
-                        o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+            for (int pn = 0; pn < 8; ++pn) {
+                if (pn * 32 < p.BN) {
+                    const bool wide = p.BN - pn * 32 >= 32;                 // BN is a multiple of 16: 32 or 16 columns
+                    const int n = nt * p.BN + pn * 32;                      // first global column of the panel
+                    float v[32];
+                    if (wide) {
+                        tmem_ld32(taddr + (uint32_t)(pn * 32), v);
                     } else {
-                        o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    stg[rl * 8 + (j ^ (rl & 7))] = o;
-                }
-                if (p.stats) asm volatile("bar.sync 1, 128;" ::: "memory");
-                else __syncwarp();
-                // this warp's 32 rows, 4 rows x 128 contiguous bytes per store instruction
+                        tmem_ld16(taddr + (uint32_t)(pn * 32), v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = q * 32 + 4 * i + (lane >> 3), j = lane & 7;
-                    const float4 o = stg[r * 8 + (j ^ (r & 7))];
-                    const long long grow = m0 + r;
-                    const int cg = n + 4 * j;
-                    if (grow < p.rows && cg < p.ldz && 4 * j < cols) *reinterpret_cast<float4*>(p.Z + grow * p.ldz + cg) = o;
-                }
-                if (p.stats) {
-                    // column sums over the 128 rows: warp q owns columns 8q..8q+7, lane>>3 selects a 32-row quarter
-                    const int cl = 8 * q + (lane & 7), rq = lane >> 3;
-                    const uint32_t bits = tile_mask[rq];
-                    const float* stf = reinterpret_cast<const float*>(stg);
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const int rr = (i + 2 * rq) & 31;              // staggered: conflict-free across quarters
-                        const int r = 32 * rq + rr;
-                        const float x = stf[r * 32 + (((cl >> 2) ^ (r & 7)) << 2) + (cl & 3)];
-                        if ((bits >> rr) & 1u) { s1 += x; s2 = fmaf(x, x, s2); }
+                        for (int i = 16; i < 32; ++i) v[i] = 0.f;
                     }
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                    const int cg = n + cl;
-                    if (lane < 8 && cg < p.ldz && cl < cols) {          // unique owner of this column: no atomics
-                        stat_acc[cg] += (double)s1;
-                        stat_acc[p.ldz + cg] += (double)s2;
+                    if ((pn + 1) * 32 >= p.BN) {       // accumulator drained: hand the TMEM buffer back early
+                        tc_fence_before();
+                        mbar_arrive(bT_empty + 8u * buf);
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");     // panel fully consumed
-                } else {
+                    // the staging buffer about to be overwritten was read by the TMA store issued two panels ago
+                    if (lane == 0) {
+                        if (p.nstg == 2) bulk_wait_read<1>();
+                        else bulk_wait_read<0>();
+                    }
                     __syncwarp();
+                    const uint32_t stg = stg0 + sb * EPI_BOX_BYTES;
+                    if (wide) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int cg = n + 4 * j;
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (cg < p.ldz) b4 = *reinterpret_cast<const float4*>(bias_s + cg);
+                            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                            st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1],
+                                         v[4 * j + 2], v[4 * j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int cg = n + 4 * j;
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (cg < p.ldz) b4 = *reinterpret_cast<const float4*>(bias_s + cg);
+                            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                            st_shared_v4(stg + (uint32_t)lane * 64u + (uint32_t)(j << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2],
+                                         v[4 * j + 3]);
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && m0 + q * 32 < p.rows) {
+                        tma_store_2d(wide ? &tmZ32 : &tmZ16, stg, n, (int)m0 + q * 32);
+                        bulk_commit();
+                    }
+                    sb = (sb + 1u) & (uint32_t)(p.nstg - 1);
+                    if (p.stats) {
+                        float w2[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] = interior ? v[i] : 0.f;
+                            w2[i] = v[i] * v[i];
+                        }
+                        warp_column_sums(v, lane);
+                        warp_column_sums(w2, lane);
+                        acc1[pn] += (double)v[0];
+                        acc2[pn] += (double)w2[0];
+                    }
                 }
             }
         }
+        if (lane == 0) bulk_wait_all();            // the staged boxes must be written before the CTA retires
         if (p.stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+            // merge the four warps' partials in warp order (fixed order: deterministic), then publish the CTA record
+            for (int w = 0; w < 4; ++w) {
+                if (q == w) {
+#pragma unroll
+                    for (int pn = 0; pn < 8; ++pn) {
+                        const int cl = pn * 32 + lane, cg = nt * p.BN + cl;
+                        if (cl < p.BN && cg < p.ldz) {
+                            stat_acc[cg] += acc1[pn];
+                            stat_acc[p.ldz + cg] += acc2[pn];
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             double* o = p.stats + (long long)blockIdx.x * 2 * p.ldz;
             for (int i = threadIdx.x - 64; i < 2 * p.ldz; i += 128) o[i] = stat_acc[i];
         }
@@ -669,6 +716,27 @@ int make_w_map(CUtensorMap* m, const void* base, long long total_rows, int kpad,
     return 0;
 }
 
+// float32 output matrix (ldz, rows), box (box_cols, 32): the epilogue's TMA-store target
+int make_out_map(CUtensorMap* m, const float* base, long long rows, int ldz, int box_cols, bool swizzle) {
+    auto fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return FSB_E_NODEVICE;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)ldz, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldz * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(output rows=%lld ldz=%d box=%d) failed: %d", rows, ldz, box_cols, (int)r);
+        return FSB_E_INVALID;
+    }
+    return 0;
+}
+
 int tc_mode() {
     // debugging switches: bit 0 = one TMA box per tap (no dx sharing), bit 1 = set the descriptor base_offset to
     // the row shift (measured on B200: the swizzle is a function of the absolute smem address, so a
@@ -742,10 +810,12 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
         const Geo& g = *st->g;
         FSB_REQUIRE(g.rows == rows && g.Cs == ldz, "conv_tc: statistics geometry does not match the output");
         p.stats = st->partials;
-        p.Hp = g.Hp; p.Wp = g.Wp; p.H = g.H; p.W = g.W; p.padH = g.padH; p.padW = g.padW;
+        p.mask = g.mask;
     }
-    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + 16384 + 16 /*staging panel, tile mask*/ +
-                         (((size_t)ldz * 4 + 15) & ~(size_t)15) /*bias*/ + (size_t)16 * ldz /*statistics*/;
+    size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (((size_t)ldz * 4 + 15) & ~(size_t)15) /*bias*/ +
+                   (size_t)16 * ldz /*statistics*/;
+    p.nstg = fixed + 8 * EPI_BOX_BYTES + 2 * a_stage + 2 * w_stage <= SMEM_LIMIT ? 2 : 1;
+    fixed += (size_t)4 * p.nstg * EPI_BOX_BYTES;   // TMA-store staging
     // ring depths: at least 2 each; give W the stages it needs to cover one A stage, then grow both
     p.nA = 2; p.nW = 2;
     for (;;) {
@@ -756,17 +826,20 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     }
     const size_t smem = fixed + a_stage * p.nA + w_stage * p.nW;
     FSB_REQUIRE(smem <= SMEM_LIMIT, "conv_tc: shared memory %zu exceeds the limit (BN=%d)", smem, bn);
-    CUtensorMap tmA, tmW;
+    CUtensorMap tmA, tmW, tmZ32, tmZ16;
     FSB_TRY(make_act_map(&tmA, A, rows, K, p.a_box_rows));
     FSB_TRY(make_w_map(&tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn));
+    FSB_TRY(make_out_map(&tmZ32, Z, rows, ldz, 32, true));
+    FSB_TRY(make_out_map(&tmZ16, Z, rows, ldz, 16, false));
     static bool attr_set = false;
     if (!attr_set) {
         FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    int grid = p.m_tiles * p.n_tiles;
-    if (grid > num_sms()) grid = num_sms();
-    conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmW, p);
+    // every CTA owns one column tile: the grid is a multiple of n_tiles
+    FSB_REQUIRE(p.n_tiles <= num_sms() && bn <= 256, "conv_tc: too many column tiles (%d)", p.n_tiles);
+    int grid = p.m_tiles < num_sms() / p.n_tiles ? p.m_tiles * p.n_tiles : num_sms() / p.n_tiles * p.n_tiles;
+    conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmW, tmZ32, tmZ16, p);
     FSB_LAUNCHED();
     if (st) *st->nblk = grid;
     return 0;

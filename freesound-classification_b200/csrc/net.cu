@@ -63,6 +63,7 @@ struct BlockPlan {
     float *zf, *zp, *z1, *z2, *z3, *out;
     void *r0, *a1, *a2;
     int* argrow;
+    void* gmax_scratch;
     unsigned char *mask, *mask_in;
     int head_off;        // column offset in the concatenated head input, -1 if no head
     // backward
@@ -98,7 +99,7 @@ struct fsb_net {
     float *feats, *h0, *z1h, *h1, *zl, *dzl, *dh1, *dz1h, *dh0, *dfeats;
     BnBuf hbn0, hbn2;
     ConvGeom lin1, lin5;
-    void *pk_l1, *pk_l5;
+    void *pk_l1, *pk_l5, *head_scratch;
     Geo g_head, g_cls;
 
     // profiling
@@ -219,9 +220,11 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
             B.head_off = head_off;
             head_off += B.C;
             B.argrow = b.take<int>((size_t)N * B.C);
+            B.gmax_scratch = b.take_bytes(gmax_scratch_bytes(B.g));
         } else {
             B.head_off = -1;
             B.argrow = nullptr;
+            B.gmax_scratch = nullptr;
         }
         if (training) {
             B.d_out = b.take<float>(pe);
@@ -256,6 +259,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
     carve_bn(b, net->hbn2, net->D);
     net->pk_l1 = b.take_bytes(simt_packed_weight_bytes(net->lin1));
     net->pk_l5 = b.take_bytes(simt_packed_weight_bytes(net->lin5));
+    net->head_scratch = b.take_bytes(std::max(simt_skinny_scratch_bytes(net->lin1), simt_skinny_scratch_bytes(net->lin5)));
     size_t he = (size_t)N * net->Ds;
     net->feats = b.take<float>(he);
     net->h0 = b.take<float>(he);
@@ -524,7 +528,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
                                            next_stats ? net->partials : nullptr, s));
         carried_nblk = ew_num_blocks(B.g);
         if (B.head_off >= 0)
-            RUN(CAT_ELT_FWD, 0, gmax_forward(B.out, B.g, net->feats, net->Ds, B.head_off, B.argrow, s));
+            RUN(CAT_ELT_FWD, 0, gmax_forward(B.out, B.g, net->feats, net->Ds, B.head_off, B.argrow, B.gmax_scratch, s));
     }
 
     // ---- FC head (float32 CUDA-core GEMMs in every precision mode)
@@ -539,13 +543,13 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
                                         FMT_F32, net->h0, nullptr, s));
         RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L1_W], P[H_L1_B], net->lin1, net->pk_l1, s));
         RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L5_W], P[H_L5_B], net->lin5, net->pk_l5, s));
-        RUN(CAT_HEAD, 0, simt_fwd(net->h0, net->pk_l1, net->z1h, net->lin1, s));
+        RUN(CAT_HEAD, 0, simt_skinny_fwd(net->h0, net->pk_l1, net->z1h, net->lin1, net->head_scratch, s));
         FSB_TRY(bn_forward_stats(net, s, net->z1h, net->g_head, net->hbn2, P[H_BN2_W], P[H_BN2_B], RM[1], RV[1],
                                  CT ? CT[1] : nullptr, training, CAT_HEAD));
         Dropout dr = {training ? c.dropout_p : 0.f, dropout_seed};
         RUN(CAT_HEAD, 0, bn_act_forward(net->z1h, net->g_head, net->hbn2.coef(P[H_PRELU]), kNoRes, dr, nullptr,
                                         FMT_F32, net->h1, nullptr, s));
-        RUN(CAT_HEAD, 0, simt_fwd(net->h1, net->pk_l5, net->zl, net->lin5, s));
+        RUN(CAT_HEAD, 0, simt_skinny_fwd(net->h1, net->pk_l5, net->zl, net->lin5, net->head_scratch, s));
         RUN(CAT_HEAD, 0, copy2d(net->zl, n, c.n_classes, net->CsCls, logits, c.n_classes, s));
     }
     net->fwd_done = true;
@@ -586,12 +590,12 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
         RUN(CAT_HEAD, 0, copy2d(dlogits, n, c.n_classes, c.n_classes, net->dzl, net->CsCls, s));
         RUN(CAT_HEAD, 0, colsum(dlogits, n, c.n_classes, c.n_classes, G(hb + H_L5_B), s));
         RUN(CAT_HEAD, 0, simt_wgrad(net->h1, net->dzl, G(hb + H_L5_W), net->wgrad_scratch, net->lin5, s));
-        RUN(CAT_HEAD, 0, simt_dgrad(net->dzl, net->pk_l5, net->dh1, net->lin5, s));
+        RUN(CAT_HEAD, 0, simt_skinny_dgrad(net->dzl, net->pk_l5, net->dh1, net->lin5, net->head_scratch, s));
         Dropout dr = {c.dropout_p, net->dropout_seed};
         FSB_TRY(bn_backward(net, s, net->dh1, nullptr, net->z1h, net->g_head, net->hbn2, P[H_PRELU], kNoRes, dr,
                             G(hb + H_BN2_W), G(hb + H_BN2_B), G(hb + H_PRELU), net->dz1h, FMT_F32, nullptr, CAT_HEAD));
         RUN(CAT_HEAD, 0, simt_wgrad(net->h0, net->dz1h, G(hb + H_L1_W), net->wgrad_scratch, net->lin1, s));
-        RUN(CAT_HEAD, 0, simt_dgrad(net->dz1h, net->pk_l1, net->dh0, net->lin1, s));
+        RUN(CAT_HEAD, 0, simt_skinny_dgrad(net->dz1h, net->pk_l1, net->dh0, net->lin1, net->head_scratch, s));
         FSB_TRY(bn_backward(net, s, net->dh0, nullptr, net->feats, net->g_head, net->hbn0, nullptr, kNoRes, kNoDrop,
                             G(hb + H_BN0_W), G(hb + H_BN0_B), nullptr, net->dfeats, FMT_F32, nullptr, CAT_HEAD));
     }

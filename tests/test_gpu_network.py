@@ -133,13 +133,21 @@ def test_canonical_width_against_oracle(precision):
     # measured behaviour of two valid float32 evaluations, not an arithmetic defect (tools/grad_debug2.py: the
     # difference sits in a single channel of one d(beta) while d(gamma) and the slope gradient agree to 3e-5),
     # so the gate is flip-robust: tight in the L2 norm per tensor, looser on the single worst element.
+    # Conditioning.  tools/conditioning.py runs the ORACLE in float64 on this very problem and perturbs its input
+    # features by 1e-5 relative: logits move by 4e-4 and every gradient tensor by 3-5e-2 in the L2 norm (train-mode
+    # BatchNorm over 64 values per channel of an untrained net amplifies a forward difference ~4000x).  The float32
+    # back end differs from the oracle by ~1e-6 in the forward pass and is held to 2e-2; the bf16x3 tensor-core back
+    # end keeps ~2^-16 per product (forward logits ~1e-4 here), so its gradients are held to the oracle's own
+    # sensitivity at that forward difference.  The GEMMs themselves are checked to 1e-4 (forward, dgrad, wgrad) in
+    # test_gpu_kernels.py::test_conv_forward_backward.
+    l2_gate = 2e-2 if precision == "fp32" else 8e-2
     gmax = max(float(p.grad.abs().max()) for p in params.values() if p.requires_grad)
     for k, p in model.named_parameters():
         ref = params[k].grad.numpy().astype(np.float64)
         got = p.grad.cpu().numpy().astype(np.float64)
         if ref.size >= 64:             # the norm is only flip-robust for tensors with many elements
             l2 = np.sqrt(((got - ref) ** 2).sum()) / max(np.sqrt((ref ** 2).sum()), 1e-3 * gmax)
-            assert l2 <= 2e-2, (k, l2)
+            assert l2 <= l2_gate, (k, l2)
         loose = 0.25 if ref.size < 8 else 0.1       # BN_in of block 0 has two elements: one flip is 1/2 of it
         assert np.abs(got - ref).max() <= loose * np.abs(ref).max() + 2e-3 * gmax, k
 
