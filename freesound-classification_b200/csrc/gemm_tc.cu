@@ -122,6 +122,352 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// All MMAs of one pipeline stage -- (dy, k-chunk): up to 3 dx taps x up to 4 k-steps x 3 products x up to 2 row tiles --
+// in ONE straight-line, predicated asm block.  Per-MMA issue cost decides this kernel: an M128 x N112 x K16 MMA occupies
+// the tensor pipe for 60 cycles (tools/micro/umma_bench.cu: max(N/2, ~44), independent of the accumulator being reused,
+// of SWIZZLE_64B/128B and of a row-shifted A start address), and a C++ loop around single-MMA asm statements costs the
+// issuing thread ~15 instructions (~130 cycles) per MMA in uniform-register moves, predicates and branches.
+//   d_tmem0 / bn: accumulator of tile 0, column stride to tile 1;   a_hi: descriptor of (tile 0, tap 0, hi plane);
+//   a_tile16 / a_box16 / row16: descriptor-unit (16 B) strides tile -> tile, hi -> lo, tap -> tap (one smem row);
+//   b_hi: descriptor of (tap 0, hi plane); w_tap16 / w_plane16: strides tap -> tap, hi -> lo.   acc = 0 starts the tile.
+__device__ __forceinline__ void umma_stage_x3(uint32_t d_tmem0, uint32_t bn, uint64_t a_hi, uint32_t a_tile16, uint32_t a_box16,
+                                              uint32_t row16, uint64_t b_hi, uint32_t w_tap16, uint32_t w_plane16, uint32_t idesc,
+                                              uint32_t acc, int ksteps, int ntile, int ntaps) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, pt, pk1, pk2, pk3, pt1, ps1, ps2;\n\t"
+        ".reg .b32 d0, d1;\n\t"
+        ".reg .b64 ah0, ah1, al0, al1, bh, bl, at, ab, ar, wt, wb;\n\t"
+        ".reg .b64 xh0, xh1, xl0, xl1, yh, yl;\n\t"
+        "setp.ne.b32 pacc, %10, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.gt.s32 pk1, %11, 1;\n\t"
+        "setp.gt.s32 pk2, %11, 2;\n\t"
+        "setp.gt.s32 pk3, %11, 3;\n\t"
+        "setp.gt.s32 pt1, %12, 1;\n\t"
+        "setp.gt.s32 ps1, %13, 1;\n\t"
+        "setp.gt.s32 ps2, %13, 2;\n\t"
+        "mov.b32 d0, %0;\n\t"
+        "add.u32 d1, d0, %1;\n\t"
+        "cvt.u64.u32 at, %3;\n\t"
+        "cvt.u64.u32 ab, %4;\n\t"
+        "cvt.u64.u32 ar, %5;\n\t"
+        "cvt.u64.u32 wt, %7;\n\t"
+        "cvt.u64.u32 wb, %8;\n\t"
+        "mov.b64 ah0, %2;\n\t"
+        "add.u64 ah1, ah0, at;\n\t"
+        "add.u64 al0, ah0, ab;\n\t"
+        "add.u64 al1, ah1, ab;\n\t"
+        "mov.b64 bh, %6;\n\t"
+        "add.u64 bl, bh, wb;\n\t"
+        "add.u64 xh0, ah0, 0;\n\t"
+        "add.u64 xl0, al0, 0;\n\t"
+        "add.u64 xh1, ah1, 0;\n\t"
+        "add.u64 xl1, al1, 0;\n\t"
+        "add.u64 yh, bh, 0;\n\t"
+        "add.u64 yl, bl, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pacc;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pacc;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk1 bra.uni NEXT0;\n\t"
+        "add.u64 xh0, ah0, 2;\n\t"
+        "add.u64 xl0, al0, 2;\n\t"
+        "add.u64 xh1, ah1, 2;\n\t"
+        "add.u64 xl1, al1, 2;\n\t"
+        "add.u64 yh, bh, 2;\n\t"
+        "add.u64 yl, bl, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk2 bra.uni NEXT0;\n\t"
+        "add.u64 xh0, ah0, 4;\n\t"
+        "add.u64 xl0, al0, 4;\n\t"
+        "add.u64 xh1, ah1, 4;\n\t"
+        "add.u64 xl1, al1, 4;\n\t"
+        "add.u64 yh, bh, 4;\n\t"
+        "add.u64 yl, bl, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk3 bra.uni NEXT0;\n\t"
+        "add.u64 xh0, ah0, 6;\n\t"
+        "add.u64 xl0, al0, 6;\n\t"
+        "add.u64 xh1, ah1, 6;\n\t"
+        "add.u64 xl1, al1, 6;\n\t"
+        "add.u64 yh, bh, 6;\n\t"
+        "add.u64 yl, bl, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "NEXT0:\n\t"
+        "@!ps1 bra.uni DONE;\n\t"
+        "add.u64 ah0, ah0, ar;\n\t"
+        "add.u64 ah1, ah1, ar;\n\t"
+        "add.u64 al0, al0, ar;\n\t"
+        "add.u64 al1, al1, ar;\n\t"
+        "add.u64 bh, bh, wt;\n\t"
+        "add.u64 bl, bl, wt;\n\t"
+        "add.u64 xh0, ah0, 0;\n\t"
+        "add.u64 xl0, al0, 0;\n\t"
+        "add.u64 xh1, ah1, 0;\n\t"
+        "add.u64 xl1, al1, 0;\n\t"
+        "add.u64 yh, bh, 0;\n\t"
+        "add.u64 yl, bl, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk1 bra.uni NEXT1;\n\t"
+        "add.u64 xh0, ah0, 2;\n\t"
+        "add.u64 xl0, al0, 2;\n\t"
+        "add.u64 xh1, ah1, 2;\n\t"
+        "add.u64 xl1, al1, 2;\n\t"
+        "add.u64 yh, bh, 2;\n\t"
+        "add.u64 yl, bl, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk2 bra.uni NEXT1;\n\t"
+        "add.u64 xh0, ah0, 4;\n\t"
+        "add.u64 xl0, al0, 4;\n\t"
+        "add.u64 xh1, ah1, 4;\n\t"
+        "add.u64 xl1, al1, 4;\n\t"
+        "add.u64 yh, bh, 4;\n\t"
+        "add.u64 yl, bl, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk3 bra.uni NEXT1;\n\t"
+        "add.u64 xh0, ah0, 6;\n\t"
+        "add.u64 xl0, al0, 6;\n\t"
+        "add.u64 xh1, ah1, 6;\n\t"
+        "add.u64 xl1, al1, 6;\n\t"
+        "add.u64 yh, bh, 6;\n\t"
+        "add.u64 yl, bl, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "NEXT1:\n\t"
+        "@!ps2 bra.uni DONE;\n\t"
+        "add.u64 ah0, ah0, ar;\n\t"
+        "add.u64 ah1, ah1, ar;\n\t"
+        "add.u64 al0, al0, ar;\n\t"
+        "add.u64 al1, al1, ar;\n\t"
+        "add.u64 bh, bh, wt;\n\t"
+        "add.u64 bl, bl, wt;\n\t"
+        "add.u64 xh0, ah0, 0;\n\t"
+        "add.u64 xl0, al0, 0;\n\t"
+        "add.u64 xh1, ah1, 0;\n\t"
+        "add.u64 xl1, al1, 0;\n\t"
+        "add.u64 yh, bh, 0;\n\t"
+        "add.u64 yl, bl, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk1 bra.uni NEXT2;\n\t"
+        "add.u64 xh0, ah0, 2;\n\t"
+        "add.u64 xl0, al0, 2;\n\t"
+        "add.u64 xh1, ah1, 2;\n\t"
+        "add.u64 xl1, al1, 2;\n\t"
+        "add.u64 yh, bh, 2;\n\t"
+        "add.u64 yl, bl, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk2 bra.uni NEXT2;\n\t"
+        "add.u64 xh0, ah0, 4;\n\t"
+        "add.u64 xl0, al0, 4;\n\t"
+        "add.u64 xh1, ah1, 4;\n\t"
+        "add.u64 xl1, al1, 4;\n\t"
+        "add.u64 yh, bh, 4;\n\t"
+        "add.u64 yl, bl, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk3 bra.uni NEXT2;\n\t"
+        "add.u64 xh0, ah0, 6;\n\t"
+        "add.u64 xl0, al0, 6;\n\t"
+        "add.u64 xh1, ah1, 6;\n\t"
+        "add.u64 xl1, al1, 6;\n\t"
+        "add.u64 yh, bh, 6;\n\t"
+        "add.u64 yl, bl, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "NEXT2:\n\t"
+        "DONE:\n\t"
+        "}"
+        ::"r"(d_tmem0), "r"(bn), "l"(a_hi), "r"(a_tile16), "r"(a_box16), "r"(row16), "l"(b_hi), "r"(w_tap16), "r"(w_plane16),
+          "r"(idesc), "r"(acc), "r"(ksteps), "r"(ntile), "r"(ntaps)
+        : "memory");
+}
+__device__ __forceinline__ void umma_stage_x1(uint32_t d_tmem0, uint32_t bn, uint64_t a_hi, uint32_t a_tile16, uint32_t a_box16,
+                                              uint32_t row16, uint64_t b_hi, uint32_t w_tap16, uint32_t w_plane16, uint32_t idesc,
+                                              uint32_t acc, int ksteps, int ntile, int ntaps) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, pt, pk1, pk2, pk3, pt1, ps1, ps2;\n\t"
+        ".reg .b32 d0, d1;\n\t"
+        ".reg .b64 ah0, ah1, al0, al1, bh, bl, at, ab, ar, wt, wb;\n\t"
+        ".reg .b64 xh0, xh1, xl0, xl1, yh, yl;\n\t"
+        "setp.ne.b32 pacc, %10, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.gt.s32 pk1, %11, 1;\n\t"
+        "setp.gt.s32 pk2, %11, 2;\n\t"
+        "setp.gt.s32 pk3, %11, 3;\n\t"
+        "setp.gt.s32 pt1, %12, 1;\n\t"
+        "setp.gt.s32 ps1, %13, 1;\n\t"
+        "setp.gt.s32 ps2, %13, 2;\n\t"
+        "mov.b32 d0, %0;\n\t"
+        "add.u32 d1, d0, %1;\n\t"
+        "cvt.u64.u32 at, %3;\n\t"
+        "cvt.u64.u32 ab, %4;\n\t"
+        "cvt.u64.u32 ar, %5;\n\t"
+        "cvt.u64.u32 wt, %7;\n\t"
+        "cvt.u64.u32 wb, %8;\n\t"
+        "mov.b64 ah0, %2;\n\t"
+        "add.u64 ah1, ah0, at;\n\t"
+        "add.u64 al0, ah0, ab;\n\t"
+        "add.u64 al1, ah1, ab;\n\t"
+        "mov.b64 bh, %6;\n\t"
+        "add.u64 bl, bh, wb;\n\t"
+        "add.u64 xh0, ah0, 0;\n\t"
+        "add.u64 xh1, ah1, 0;\n\t"
+        "add.u64 yh, bh, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pacc;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pacc;\n\t"
+        "@!pk1 bra.uni NEXT0;\n\t"
+        "add.u64 xh0, ah0, 2;\n\t"
+        "add.u64 xh1, ah1, 2;\n\t"
+        "add.u64 yh, bh, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk2 bra.uni NEXT0;\n\t"
+        "add.u64 xh0, ah0, 4;\n\t"
+        "add.u64 xh1, ah1, 4;\n\t"
+        "add.u64 yh, bh, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk3 bra.uni NEXT0;\n\t"
+        "add.u64 xh0, ah0, 6;\n\t"
+        "add.u64 xh1, ah1, 6;\n\t"
+        "add.u64 yh, bh, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "NEXT0:\n\t"
+        "@!ps1 bra.uni DONE;\n\t"
+        "add.u64 ah0, ah0, ar;\n\t"
+        "add.u64 ah1, ah1, ar;\n\t"
+        "add.u64 al0, al0, ar;\n\t"
+        "add.u64 al1, al1, ar;\n\t"
+        "add.u64 bh, bh, wt;\n\t"
+        "add.u64 bl, bl, wt;\n\t"
+        "add.u64 xh0, ah0, 0;\n\t"
+        "add.u64 xh1, ah1, 0;\n\t"
+        "add.u64 yh, bh, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk1 bra.uni NEXT1;\n\t"
+        "add.u64 xh0, ah0, 2;\n\t"
+        "add.u64 xh1, ah1, 2;\n\t"
+        "add.u64 yh, bh, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk2 bra.uni NEXT1;\n\t"
+        "add.u64 xh0, ah0, 4;\n\t"
+        "add.u64 xh1, ah1, 4;\n\t"
+        "add.u64 yh, bh, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk3 bra.uni NEXT1;\n\t"
+        "add.u64 xh0, ah0, 6;\n\t"
+        "add.u64 xh1, ah1, 6;\n\t"
+        "add.u64 yh, bh, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "NEXT1:\n\t"
+        "@!ps2 bra.uni DONE;\n\t"
+        "add.u64 ah0, ah0, ar;\n\t"
+        "add.u64 ah1, ah1, ar;\n\t"
+        "add.u64 al0, al0, ar;\n\t"
+        "add.u64 al1, al1, ar;\n\t"
+        "add.u64 bh, bh, wt;\n\t"
+        "add.u64 bl, bl, wt;\n\t"
+        "add.u64 xh0, ah0, 0;\n\t"
+        "add.u64 xh1, ah1, 0;\n\t"
+        "add.u64 yh, bh, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk1 bra.uni NEXT2;\n\t"
+        "add.u64 xh0, ah0, 2;\n\t"
+        "add.u64 xh1, ah1, 2;\n\t"
+        "add.u64 yh, bh, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk2 bra.uni NEXT2;\n\t"
+        "add.u64 xh0, ah0, 4;\n\t"
+        "add.u64 xh1, ah1, 4;\n\t"
+        "add.u64 yh, bh, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "@!pk3 bra.uni NEXT2;\n\t"
+        "add.u64 xh0, ah0, 6;\n\t"
+        "add.u64 xh1, ah1, 6;\n\t"
+        "add.u64 yh, bh, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
+        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
+        "NEXT2:\n\t"
+        "DONE:\n\t"
+        "}"
+        ::"r"(d_tmem0), "r"(bn), "l"(a_hi), "r"(a_tile16), "r"(a_box16), "r"(row16), "l"(b_hi), "r"(w_tap16), "r"(w_plane16),
+          "r"(idesc), "r"(acc), "r"(ksteps), "r"(ntile), "r"(ntaps)
+        : "memory");
+}
+// one lane of a fully converged warp (always the same one)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok));
+    return ok != 0;
+}
 // mbarrier arrives once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -138,20 +484,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+// asynchronous TMEM loads: the destination registers are valid only after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld64_async(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// pins a value behind every preceding asm volatile (the loads' wait): nothing computed from it can be scheduled earlier
+__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
 
 // shared-memory matrix descriptor (SWIZZLE_128B; sm_100 descriptor version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
@@ -173,19 +527,25 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int
 // ---------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ---------------------------------------------------------------------------------------------
+// Pipeline stage = one (dy, k-chunk): the activation boxes of the group's T row tiles (hi + lo planes) and the weight
+// tiles of the dx taps that share them, under ONE full / empty barrier pair; the MMA warp issues the whole stage from
+// one asm block.  Two accumulator sets in TMEM let the epilogue of group i overlap the main loop of group i + 1.
 struct ConvTcParams {
     long long rows;        // rows of the output (and of each activation plane)
     int m_tiles, n_tiles;
+    int T;                 // row tiles per group: 1 or 2
+    int nbuf;              // accumulator sets (2 whenever 2 * T * BN <= 512)
     int BN;                // output channels per tile (multiple of 16, <= 256)
     int K;                 // padded input channels CsIn (multiple of 16)
+    int bk;                // channels per smem stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)
     int ngroups, tpg;      // A boxes per k-chunk sweep, taps sharing one box
     int goff[9];           // row offset of the box origin relative to the tile's first row
     int wrow[9][3];        // first row of tap (group, shift) in the packed weight matrix (hi plane)
     int w_lo_row;          // row offset of the lo plane in the packed weight matrix
     int a_box_rows;        // 128 (tpg == 1) or 136
-    int nA, nW;            // ring depths
+    int nstages;           // ring depth
     int planes;            // 2 = bf16x3, 1 = bf16 (hi only)
-    int nstg;              // epilogue staging buffers per warp: 2 (double buffered) or 1 (wide tiles: smem is tight)
+    int nstg;              // epilogue staging buffers per warp: 2 (double buffered) or 1 (smem is tight)
     int base_off_mode;     // 1: descriptor base_offset = row shift, 0: always 0
     float* Z;
     int ldz;               // CsOut
@@ -193,61 +553,54 @@ struct ConvTcParams {
     // optional fused BatchNorm statistics of Z over interior pixels: partials[blockIdx.x][2][ldz] (doubles)
     double* stats;
     const unsigned char* mask;   // interior mask of the output geometry (nullptr = every row is interior)
+    int dbg;                     // timing experiments only (FSB200_TC_DBG): 1 = no TMA store, 2 = no statistics, 4 = no staging,
+                                 // 8 = no MMAs, 16 = no activation loads, 32 = no weight loads
 };
 
 constexpr int EPI_BOX_BYTES = 4096;             // one staged box: 32 rows x 128 bytes; 4 epilogue warps x nstg boxes
-
-// Sum over the 32 lanes of a warp of v[j], for every j: afterwards lane l holds the total of column l in v[0].
-// Butterfly transpose-reduction: 31 shuffles instead of 32 x 5.
-__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float send = upper ? v[i] : v[i + off];
-            const float keep = upper ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-}
+constexpr int MAX_T = 2;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmZ32, const __grid_constant__ CUtensorMap tmZ16, const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: [A ring][W ring][epilogue staging][barriers][bias][statistics]   (every ring stage is a multiple of 1 KB)
+    // carve: [stage ring: T x (hi, lo) activation boxes | tpg x (hi, lo) weight tiles][epilogue staging][barriers][bias][statistics]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_plane = (uint32_t)p.a_box_rows * 128u;
-    const uint32_t a_stage = a_plane * 2u;
-    const uint32_t w_plane = (uint32_t)p.BN * 128u;
-    const uint32_t w_stage = w_plane * 2u;
-    const uint32_t a_ring = smem_base;
-    const uint32_t w_ring = a_ring + a_stage * p.nA;
-    const uint32_t epi_stage = w_ring + w_stage * p.nW;     // 1 KB aligned: SWIZZLE_128B boxes
-    const uint32_t bars = epi_stage + 4u * p.nstg * EPI_BOX_BYTES;      // 8-byte mbarriers
-    // barrier layout: A_full[nA] A_empty[nA] W_full[nW] W_empty[nW] T_full[2] T_empty[2], then tmem ptr
-    const uint32_t bA_full = bars, bA_empty = bA_full + 8u * p.nA;
-    const uint32_t bW_full = bA_empty + 8u * p.nA, bW_empty = bW_full + 8u * p.nW;
-    const uint32_t bT_full = bW_empty + 8u * p.nW, bT_empty = bT_full + 16u;
-    const uint32_t tmem_slot = bT_empty + 16u;
+    const uint32_t row_bytes = (uint32_t)p.bk * 2u;                 // 128 or 64
+    const uint32_t a_box = (uint32_t)p.a_box_rows * row_bytes;      // one plane of one tile
+    const uint32_t a_tile = a_box * 2u;                             // hi + lo
+    const uint32_t a_part = a_tile * (uint32_t)p.T;
+    const uint32_t w_plane = (uint32_t)p.BN * row_bytes;
+    const uint32_t w_tap = w_plane * 2u;
+    const uint32_t stage_bytes = a_part + w_tap * (uint32_t)p.tpg;  // multiple of 1 KB
+    const uint32_t ring = smem_base;
+    const uint32_t epi_stage = (ring + stage_bytes * p.nstages + 1023u) & ~1023u;     // SWIZZLE_128B store boxes
+    const uint32_t bars = epi_stage + 4u * p.nstg * EPI_BOX_BYTES;                    // 8-byte mbarriers
+    // barrier layout: full[nstages] empty[nstages] T_full[2 MAX_T] T_empty[2 MAX_T], then tmem ptr
+    const uint32_t b_full = bars, b_empty = b_full + 8u * p.nstages;
+    const uint32_t bT_full = b_empty + 8u * p.nstages, bT_empty = bT_full + 16u * MAX_T;
+    const uint32_t tmem_slot = bT_empty + 16u * MAX_T;
     unsigned char* tail = smem_raw + (bars - smem_u32(smem_raw)) + 256u;
-    float* bias_s = reinterpret_cast<float*>(tail);
-    double* stat_acc = reinterpret_cast<double*>(tail + (((size_t)p.ldz * 4 + 15) & ~(size_t)15));
-    for (int i = threadIdx.x; i < p.ldz; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
-    if (p.stats)
-        for (int i = threadIdx.x; i < 2 * p.ldz; i += TC_THREADS) stat_acc[i] = 0.0;
+    float* bias_s = reinterpret_cast<float*>(tail);                                              // [BN]
+    double* stat_acc = reinterpret_cast<double*>(tail + (((size_t)p.BN * 4 + 15) & ~(size_t)15));  // [4 warps][2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile schedule: a CTA keeps one column tile nt for its whole life (its statistics then cover one column range)
+    // schedule: a CTA keeps one column tile nt for its whole life and walks groups of T row tiles
     const int nt = blockIdx.x % p.n_tiles;
-    const int mt0 = blockIdx.x / p.n_tiles, mt_step = gridDim.x / p.n_tiles;
-    const int kchunks = (p.K + BK - 1) / BK;
+    const int grp0 = blockIdx.x / p.n_tiles, grp_step = gridDim.x / p.n_tiles;
+    const int n_groups = (p.m_tiles + p.T - 1) / p.T;
+    const int kchunks = (p.K + p.bk - 1) / p.bk;
+
+    for (int i = threadIdx.x; i < p.BN; i += TC_THREADS) {
+        const int cg = nt * p.BN + i;
+        bias_s[i] = (p.bias && cg < p.ldz) ? p.bias[cg] : 0.f;
+    }
+    if (p.stats)
+        for (int i = threadIdx.x; i < 8 * p.BN; i += TC_THREADS) stat_acc[i] = 0.0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.nA; ++i) { mbar_init(bA_full + 8u * i, 1); mbar_init(bA_empty + 8u * i, 1); }
-        for (int i = 0; i < p.nW; ++i) { mbar_init(bW_full + 8u * i, 1); mbar_init(bW_empty + 8u * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bT_full + 8u * i, 1); mbar_init(bT_empty + 8u * i, 128); }
+        for (int i = 0; i < p.nstages; ++i) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
+        for (int i = 0; i < 2 * MAX_T; ++i) { mbar_init(bT_full + 8u * i, 1); mbar_init(bT_empty + 8u * i, 128); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
@@ -264,184 +617,221 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
-            for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
-                const int r0 = mt * BM;
+            uint32_t st = 0, ph = 0;
+            for (int grp = grp0; grp < n_groups; grp += grp_step) {
+                const int mt_first = grp * p.T;
+                const int ntile = min(p.T, p.m_tiles - mt_first);
                 for (int g = 0; g < p.ngroups; ++g) {
                     for (int kc = 0; kc < kchunks; ++kc) {
-                        mbar_wait(bA_empty + 8u * sa, pa ^ 1u);
-                        mbar_expect_tx(bA_full + 8u * sa, a_plane * p.planes);
-                        const uint32_t dst = a_ring + a_stage * sa;
-                        tma_load_3d(dst, &tmA, kc * BK, r0 + p.goff[g], 0, bA_full + 8u * sa);
-                        if (p.planes == 2) tma_load_3d(dst + a_plane, &tmA, kc * BK, r0 + p.goff[g], 1, bA_full + 8u * sa);
-                        if (++sa == (uint32_t)p.nA) { sa = 0; pa ^= 1u; }
-                        for (int s = 0; s < p.tpg; ++s) {
-                            mbar_wait(bW_empty + 8u * sw, pw ^ 1u);
-                            mbar_expect_tx(bW_full + 8u * sw, w_plane * p.planes);
-                            const uint32_t wd = w_ring + w_stage * sw;
-                            const int wr = p.wrow[g][s] + nt * p.BN;
-                            tma_load_2d(wd, &tmW, kc * BK, wr, bW_full + 8u * sw);
-                            if (p.planes == 2) tma_load_2d(wd + w_plane, &tmW, kc * BK, p.w_lo_row + wr, bW_full + 8u * sw);
-                            if (++sw == (uint32_t)p.nW) { sw = 0; pw ^= 1u; }
+                        mbar_wait(b_empty + 8u * st, ph ^ 1u);
+                        const uint32_t full = b_full + 8u * st;
+                        const uint32_t a_bytes = (p.dbg & 16) ? 0u : a_box * (uint32_t)(p.planes * ntile);
+                        const uint32_t w_bytes = (p.dbg & 32) ? 0u : w_plane * (uint32_t)(p.planes * p.tpg);
+                        if (a_bytes + w_bytes) mbar_expect_tx(full, a_bytes + w_bytes);
+                        else mbar_arrive(full);
+                        const uint32_t base = ring + stage_bytes * st;
+                        for (int t = 0; t < ntile && a_bytes; ++t) {
+                            const uint32_t dst = base + a_tile * (uint32_t)t;
+                            const int r0 = (mt_first + t) * BM + p.goff[g];
+                            tma_load_3d(dst, &tmA, kc * p.bk, r0, 0, full);
+                            if (p.planes == 2) tma_load_3d(dst + a_box, &tmA, kc * p.bk, r0, 1, full);
                         }
+                        for (int s = 0; s < p.tpg && w_bytes; ++s) {
+                            const uint32_t wd = base + a_part + w_tap * (uint32_t)s;
+                            const int wr = p.wrow[g][s] + nt * p.BN;
+                            tma_load_2d(wd, &tmW, kc * p.bk, wr, full);
+                            if (p.planes == 2) tma_load_2d(wd + w_plane, &tmW, kc * p.bk, p.w_lo_row + wr, full);
+                        }
+                        if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp walks the schedule and waits on the barriers (warp-uniform control flow); one elected lane
+        // issues each stage's MMAs from a single asm block and commits.
+        {
             const uint32_t idesc = make_idesc(BM, p.BN, 0, 0);
-            uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+            const uint32_t layout = p.bk == 64 ? 2u : 4u;            // SWIZZLE_128B / SWIZZLE_64B
+            const uint32_t sbo = 8u * row_bytes;                      // 8-row core-matrix groups
+            // descriptor words: lo = start address >> 4 | LBO (16 B) << 16 ; hi = SBO >> 4 | version 1 << 14 | layout << 29
+            const uint32_t d_lo = 1u << 16;
+            const uint32_t d_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+            const int last_stage = p.ngroups * kchunks - 1;
+            uint32_t st = 0, ph = 0;
             uint32_t it = 0;
-            for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
-                const uint32_t buf = it & 1u, use = it >> 1;
-                mbar_wait(bT_empty + 8u * buf, (use & 1u) ^ 1u);
+            for (int grp = grp0; grp < n_groups; grp += grp_step, ++it) {
+                const int ntile = min(p.T, p.m_tiles - grp * p.T);
+                const uint32_t set = p.nbuf == 2 ? (it & 1u) : 0u, use = p.nbuf == 2 ? (it >> 1) : it;
+                const uint32_t d_tmem0 = tmem_base + set * (uint32_t)(p.T * p.BN);
+                // the epilogue must have drained this accumulator set (earlier group)
+                for (int t = 0; t < ntile; ++t) mbar_wait(bT_empty + 8u * (set * MAX_T + (uint32_t)t), (use & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * 256u;
-                uint32_t acc = 0;
-                for (int g = 0; g < p.ngroups; ++g) {
-                    for (int kc = 0; kc < kchunks; ++kc) {
-                        mbar_wait(bA_full + 8u * sa, pa);
-                        tc_fence_after();
-                        const uint32_t a_base = a_ring + a_stage * sa;
-                        int ksteps = (p.K - kc * BK + 15) / 16;
-                        if (ksteps > BK / 16) ksteps = BK / 16;
-                        for (int s = 0; s < p.tpg; ++s) {
-                            mbar_wait(bW_full + 8u * sw, pw);
-                            tc_fence_after();
-                            const uint32_t w_base = w_ring + w_stage * sw;
-                            const uint32_t boff = p.base_off_mode ? (uint32_t)s : 0u;
-                            for (int k = 0; k < ksteps; ++k) {
-                                const uint64_t a_hi = make_desc(a_base + s * 128u + k * 32u, 16, 1024, boff);
-                                const uint64_t b_hi = make_desc(w_base + k * 32u, 16, 1024, 0);
-                                if (p.planes == 2) {
-                                    const uint64_t a_lo = make_desc(a_base + a_plane + s * 128u + k * 32u, 16, 1024, boff);
-                                    const uint64_t b_lo = make_desc(w_base + w_plane + k * 32u, 16, 1024, 0);
-                                    umma_bf16(d_tmem, a_lo, b_hi, idesc, acc);
-                                    umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-                                    umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
-                                } else {
-                                    umma_bf16(d_tmem, a_hi, b_hi, idesc, acc);
-                                }
-                                acc = 1u;
-                            }
-                            umma_commit(bW_empty + 8u * sw);
-                            if (++sw == (uint32_t)p.nW) { sw = 0; pw ^= 1u; }
+                int kc = 0;
+                for (int sidx = 0; sidx <= last_stage; ++sidx) {
+                    mbar_wait(b_full + 8u * st, ph);
+                    tc_fence_after();
+                    const uint32_t base = ring + stage_bytes * st;
+                    int ksteps = (p.K - kc * p.bk + 15) / 16;
+                    if (ksteps > p.bk / 16) ksteps = p.bk / 16;
+                    if (elect_one()) {
+                        const uint64_t a_hi = ((uint64_t)d_hi << 32) | (d_lo | ((base & 0x3FFFFu) >> 4));
+                        const uint64_t b_hi = ((uint64_t)d_hi << 32) | (d_lo | (((base + a_part) & 0x3FFFFu) >> 4));
+                        if (p.dbg & 8) {
+                        } else if (p.planes == 2) {
+                            umma_stage_x3(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
+                                          w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
+                        } else {
+                            umma_stage_x1(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
+                                          w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
                         }
-                        umma_commit(bA_empty + 8u * sa);
-                        if (++sa == (uint32_t)p.nA) { sa = 0; pa ^= 1u; }
+                        umma_commit(b_empty + 8u * st);
+                        if (sidx == last_stage)
+                            for (int t = 0; t < ntile; ++t) umma_commit(bT_full + 8u * (set * MAX_T + (uint32_t)t));
                     }
+                    __syncwarp();
+                    if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1u; }
+                    if (++kc == kchunks) kc = 0;
                 }
-                umma_commit(bT_full + 8u * buf);
             }
         }
     } else {
-        // ====== epilogue: TMEM -> registers (+bias) -> swizzled smem box -> TMA store; column statistics by shuffles ======
+        // ====== epilogue: TMEM -> registers (128-column chunks) -> (+bias) swizzled smem boxes -> TMA stores;
+        //        column statistics are summed from the staged boxes ======
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
         const int rl = q * 32 + lane;              // this thread's row within the tile
         const uint32_t stg0 = epi_stage + (uint32_t)(q * p.nstg) * EPI_BOX_BYTES;
+        const unsigned char* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
+        double* my_acc = stat_acc + (size_t)q * 2 * p.BN;
         uint32_t sb = 0;                           // staging buffer toggle
-        double acc1[8], acc2[8];                   // lane l: column 32*pn + l of this CTA's column tile
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { acc1[i] = 0.0; acc2[i] = 0.0; }
         uint32_t it = 0;
-        for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
-            const uint32_t buf = it & 1u, use = it >> 1;
-            const long long m0 = (long long)mt * BM;
-            bool interior = false;
-            if (p.stats) {
-                const long long row = m0 + rl;
-                interior = row < p.rows && (p.mask == nullptr || p.mask[row] != 0);
+        // interior flags of this thread's row in each tile of the NEXT group (global loads issued a group ahead)
+        unsigned char inext[MAX_T];
+        auto load_flags = [&](int grp) {
+#pragma unroll
+            for (int t = 0; t < MAX_T; ++t) {
+                const long long row = ((long long)grp * p.T + t) * BM + rl;
+                inext[t] = (p.stats && grp < n_groups && t < p.T && row < p.rows) ? (p.mask ? p.mask[row] : 1) : 0;
             }
-            mbar_wait(bT_full + 8u * buf, use & 1u);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+        };
+        load_flags(grp0);
+        for (int grp = grp0; grp < n_groups; grp += grp_step, ++it) {
+            const int mt_first = grp * p.T;
+            const int ntile = min(p.T, p.m_tiles - mt_first);
+            const uint32_t set = p.nbuf == 2 ? (it & 1u) : 0u, use = p.nbuf == 2 ? (it >> 1) : it;
+            uint32_t ibits[MAX_T];
 #pragma unroll
-            for (int pn = 0; pn < 8; ++pn) {
-                if (pn * 32 < p.BN) {
-                    const bool wide = p.BN - pn * 32 >= 32;                 // BN is a multiple of 16: 32 or 16 columns
-                    const int n = nt * p.BN + pn * 32;                      // first global column of the panel
-                    float v[32];
-                    if (wide) {
-                        tmem_ld32(taddr + (uint32_t)(pn * 32), v);
-                    } else {
-                        tmem_ld16(taddr + (uint32_t)(pn * 32), v);
+            for (int t = 0; t < MAX_T; ++t) ibits[t] = __ballot_sync(0xffffffffu, inext[t] != 0);
+            load_flags(grp + grp_step);
 #pragma unroll
-                        for (int i = 16; i < 32; ++i) v[i] = 0.f;
-                    }
-                    if ((pn + 1) * 32 >= p.BN) {       // accumulator drained: hand the TMEM buffer back early
-                        tc_fence_before();
-                        mbar_arrive(bT_empty + 8u * buf);
-                    }
-                    // the staging buffer about to be overwritten was read by the TMA store issued two panels ago
-                    if (lane == 0) {
-                        if (p.nstg == 2) bulk_wait_read<1>();
-                        else bulk_wait_read<0>();
-                    }
-                    __syncwarp();
-                    const uint32_t stg = stg0 + sb * EPI_BOX_BYTES;
-                    if (wide) {
+            for (int t = 0; t < MAX_T; ++t) {
+                if (t < ntile) {
+                    const long long m0 = (long long)(mt_first + t) * BM;
+                    const uint32_t slot = set * MAX_T + (uint32_t)t;
+                    mbar_wait(bT_full + 8u * slot, use & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + (set * (uint32_t)p.T + (uint32_t)t) * (uint32_t)p.BN + ((uint32_t)(q * 32) << 16);
+                    for (int c0 = 0; c0 < p.BN; c0 += 128) {
+                        // ---- this thread's row, columns [c0, c0 + width): one burst of TMEM loads, one wait
+                        const int width = min(128, p.BN - c0);               // multiple of 16
+                        float v[128];
+                        {
+                            const uint32_t ta = taddr + (uint32_t)c0;       // register positions are compile-time
+                            if (width >= 64) {
+                                tmem_ld64_async(ta, v);
+                                const int r = width - 64;
+                                if (r >= 64) tmem_ld64_async(ta + 64u, v + 64);
+                                else if (r >= 32) { tmem_ld32_async(ta + 64u, v + 64); if (r >= 48) tmem_ld16_async(ta + 96u, v + 96); }
+                                else if (r >= 16) tmem_ld16_async(ta + 64u, v + 64);
+                            } else if (width >= 32) {
+                                tmem_ld32_async(ta, v);
+                                if (width >= 48) tmem_ld16_async(ta + 32u, v + 32);
+                            } else {
+                                tmem_ld16_async(ta, v);
+                            }
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int cg = n + 4 * j;
-                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (cg < p.ldz) b4 = *reinterpret_cast<const float4*>(bias_s + cg);
-                            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-                            st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1],
-                                         v[4 * j + 2], v[4 * j + 3]);
+                            for (int i = 0; i < 128; ++i) pin(v[i]);
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int cg = n + 4 * j;
-                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (cg < p.ldz) b4 = *reinterpret_cast<const float4*>(bias_s + cg);
-                            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-                            st_shared_v4(stg + (uint32_t)lane * 64u + (uint32_t)(j << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2],
-                                         v[4 * j + 3]);
+                        if (c0 + 128 >= p.BN) {            // accumulator drained: hand it back to the MMA warp at once
+                            tc_fence_before();
+                            mbar_arrive(bT_empty + 8u * slot);
                         }
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && m0 + q * 32 < p.rows) {
-                        tma_store_2d(wide ? &tmZ32 : &tmZ16, stg, n, (int)m0 + q * 32);
-                        bulk_commit();
-                    }
-                    sb = (sb + 1u) & (uint32_t)(p.nstg - 1);
-                    if (p.stats) {
-                        float w2[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            v[i] = interior ? v[i] : 0.f;
-                            w2[i] = v[i] * v[i];
+                        for (int pn = 0; pn < 4; ++pn) {
+                            const int cl0 = c0 + pn * 32;                           // first column within the CTA's column tile
+                            if (pn * 32 < width) {
+                                const bool wide = width - pn * 32 >= 32;           // 32 or 16 columns
+                                // the staging buffer about to be overwritten was read by the TMA store issued nstg panels ago
+                                if (lane == 0 && !(p.dbg & 1)) {
+                                    if (p.nstg == 2) bulk_wait_read<1>();
+                                    else bulk_wait_read<0>();
+                                }
+                                __syncwarp();
+                                const uint32_t stg = stg0 + sb * EPI_BOX_BYTES;
+                                const float* stg_g = reinterpret_cast<const float*>(stg0_g + sb * EPI_BOX_BYTES);
+                                const uint32_t rb = wide ? 128u : 64u;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    if ((wide || j < 4) && !(p.dbg & 4)) {
+                                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cl0 + 4 * j);
+                                        const uint32_t ch = wide ? (uint32_t)((j ^ (lane & 7)) << 4) : (uint32_t)(j << 4);
+                                        const float* vv = v + pn * 32 + 4 * j;
+                                        st_shared_v4(stg + (uint32_t)lane * rb + ch, vv[0] + b4.x, vv[1] + b4.y, vv[2] + b4.z,
+                                                     vv[3] + b4.w);
+                                    }
+                                }
+                                fence_async_smem();
+                                __syncwarp();
+                                if (lane == 0 && m0 + q * 32 < p.rows && !(p.dbg & 1)) {
+                                    tma_store_2d(wide ? &tmZ32 : &tmZ16, stg, nt * p.BN + cl0, (int)m0 + q * 32);
+                                    bulk_commit();
+                                }
+                                if (p.stats && (wide || lane < 16) && !(p.dbg & 2)) {
+                                    // lane l sums column cl0 + l over this warp's interior rows, straight from the staged box
+                                    const uint32_t bits = ibits[t];
+                                    float s1 = 0.f, s2 = 0.f;
+                                    if (wide) {
+#pragma unroll
+                                        for (int r = 0; r < 32; ++r) {
+                                            const float x = stg_g[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+                                            if ((bits >> r) & 1u) { s1 += x; s2 = fmaf(x, x, s2); }
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int r = 0; r < 32; ++r) {
+                                            const float x = stg_g[r * 16 + lane];
+                                            if ((bits >> r) & 1u) { s1 += x; s2 = fmaf(x, x, s2); }
+                                        }
+                                    }
+                                    my_acc[cl0 + lane] += (double)s1;
+                                    my_acc[p.BN + cl0 + lane] += (double)s2;
+                                }
+                                sb = (sb + 1u) & (uint32_t)(p.nstg - 1);
+                            }
                         }
-                        warp_column_sums(v, lane);
-                        warp_column_sums(w2, lane);
-                        acc1[pn] += (double)v[0];
-                        acc2[pn] += (double)w2[0];
                     }
                 }
             }
         }
         if (lane == 0) bulk_wait_all();            // the staged boxes must be written before the CTA retires
         if (p.stats) {
-            // merge the four warps' partials in warp order (fixed order: deterministic), then publish the CTA record
-            for (int w = 0; w < 4; ++w) {
-                if (q == w) {
-#pragma unroll
-                    for (int pn = 0; pn < 8; ++pn) {
-                        const int cl = pn * 32 + lane, cg = nt * p.BN + cl;
-                        if (cl < p.BN && cg < p.ldz) {
-                            stat_acc[cg] += acc1[pn];
-                            stat_acc[p.ldz + cg] += acc2[pn];
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
+            // merge the four warps' partials in warp order (deterministic) and publish the CTA record: zero
+            // outside this CTA's column tile
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             double* o = p.stats + (long long)blockIdx.x * 2 * p.ldz;
-            for (int i = threadIdx.x - 64; i < 2 * p.ldz; i += 128) o[i] = stat_acc[i];
+            const int e = threadIdx.x - 64;
+            for (int i = e; i < 2 * p.ldz; i += 128) {
+                const int h = i >= p.ldz ? 1 : 0;
+                const int cl = i - h * p.ldz - nt * p.BN;
+                double tot = 0.0;
+                if (cl >= 0 && cl < p.BN) {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) tot += stat_acc[(size_t)(w * 2 + h) * p.BN + cl];
+                }
+                o[i] = tot;
+            }
         }
     }
     tc_fence_before();
@@ -675,7 +1065,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // activation planes: (C, rows, 2 planes) bf16, box (64, box_rows, 1)
-int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int box_rows) {
+int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int box_rows, int bk = BK) {
     auto fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -683,10 +1073,11 @@ int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int b
     }
     cuuint64_t dims[3] = {(cuuint64_t)Cs, (cuuint64_t)rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)Cs * 2, (cuuint64_t)rows * Cs * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(act rows=%lld Cs=%d box=%d) failed: %d", rows, Cs, box_rows, (int)r);
@@ -696,7 +1087,7 @@ int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int b
 }
 
 // packed weights: (Kpad, total_rows) bf16, box (64, box_rows)
-int make_w_map(CUtensorMap* m, const void* base, long long total_rows, int kpad, int box_rows) {
+int make_w_map(CUtensorMap* m, const void* base, long long total_rows, int kpad, int box_rows, int bk = BK) {
     auto fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -704,10 +1095,11 @@ int make_w_map(CUtensorMap* m, const void* base, long long total_rows, int kpad,
     }
     cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)total_rows};
     cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(weights rows=%lld kpad=%d box=%d) failed: %d", total_rows, kpad, box_rows, (int)r);
@@ -735,6 +1127,11 @@ int make_out_map(CUtensorMap* m, const float* base, long long rows, int ldz, int
         return FSB_E_INVALID;
     }
     return 0;
+}
+
+int tc_env(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
 }
 
 int tc_mode() {
@@ -794,41 +1191,59 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     p.n_tiles = nt;
     p.BN = bn;
     p.K = K;
-    int tap_of[9][3];
-    group_taps(c, sign, !(tc_mode() & 1), p.ngroups, p.tpg, p.goff, tap_of);
-    for (int g = 0; g < p.ngroups; ++g)
-        for (int t = 0; t < p.tpg; ++t) p.wrow[g][t] = tap_of[g][t] * w_npad;
     p.w_lo_row = c.ntaps * w_npad;
-    p.a_box_rows = p.tpg == 1 ? BM : BM + A_HALO;
     p.planes = precision == 1 ? 2 : 1;
     p.base_off_mode = (tc_mode() & 2) ? 1 : 0;
     p.Z = Z;
     p.ldz = ldz;
     p.bias = bias;
-    const size_t a_stage = (size_t)p.a_box_rows * 128 * 2, w_stage = (size_t)bn * 128 * 2;
     if (st) {
         const Geo& g = *st->g;
         FSB_REQUIRE(g.rows == rows && g.Cs == ldz, "conv_tc: statistics geometry does not match the output");
         p.stats = st->partials;
         p.mask = g.mask;
     }
-    size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (((size_t)ldz * 4 + 15) & ~(size_t)15) /*bias*/ +
-                   (size_t)16 * ldz /*statistics*/;
-    p.nstg = fixed + 8 * EPI_BOX_BYTES + 2 * a_stage + 2 * w_stage <= SMEM_LIMIT ? 2 : 1;
-    fixed += (size_t)4 * p.nstg * EPI_BOX_BYTES;   // TMA-store staging
-    // ring depths: at least 2 each; give W the stages it needs to cover one A stage, then grow both
-    p.nA = 2; p.nW = 2;
-    for (;;) {
-        bool grown = false;
-        if (p.nW < 6 && fixed + a_stage * p.nA + w_stage * (p.nW + 1) <= SMEM_LIMIT) { ++p.nW; grown = true; }
-        if (p.nA < 4 && p.nA * p.tpg < p.nW + 1 && fixed + a_stage * (p.nA + 1) + w_stage * p.nW <= SMEM_LIMIT) { ++p.nA; grown = true; }
-        if (!grown) break;
+    FSB_REQUIRE(p.n_tiles <= num_sms() && bn <= 256 && bn % 16 == 0, "conv_tc: bad column tiling (%d x %d)", p.n_tiles, bn);
+    // Two row tiles per group when two accumulator sets of two tiles fit in the 512 TMEM columns (BN <= 128), else
+    // one; never more tiles per group than needed to give every CTA a group.
+    const int ctas_per_col = num_sms() / p.n_tiles;
+    int T = 4 * bn <= 512 ? 2 : 1;
+    if (tc_env("FSB200_TC_T") == 1) T = 1;
+    while (T > 1 && (p.m_tiles + T - 1) / T < ctas_per_col) --T;
+    const int nbuf = 2 * T * bn <= 512 ? 2 : 1;
+    const size_t fixed0 = 1024 /*align*/ + 1024 /*staging align*/ + 256 /*barriers*/ +
+                          (((size_t)bn * 4 + 15) & ~(size_t)15) /*bias*/ + (size_t)64 * bn /*statistics*/;
+    // Stage shape.  Preferred: the three dx taps of a dy share one (128 + 8)-row activation box (a third of the
+    // activation fills); wide tiles whose three weight tiles do not fit beside it fall back to one box per tap.
+    // Stage width: 64 channels (SWIZZLE_128B) when three stages and the double-buffered store staging fit, else 32
+    // channels (SWIZZLE_64B); staging falls back to single buffering before the ring drops below two stages.
+    size_t stage = 0, fixed = 0;
+    bool ok = false;
+    for (int share = (tc_mode() & 1) ? 0 : 1; share >= 0 && !ok; --share) {
+        int tap_of[9][3];
+        group_taps(c, sign, share != 0, p.ngroups, p.tpg, p.goff, tap_of);
+        for (int g = 0; g < p.ngroups; ++g)
+            for (int t = 0; t < p.tpg; ++t) p.wrow[g][t] = tap_of[g][t] * w_npad;
+        p.a_box_rows = p.tpg == 1 ? BM : BM + A_HALO;
+        for (int bk = (tc_env("FSB200_TC_BK") == 32 ? 32 : 64); bk >= 32 && !ok; bk -= 32) {
+            stage = ((size_t)p.a_box_rows * T + (size_t)bn * p.tpg) * bk * 2 * 2;
+            for (int nstg = 2; nstg >= 1 && !ok; --nstg) {
+                fixed = fixed0 + (size_t)4 * nstg * EPI_BOX_BYTES;
+                const int need = (bk == 64 && nstg == 2) ? 3 : 2;
+                if (fixed + need * stage <= SMEM_LIMIT) { p.bk = bk; p.nstg = nstg; ok = true; }
+            }
+        }
     }
-    const size_t smem = fixed + a_stage * p.nA + w_stage * p.nW;
-    FSB_REQUIRE(smem <= SMEM_LIMIT, "conv_tc: shared memory %zu exceeds the limit (BN=%d)", smem, bn);
+    FSB_REQUIRE(ok, "conv_tc: tile does not fit in shared memory (BN=%d)", bn);
+    p.T = T;
+    p.nbuf = nbuf;
+    p.dbg = tc_env("FSB200_TC_DBG");
+    p.nstages = (int)((SMEM_LIMIT - fixed) / stage);
+    if (p.nstages > 8) p.nstages = 8;
+    const size_t smem = fixed + stage * p.nstages;
     CUtensorMap tmA, tmW, tmZ32, tmZ16;
-    FSB_TRY(make_act_map(&tmA, A, rows, K, p.a_box_rows));
-    FSB_TRY(make_w_map(&tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn));
+    FSB_TRY(make_act_map(&tmA, A, rows, K, p.a_box_rows, p.bk));
+    FSB_TRY(make_w_map(&tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn, p.bk));
     FSB_TRY(make_out_map(&tmZ32, Z, rows, ldz, 32, true));
     FSB_TRY(make_out_map(&tmZ16, Z, rows, ldz, 16, false));
     static bool attr_set = false;
@@ -837,8 +1252,8 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
         attr_set = true;
     }
     // every CTA owns one column tile: the grid is a multiple of n_tiles
-    FSB_REQUIRE(p.n_tiles <= num_sms() && bn <= 256, "conv_tc: too many column tiles (%d)", p.n_tiles);
-    int grid = p.m_tiles < num_sms() / p.n_tiles ? p.m_tiles * p.n_tiles : num_sms() / p.n_tiles * p.n_tiles;
+    const int n_groups = (p.m_tiles + T - 1) / T;
+    int grid = (n_groups < ctas_per_col ? n_groups : ctas_per_col) * p.n_tiles;
     conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmW, tmZ32, tmZ16, p);
     FSB_LAUNCHED();
     if (st) *st->nblk = grid;
