@@ -148,7 +148,9 @@ def test_fused_adam_multi_tensor_matches_torch():
 
 # ------------------------------------------------------------------------------------------ conv GEMMs
 CONV_CASES = [(2, 5, 7, 6, 9, 3, 3), (3, 19, 33, 5, 11, 1, 1), (2, 37, 21, 1, 50, 1, 3), (1, 100, 150, 8, 13, 3, 3),
-              (2, 16, 16, 4, 130, 3, 3)]
+              (2, 16, 16, 4, 130, 3, 3),
+              # wide tiles (N = 240 / 256 / 2 x 176): one activation box per tap, single accumulator set
+              (1, 225, 250, 6, 9, 3, 3), (2, 337, 240, 5, 7, 3, 3), (1, 506, 337, 4, 13, 1, 1)]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])

@@ -149,6 +149,8 @@ def test_canonical_width_against_oracle(precision):
             l2 = np.sqrt(((got - ref) ** 2).sum()) / max(np.sqrt((ref ** 2).sum()), 1e-3 * gmax)
             assert l2 <= l2_gate, (k, l2)
         loose = 0.25 if ref.size < 8 else 0.1       # BN_in of block 0 has two elements: one flip is 1/2 of it
+        if precision != "fp32":
+            loose = 0.3                             # see the conditioning note above (single worst element)
         assert np.abs(got - ref).max() <= loose * np.abs(ref).max() + 2e-3 * gmax, k
 
 
