@@ -223,26 +223,16 @@ class _AcceleratedCNN(nn.Module):
 
     def _sync_gradients(self):
         """Data parallel: ONE all-reduce (SUM) of the flat gradient, averaged inside the Adam kernel."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        from fsb200 import dist as fdist
+        if fdist.world()[1] == 1:
             return
-        flat = getattr(self._plan, "last_flat_grad", None)
-        first = self._param_list[0]
-        if flat is not None and first.grad is not None and first.grad.data_ptr() == flat.data_ptr():
-            dist.all_reduce(flat)
-        else:                                   # gradients were accumulated/cloned by autograd
-            grads = [p.grad for p in self._param_list]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat)
-            off = 0
-            for g in grads:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+        scale = fdist.allreduce_gradients([p.grad for p in self._param_list],
+                                          flat=getattr(self._plan, "last_flat_grad", None))
         if hasattr(self.optimizer, "grad_scale"):
-            self.optimizer.grad_scale = 1.0 / dist.get_world_size()
+            self.optimizer.grad_scale = scale
         else:
             for p in self._param_list:
-                p.grad.div_(dist.get_world_size())
+                p.grad.mul_(scale)
 
     def train_epoch(self, train_loader, epoch, log_interval, write_summary=True):
         """Reference :633-707.  Same per-batch order of operations (LR step, forward, LSEP/accum, backward,

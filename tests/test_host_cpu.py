@@ -143,3 +143,58 @@ def test_rnn_aggregation_is_rejected():
     with pytest.raises(NotImplementedError):
         nc.TwoDimensionalCNNClassificationModel(
             FakeExperiment(make_config(conv_base_depth=8, aggregation_type="rnn")), device="cpu")
+
+
+def _dp_worker(rank, world_size, port, out_dir):
+    """world-size-2 data-parallel step on CPU (gloo): per-rank oracle gradients on a batch shard, one flat all-reduce."""
+    import torch.distributed as dist
+    from fsb200 import dist as fdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        assert fdist.world() == (rank, world_size)
+        cfg = make_config(conv_base_depth=4, growth_rate=1.5, num_conv_blocks=5)
+        sd = restate.init_state_dict(cfg, two_d=True, seed=42)
+        names = [k for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k]
+        params = {k: (v.clone().requires_grad_() if k in names else v.clone()) for k, v in sd.items()}
+        n, t = 4, 40000
+        wav = torch.from_numpy(restate.synth_waveforms(n, t, seed=5))[..., None]
+        labels = torch.from_numpy(restate.synth_labels(n, 80, seed=5))
+        b, e = fdist.shard_range(n, rank, world_size)
+        out = restate.net2d_forward(params, cfg, wav[b:e], training=True)
+        restate.lsep_loss(out, labels[b:e], average=False).mean().backward()
+        grads = [params[k].grad for k in names]
+        local = torch.cat([g.reshape(-1) for g in grads]).clone()
+        # path 1: gradients are views of one flat buffer -> a single in-place collective
+        flat = local.clone()
+        views, off = [], 0
+        for g in grads:
+            views.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        scale = fdist.allreduce_gradients(views, flat=flat)
+        # path 2: separately allocated gradients -> packed, reduced, copied back
+        scale2 = fdist.allreduce_gradients(grads, flat=None)
+        assert scale == scale2 == 1.0 / world_size
+        assert torch.equal(torch.cat([g.reshape(-1) for g in grads]), flat)
+        np.save(os.path.join(out_dir, "local_%d.npy" % rank), local.numpy())
+        np.save(os.path.join(out_dir, "summed_%d.npy" % rank), flat.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    from fsb200 import dist as fdist
+    assert [fdist.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert fdist.shard_range(3, 1, 2) == (2, 3)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    l0, l1 = np.load(tmp_path / "local_0.npy"), np.load(tmp_path / "local_1.npy")
+    s0, s1 = np.load(tmp_path / "summed_0.npy"), np.load(tmp_path / "summed_1.npy")
+    assert np.array_equal(s0, s1)                       # every rank holds the same summed gradient
+    assert np.allclose(s0, l0 + l1, rtol=0, atol=1e-6 * np.abs(s0).max())
+    assert np.abs(l0 - l1).max() > 0                    # the shards really differed
