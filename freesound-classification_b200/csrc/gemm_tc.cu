@@ -37,7 +37,6 @@ constexpr int A_HALO = 8;          // extra rows of the A box (row shifts 0..2 u
 constexpr int TC_THREADS = 192;    // 6 warps
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int WG_R = 64;           // wgrad: pixel rows per pipeline stage
-constexpr int WG_BN = 128;         // wgrad: input channels per tile
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -458,6 +457,203 @@ __device__ __forceinline__ void umma_stage_x1(uint32_t d_tmem0, uint32_t bn, uin
           "r"(idesc), "r"(acc), "r"(ksteps), "r"(ntile), "r"(ntaps)
         : "memory");
 }
+// wgrad: all MMAs of one 64-pixel-row stage -- up to 3 dx taps (one accumulator each, `ncol` TMEM columns apart) x 4
+// k-steps (16 rows = 2048 bytes apart in both MN-major operands) x 3 products -- in one asm block (see umma_stage_x3).
+// The tap shift (one smem row = 128 bytes = 8 descriptor units) applies to whichever operand holds the activations.
+__device__ __forceinline__ void umma_wgrad_x3(uint32_t d0, uint32_t ncol, uint64_t m_hi, uint64_t m_lo, uint64_t n_hi,
+                                              uint64_t n_lo, uint32_t m_shift16, uint32_t n_shift16, uint32_t idesc,
+                                              uint32_t acc, int ntaps) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, pt, ps1, ps2;\n\t"
+        ".reg .b32 d;\n\t"
+        ".reg .b64 mh, ml, nh, nl, ms, ns, xh, xl, yh, yl;\n\t"
+        "setp.ne.b32 pacc, %9, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.gt.s32 ps1, %10, 1;\n\t"
+        "setp.gt.s32 ps2, %10, 2;\n\t"
+        "mov.b32 d, %0;\n\t"
+        "cvt.u64.u32 ms, %6;\n\t"
+        "cvt.u64.u32 ns, %7;\n\t"
+        "mov.b64 mh, %2;\n\t"
+        "mov.b64 ml, %3;\n\t"
+        "mov.b64 nh, %4;\n\t"
+        "mov.b64 nl, %5;\n\t"
+        "add.u64 xh, mh, 0;\n\t"
+        "add.u64 yh, nh, 0;\n\t"
+        "add.u64 xl, ml, 0;\n\t"
+        "add.u64 yl, nl, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pacc;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 128;\n\t"
+        "add.u64 yh, nh, 128;\n\t"
+        "add.u64 xl, ml, 128;\n\t"
+        "add.u64 yl, nl, 128;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 256;\n\t"
+        "add.u64 yh, nh, 256;\n\t"
+        "add.u64 xl, ml, 256;\n\t"
+        "add.u64 yl, nl, 256;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 384;\n\t"
+        "add.u64 yh, nh, 384;\n\t"
+        "add.u64 xl, ml, 384;\n\t"
+        "add.u64 yl, nl, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "@!ps1 bra.uni DONE;\n\t"
+        "add.u32 d, d, %1;\n\t"
+        "add.u64 mh, mh, ms;\n\t"
+        "add.u64 ml, ml, ms;\n\t"
+        "add.u64 nh, nh, ns;\n\t"
+        "add.u64 nl, nl, ns;\n\t"
+        "add.u64 xh, mh, 0;\n\t"
+        "add.u64 yh, nh, 0;\n\t"
+        "add.u64 xl, ml, 0;\n\t"
+        "add.u64 yl, nl, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pacc;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 128;\n\t"
+        "add.u64 yh, nh, 128;\n\t"
+        "add.u64 xl, ml, 128;\n\t"
+        "add.u64 yl, nl, 128;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 256;\n\t"
+        "add.u64 yh, nh, 256;\n\t"
+        "add.u64 xl, ml, 256;\n\t"
+        "add.u64 yl, nl, 256;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 384;\n\t"
+        "add.u64 yh, nh, 384;\n\t"
+        "add.u64 xl, ml, 384;\n\t"
+        "add.u64 yl, nl, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "@!ps2 bra.uni DONE;\n\t"
+        "add.u32 d, d, %1;\n\t"
+        "add.u64 mh, mh, ms;\n\t"
+        "add.u64 ml, ml, ms;\n\t"
+        "add.u64 nh, nh, ns;\n\t"
+        "add.u64 nl, nl, ns;\n\t"
+        "add.u64 xh, mh, 0;\n\t"
+        "add.u64 yh, nh, 0;\n\t"
+        "add.u64 xl, ml, 0;\n\t"
+        "add.u64 yl, nl, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pacc;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 128;\n\t"
+        "add.u64 yh, nh, 128;\n\t"
+        "add.u64 xl, ml, 128;\n\t"
+        "add.u64 yl, nl, 128;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 256;\n\t"
+        "add.u64 yh, nh, 256;\n\t"
+        "add.u64 xl, ml, 256;\n\t"
+        "add.u64 yl, nl, 256;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 384;\n\t"
+        "add.u64 yh, nh, 384;\n\t"
+        "add.u64 xl, ml, 384;\n\t"
+        "add.u64 yl, nl, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "DONE:\n\t"
+        "}"
+        ::"r"(d0), "r"(ncol), "l"(m_hi), "l"(m_lo), "l"(n_hi), "l"(n_lo), "r"(m_shift16), "r"(n_shift16), "r"(idesc), "r"(acc),
+          "r"(ntaps)
+        : "memory");
+}
+__device__ __forceinline__ void umma_wgrad_x1(uint32_t d0, uint32_t ncol, uint64_t m_hi, uint64_t m_lo, uint64_t n_hi,
+                                              uint64_t n_lo, uint32_t m_shift16, uint32_t n_shift16, uint32_t idesc,
+                                              uint32_t acc, int ntaps) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, pt, ps1, ps2;\n\t"
+        ".reg .b32 d;\n\t"
+        ".reg .b64 mh, ml, nh, nl, ms, ns, xh, xl, yh, yl;\n\t"
+        "setp.ne.b32 pacc, %9, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.gt.s32 ps1, %10, 1;\n\t"
+        "setp.gt.s32 ps2, %10, 2;\n\t"
+        "mov.b32 d, %0;\n\t"
+        "cvt.u64.u32 ms, %6;\n\t"
+        "cvt.u64.u32 ns, %7;\n\t"
+        "mov.b64 mh, %2;\n\t"
+        "mov.b64 ml, %3;\n\t"
+        "mov.b64 nh, %4;\n\t"
+        "mov.b64 nl, %5;\n\t"
+        "add.u64 xh, mh, 0;\n\t"
+        "add.u64 yh, nh, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pacc;\n\t"
+        "add.u64 xh, mh, 128;\n\t"
+        "add.u64 yh, nh, 128;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 256;\n\t"
+        "add.u64 yh, nh, 256;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 384;\n\t"
+        "add.u64 yh, nh, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "@!ps1 bra.uni DONE;\n\t"
+        "add.u32 d, d, %1;\n\t"
+        "add.u64 mh, mh, ms;\n\t"
+        "add.u64 ml, ml, ms;\n\t"
+        "add.u64 nh, nh, ns;\n\t"
+        "add.u64 nl, nl, ns;\n\t"
+        "add.u64 xh, mh, 0;\n\t"
+        "add.u64 yh, nh, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pacc;\n\t"
+        "add.u64 xh, mh, 128;\n\t"
+        "add.u64 yh, nh, 128;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 256;\n\t"
+        "add.u64 yh, nh, 256;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 384;\n\t"
+        "add.u64 yh, nh, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "@!ps2 bra.uni DONE;\n\t"
+        "add.u32 d, d, %1;\n\t"
+        "add.u64 mh, mh, ms;\n\t"
+        "add.u64 ml, ml, ms;\n\t"
+        "add.u64 nh, nh, ns;\n\t"
+        "add.u64 nl, nl, ns;\n\t"
+        "add.u64 xh, mh, 0;\n\t"
+        "add.u64 yh, nh, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pacc;\n\t"
+        "add.u64 xh, mh, 128;\n\t"
+        "add.u64 yh, nh, 128;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 256;\n\t"
+        "add.u64 yh, nh, 256;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "add.u64 xh, mh, 384;\n\t"
+        "add.u64 yh, nh, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
+        "DONE:\n\t"
+        "}"
+        ::"r"(d0), "r"(ncol), "l"(m_hi), "l"(m_lo), "l"(n_hi), "l"(n_lo), "r"(m_shift16), "r"(n_shift16), "r"(idesc), "r"(acc),
+          "r"(ntaps)
+        : "memory");
+}
 // one lane of a fully converged warp (always the same one)
 __device__ __forceinline__ bool elect_one() {
     uint32_t ok;
@@ -849,14 +1045,15 @@ struct WgradTcParams {
     long long rows;
     long long rows_per_split;   // multiple of WG_R
     int splits;
-    int co_tiles, ci_tiles, ngroups, tpg;
+    int swap;                   // 0: M = output channels (dZ), N = input channels (A);  1: M = input, N = output
+    int m_tiles, n_tiles, bn;   // M tiles of 128 channels, N tiles of bn <= 160 channels (3 x bn TMEM columns)
+    int ngroups, tpg;
     int goff[9];                // row offset of the A box origin per group
     int tap_of[9][3];           // torch tap index of (group, shift)
     int ntaps;
     int CsIn, CsOut;
     int nstages;
     int planes;
-    int base_off_mode;
     float* P;                   // [split][tap][CsIn][CsOut]
 };
 
@@ -866,8 +1063,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t dz_box = WG_R * 128u;                  // one 64-channel box of dZ
     constexpr uint32_t a_box = (WG_R + A_HALO) * 128u;        // one 64-channel box of A (with halo rows)
-    constexpr uint32_t dz_plane = 2u * dz_box;                // 128 output channels
-    constexpr uint32_t a_plane = 2u * a_box;                  // 128 input channels
+    // channels of the two operands in this CTA's tile, in 64-channel boxes
+    const int cz = p.swap ? p.bn : 128, ca = p.swap ? 128 : p.bn;
+    const uint32_t nbz = (uint32_t)(cz + 63) / 64u, nba = (uint32_t)(ca + 63) / 64u;
+    const uint32_t dz_plane = nbz * dz_box, a_plane = nba * a_box;
     const uint32_t stage_bytes = (dz_plane + a_plane) * 2u;   // hi + lo (lo unused when planes == 1)
     const uint32_t ring = smem_base;
     const uint32_t bars = ring + stage_bytes * p.nstages;
@@ -879,12 +1078,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
     // work item
     int item = blockIdx.x;
     const int sp = item % p.splits; item /= p.splits;
-    const int cit = item % p.ci_tiles; item /= p.ci_tiles;
-    const int cot = item % p.co_tiles; item /= p.co_tiles;
+    const int ntile = item % p.n_tiles; item /= p.n_tiles;
+    const int mtile = item % p.m_tiles; item /= p.m_tiles;
     const int g = item;
-    const int co0 = cot * 128, ci0 = cit * WG_BN;
-    int bn = p.CsIn - ci0;
-    if (bn > WG_BN) bn = WG_BN;
+    const int m0 = mtile * 128, n0 = ntile * p.bn;
+    const int co0 = p.swap ? n0 : m0, ci0 = p.swap ? m0 : n0;
     const long long rb = (long long)sp * p.rows_per_split;
     long long re = rb + p.rows_per_split;
     if (re > p.rows) re = p.rows;
@@ -915,50 +1113,48 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
                 for (int pl = 0; pl < p.planes; ++pl) {
                     const uint32_t dzd = base + pl * dz_plane;
                     const uint32_t ad = base + 2u * dz_plane + pl * a_plane;
-                    tma_load_3d(dzd, &tmDZ, co0, r, pl, b_full + 8u * st);
-                    tma_load_3d(dzd + dz_box, &tmDZ, co0 + 64, r, pl, b_full + 8u * st);
-                    tma_load_3d(ad, &tmA, ci0, r + p.goff[g], pl, b_full + 8u * st);
-                    tma_load_3d(ad + a_box, &tmA, ci0 + 64, r + p.goff[g], pl, b_full + 8u * st);
+                    for (uint32_t b = 0; b < nbz; ++b) tma_load_3d(dzd + b * dz_box, &tmDZ, co0 + 64 * (int)b, r, pl, b_full + 8u * st);
+                    for (uint32_t b = 0; b < nba; ++b) tma_load_3d(ad + b * a_box, &tmA, ci0 + 64 * (int)b, r + p.goff[g], pl, b_full + 8u * st);
                 }
                 if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, bn, 1, 1);
-            uint32_t st = 0, ph = 0;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                mbar_wait(b_full + 8u * st, ph);
-                tc_fence_after();
-                const uint32_t base = ring + stage_bytes * st;
-                const uint32_t dz_hi = base, dz_lo = base + dz_plane;
-                const uint32_t a_hi = base + 2u * dz_plane, a_lo = a_hi + a_plane;
-                for (int s = 0; s < p.tpg; ++s) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)s * WG_BN;
-                    const uint32_t boff = p.base_off_mode ? (uint32_t)s : 0u;
-                    for (int k = 0; k < WG_R / 16; ++k) {
-                        const uint32_t acc = (ch > 0 || k > 0) ? 1u : 0u;
-                        const uint64_t m_hi = make_desc(dz_hi + k * 2048u, dz_box, 1024, 0);
-                        const uint64_t n_hi = make_desc(a_hi + s * 128u + k * 2048u, a_box, 1024, boff);
-                        if (p.planes == 2) {
-                            const uint64_t m_lo = make_desc(dz_lo + k * 2048u, dz_box, 1024, 0);
-                            const uint64_t n_lo = make_desc(a_lo + s * 128u + k * 2048u, a_box, 1024, boff);
-                            umma_bf16(d_tmem, m_lo, n_hi, idesc, acc);
-                            umma_bf16(d_tmem, m_hi, n_lo, idesc, 1u);
-                            umma_bf16(d_tmem, m_hi, n_hi, idesc, 1u);
-                        } else {
-                            umma_bf16(d_tmem, m_hi, n_hi, idesc, acc);
-                        }
-                    }
+        // whole warp walks the stages (uniform control flow), one elected lane issues each stage from one asm block
+        const uint32_t idesc = make_idesc(128, p.bn, 1, 1);
+        // MN-major SWIZZLE_128B descriptors: LBO = stride between 64-channel boxes, SBO = 8 rows x 128 B
+        const uint32_t hi_word = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t lbo_z = (dz_box >> 4) << 16, lbo_a = (a_box >> 4) << 16;
+        uint32_t st = 0, ph = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            mbar_wait(b_full + 8u * st, ph);
+            tc_fence_after();
+            const uint32_t base = ring + stage_bytes * st;
+            const uint32_t z_hi = base, z_lo = base + dz_plane;
+            const uint32_t a_hi = base + 2u * dz_plane, a_lo = a_hi + a_plane;
+            if (elect_one()) {
+                const uint64_t dzh = ((uint64_t)hi_word << 32) | (lbo_z | ((z_hi & 0x3FFFFu) >> 4));
+                const uint64_t dzl = ((uint64_t)hi_word << 32) | (lbo_z | ((z_lo & 0x3FFFFu) >> 4));
+                const uint64_t dah = ((uint64_t)hi_word << 32) | (lbo_a | ((a_hi & 0x3FFFFu) >> 4));
+                const uint64_t dal = ((uint64_t)hi_word << 32) | (lbo_a | ((a_lo & 0x3FFFFu) >> 4));
+                const uint32_t acc = ch > 0 ? 1u : 0u;
+                if (p.planes == 2) {
+                    if (p.swap) umma_wgrad_x3(tmem_base, (uint32_t)p.bn, dah, dal, dzh, dzl, 8u, 0u, idesc, acc, p.tpg);
+                    else umma_wgrad_x3(tmem_base, (uint32_t)p.bn, dzh, dzl, dah, dal, 0u, 8u, idesc, acc, p.tpg);
+                } else {
+                    if (p.swap) umma_wgrad_x1(tmem_base, (uint32_t)p.bn, dah, dal, dzh, dzl, 8u, 0u, idesc, acc, p.tpg);
+                    else umma_wgrad_x1(tmem_base, (uint32_t)p.bn, dzh, dzl, dah, dal, 0u, 8u, idesc, acc, p.tpg);
                 }
                 umma_commit(b_empty + 8u * st);
-                if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1u; }
+                if (ch == nchunks - 1) umma_commit(b_done);
             }
-            umma_commit(b_done);
+            __syncwarp();
+            if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1u; }
         }
     } else {
         const int q = warp & 3;
-        const int co = co0 + q * 32 + lane;
+        const int m = m0 + q * 32 + lane;                     // this thread's M channel
+        const int m_limit = p.swap ? p.CsIn : p.CsOut, n_limit = p.swap ? p.CsOut : p.CsIn;
         if (nchunks > 0) {
             mbar_wait(b_done, 0);
             tc_fence_after();
@@ -966,8 +1162,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
         for (int s = 0; s < p.tpg; ++s) {
             const int t = p.tap_of[g][s];
             float* Pt = p.P + ((long long)sp * p.ntaps + t) * p.CsIn * p.CsOut;
-            const uint32_t taddr = tmem_base + (uint32_t)s * WG_BN + ((uint32_t)(q * 32) << 16);
-            for (int c = 0; c < bn; c += 16) {
+            const uint32_t taddr = tmem_base + (uint32_t)(s * p.bn) + ((uint32_t)(q * 32) << 16);
+            for (int c = 0; c < p.bn; c += 16) {
                 float v[16];
                 if (nchunks > 0) {
                     tmem_ld16(taddr + (uint32_t)c, v);
@@ -975,9 +1171,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = 0.f;
                 }
-                if (co < p.CsOut) {
+                if (m < m_limit) {
+                    if (p.swap) {            // m = input channel: 16 consecutive output channels are contiguous
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) Pt[(long long)(ci0 + c + i) * p.CsOut + co] = v[i];
+                        for (int i = 0; i < 16; i += 4) {
+                            const int co = n0 + c + i;
+                            if (co < n_limit)
+                                *reinterpret_cast<float4*>(Pt + (long long)m * p.CsOut + co) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        }
+                    } else {                 // m = output channel: consecutive lanes are contiguous
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int ci = n0 + c + i;
+                            if (ci < n_limit) Pt[(long long)ci * p.CsOut + m] = v[i];
+                        }
+                    }
                 }
             }
         }
@@ -1297,45 +1505,67 @@ int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const
                           c.CsOut, c.CsIn, c, -1, nullptr, s);
 }
 
-static void wgrad_shape(const ConvGeom& c, int& ngroups, int& tpg, int& co_tiles, int& ci_tiles, int& splits,
-                        long long& rows_per_split) {
+struct WgradShape {
+    int ngroups, tpg, swap, m_tiles, n_tiles, bn, splits;
+    long long rows_per_split;
+};
+
+// N tiling of `cs` channels: equal tiles of at most 160 channels (3 accumulators x bn <= 512 TMEM columns)
+static void wgrad_n_tiles(int cs, int& nt, int& bn) {
+    nt = (cs + 159) / 160;
+    bn = round_up((cs + nt - 1) / nt, 16);
+}
+
+static WgradShape wgrad_shape(const ConvGeom& c) {
+    WgradShape w;
     int goff[9], tap_of[9][3];
-    group_taps(c, +1, !(tc_mode() & 1), ngroups, tpg, goff, tap_of);
-    co_tiles = (c.CsOut + 127) / 128;
-    ci_tiles = (c.CsIn + WG_BN - 1) / WG_BN;
-    const int items = ngroups * co_tiles * ci_tiles;
+    group_taps(c, +1, !(tc_mode() & 1), w.ngroups, w.tpg, goff, tap_of);
+    // orientation: the M side is padded to 128-channel tiles, the N side to 16; an MMA costs max(N/2, 44) cycles
+    long long cost[2];
+    int mt[2], nt[2], bn[2];
+    for (int sw = 0; sw < 2; ++sw) {
+        const int cm = sw ? c.CsIn : c.CsOut, cn = sw ? c.CsOut : c.CsIn;
+        mt[sw] = (cm + 127) / 128;
+        wgrad_n_tiles(cn, nt[sw], bn[sw]);
+        cost[sw] = (long long)mt[sw] * nt[sw] * (bn[sw] > 88 ? bn[sw] : 88);
+    }
+    w.swap = cost[1] < cost[0] ? 1 : 0;
+    if (tc_env("FSB200_WG_SWAP") == 1) w.swap = 0;
+    if (tc_env("FSB200_WG_SWAP") == 2) w.swap = 1;
+    w.m_tiles = mt[w.swap]; w.n_tiles = nt[w.swap]; w.bn = bn[w.swap];
+    const int items = w.ngroups * w.m_tiles * w.n_tiles;
     long long chunks = (c.rows + WG_R - 1) / WG_R;
     int want = (2 * num_sms()) / items;                 // at most two full waves (one CTA per SM at a time)
     if (want > chunks) want = (int)chunks;
     if (want > 128) want = 128;
     if (want < 1) want = 1;
-    splits = want;
-    rows_per_split = (chunks + splits - 1) / splits * WG_R;
+    w.splits = want;
+    w.rows_per_split = (chunks + w.splits - 1) / w.splits * WG_R;
+    return w;
 }
 
 size_t tc_wgrad_scratch_bytes(const ConvGeom& c) {
-    int ng, tpg, cot, cit, splits;
-    long long rps;
-    wgrad_shape(c, ng, tpg, cot, cit, splits, rps);
-    // both tap groupings (debug switch) need the same bound: splits <= 128
-    return (size_t)splits * c.ntaps * c.CsIn * c.CsOut * sizeof(float);
+    return (size_t)wgrad_shape(c).splits * c.ntaps * c.CsIn * c.CsOut * sizeof(float);
 }
 
 int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c, cudaStream_t s) {
     WgradTcParams p;
     memset(&p, 0, sizeof(p));
-    wgrad_shape(c, p.ngroups, p.tpg, p.co_tiles, p.ci_tiles, p.splits, p.rows_per_split);
+    const WgradShape w = wgrad_shape(c);
     group_taps(c, +1, !(tc_mode() & 1), p.ngroups, p.tpg, p.goff, p.tap_of);
+    p.swap = w.swap; p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.bn = w.bn;
+    p.splits = w.splits; p.rows_per_split = w.rows_per_split;
     p.rows = c.rows;
     p.ntaps = c.ntaps;
     p.CsIn = c.CsIn;
     p.CsOut = c.CsOut;
     p.planes = precision == 1 ? 2 : 1;
-    p.base_off_mode = (tc_mode() & 2) ? 1 : 0;
     p.P = (float*)scratch;
-    const size_t stage = (size_t)(2 * WG_R * 128 + 2 * (WG_R + A_HALO) * 128) * 2;
+    const int cz = p.swap ? p.bn : 128, ca = p.swap ? 128 : p.bn;
+    const size_t stage = (size_t)(((cz + 63) / 64) * WG_R * 128 + ((ca + 63) / 64) * (WG_R + A_HALO) * 128) * 2;
     p.nstages = (int)((SMEM_LIMIT - 1024 - 256) / stage);
     if (p.nstages > 4) p.nstages = 4;
+    FSB_REQUIRE(p.nstages >= 2 && p.tpg * p.bn <= 512, "wgrad_tc: tile does not fit (bn=%d)", p.bn);
     const size_t smem = 1024 + 256 + stage * p.nstages;
     CUtensorMap tmDZ, tmA;
     FSB_TRY(make_act_map(&tmDZ, dZ, c.rows, c.CsOut, WG_R));
@@ -1345,7 +1575,7 @@ int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scra
         FSB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    const int grid = p.ngroups * p.co_tiles * p.ci_tiles * p.splits;
+    const int grid = p.ngroups * p.m_tiles * p.n_tiles * p.splits;
     wgrad_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmDZ, tmA, p);
     FSB_LAUNCHED();
     return wgrad_finalize((const float*)scratch, p.splits, c, dw, s);
