@@ -312,30 +312,41 @@ def run_ours(args):
     peaks = measured_peaks()
 
     # ---- per-kernel-family device time (CUDA events on the launch stream) for the roofline
+    # (every rank runs these steps -- they contain the gradient all-reduce -- but only rank 0 records)
     roofline = roofline_feat = None
     phases = {}
+    plan = model._plan
+    acc = {}
+    nprof = 3
     if rank == 0:
-        plan = model._plan
         plan.set_profiling(True)
-        acc = {}
-        nprof = 3
-        for i in range(nprof):
-            train_step(dev[i % n_rot], dev_labels[i % n_rot])
-            torch.cuda.synchronize()
+    for i in range(nprof):
+        train_step(dev[i % n_rot], dev_labels[i % n_rot])
+        torch.cuda.synchronize()
+        if rank == 0:
             for name, (ms, fl) in plan.timings().items():
                 a = acc.setdefault(name, [0.0, 0.0])
                 a[0] += ms / nprof
                 a[1] += fl / nprof
+    if rank == 0:
         plan.set_profiling(False)
         phases = {k: {"ms": round(v[0], 4), "gflop": round(v[1] / 1e9, 2)} for k, v in acc.items()}
         gemm_ms = sum(acc[k][0] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad"))
         gemm_fl = sum(acc[k][1] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad"))
         achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        n_gemm_launches = 57          # 19 convs x (forward + dgrad + wgrad) tcgen05 launches per step
         roofline = {
-            "bound": "tensor", "kernel": "row-shifted conv GEMM family (fwd + dgrad + wgrad, %s)" % args.precision,
+            "bound": "tensor", "kernel": "conv_tc_kernel + wgrad_tc_kernel (tcgen05 row-shifted conv GEMMs: fwd + dgrad + "
+                                         "wgrad of the 19 convs, %s)" % args.precision,
             "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
-            "traffic": None, "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
-            "algorithmic_gflop_per_step": gemm_fl / 1e9, "ms_per_step": gemm_ms,
+            # DRAM bytes of one launch (block-0 3x3 forward, the largest layer) from the committed ncu --set full
+            # capture profiles/r01_ncu_summary.txt; algorithmic bytes of that launch = 2 x 411 MB (read a, write z)
+            "traffic": 778.8e6,
+            "peak_source": "%s bf16 sustained (kernel timed inside a long step); bf16x3 issues 3 MMAs per algorithmic "
+                           "one, so its ceiling is peak / 3" % peaks["source"],
+            "algorithmic_gflop_per_step": gemm_fl / 1e9, "algorithmic_gflop_per_launch": gemm_fl / 1e9 / n_gemm_launches,
+            "ms_per_step": gemm_ms, "ms_per_launch": gemm_ms / n_gemm_launches,
+            "frac_of_bf16x3_ceiling": 3.0 * achieved / peaks["tensor"],
             "whole_step_frac": value / world * CONV_GFLOP_PER_CLIP * 1e9 / (peaks["tensor"] * 1e12),
         }
         feat_ms = acc["feat"][0]
