@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "gemm.cuh"
+#include "umma_issue.cuh"
 
 namespace fsb {
 
@@ -119,342 +120,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// All MMAs of one pipeline stage -- (dy, k-chunk): up to 3 dx taps x up to 4 k-steps x 3 products x up to 2 row tiles --
-// in ONE straight-line, predicated asm block.  Per-MMA issue cost decides this kernel: an M128 x N112 x K16 MMA occupies
-// the tensor pipe for 60 cycles (tools/micro/umma_bench.cu: max(N/2, ~44), independent of the accumulator being reused,
-// of SWIZZLE_64B/128B and of a row-shifted A start address), and a C++ loop around single-MMA asm statements costs the
-// issuing thread ~15 instructions (~130 cycles) per MMA in uniform-register moves, predicates and branches.
-//   d_tmem0 / bn: accumulator of tile 0, column stride to tile 1;   a_hi: descriptor of (tile 0, tap 0, hi plane);
-//   a_tile16 / a_box16 / row16: descriptor-unit (16 B) strides tile -> tile, hi -> lo, tap -> tap (one smem row);
-//   b_hi: descriptor of (tap 0, hi plane); w_tap16 / w_plane16: strides tap -> tap, hi -> lo.   acc = 0 starts the tile.
-__device__ __forceinline__ void umma_stage_x3(uint32_t d_tmem0, uint32_t bn, uint64_t a_hi, uint32_t a_tile16, uint32_t a_box16,
-                                              uint32_t row16, uint64_t b_hi, uint32_t w_tap16, uint32_t w_plane16, uint32_t idesc,
-                                              uint32_t acc, int ksteps, int ntile, int ntaps) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pacc, pt, pk1, pk2, pk3, pt1, ps1, ps2;\n\t"
-        ".reg .b32 d0, d1;\n\t"
-        ".reg .b64 ah0, ah1, al0, al1, bh, bl, at, ab, ar, wt, wb;\n\t"
-        ".reg .b64 xh0, xh1, xl0, xl1, yh, yl;\n\t"
-        "setp.ne.b32 pacc, %10, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "setp.gt.s32 pk1, %11, 1;\n\t"
-        "setp.gt.s32 pk2, %11, 2;\n\t"
-        "setp.gt.s32 pk3, %11, 3;\n\t"
-        "setp.gt.s32 pt1, %12, 1;\n\t"
-        "setp.gt.s32 ps1, %13, 1;\n\t"
-        "setp.gt.s32 ps2, %13, 2;\n\t"
-        "mov.b32 d0, %0;\n\t"
-        "add.u32 d1, d0, %1;\n\t"
-        "cvt.u64.u32 at, %3;\n\t"
-        "cvt.u64.u32 ab, %4;\n\t"
-        "cvt.u64.u32 ar, %5;\n\t"
-        "cvt.u64.u32 wt, %7;\n\t"
-        "cvt.u64.u32 wb, %8;\n\t"
-        "mov.b64 ah0, %2;\n\t"
-        "add.u64 ah1, ah0, at;\n\t"
-        "add.u64 al0, ah0, ab;\n\t"
-        "add.u64 al1, ah1, ab;\n\t"
-        "mov.b64 bh, %6;\n\t"
-        "add.u64 bl, bh, wb;\n\t"
-        "add.u64 xh0, ah0, 0;\n\t"
-        "add.u64 xl0, al0, 0;\n\t"
-        "add.u64 xh1, ah1, 0;\n\t"
-        "add.u64 xl1, al1, 0;\n\t"
-        "add.u64 yh, bh, 0;\n\t"
-        "add.u64 yl, bl, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pacc;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pacc;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk1 bra.uni NEXT0;\n\t"
-        "add.u64 xh0, ah0, 2;\n\t"
-        "add.u64 xl0, al0, 2;\n\t"
-        "add.u64 xh1, ah1, 2;\n\t"
-        "add.u64 xl1, al1, 2;\n\t"
-        "add.u64 yh, bh, 2;\n\t"
-        "add.u64 yl, bl, 2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk2 bra.uni NEXT0;\n\t"
-        "add.u64 xh0, ah0, 4;\n\t"
-        "add.u64 xl0, al0, 4;\n\t"
-        "add.u64 xh1, ah1, 4;\n\t"
-        "add.u64 xl1, al1, 4;\n\t"
-        "add.u64 yh, bh, 4;\n\t"
-        "add.u64 yl, bl, 4;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk3 bra.uni NEXT0;\n\t"
-        "add.u64 xh0, ah0, 6;\n\t"
-        "add.u64 xl0, al0, 6;\n\t"
-        "add.u64 xh1, ah1, 6;\n\t"
-        "add.u64 xl1, al1, 6;\n\t"
-        "add.u64 yh, bh, 6;\n\t"
-        "add.u64 yl, bl, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "NEXT0:\n\t"
-        "@!ps1 bra.uni DONE;\n\t"
-        "add.u64 ah0, ah0, ar;\n\t"
-        "add.u64 ah1, ah1, ar;\n\t"
-        "add.u64 al0, al0, ar;\n\t"
-        "add.u64 al1, al1, ar;\n\t"
-        "add.u64 bh, bh, wt;\n\t"
-        "add.u64 bl, bl, wt;\n\t"
-        "add.u64 xh0, ah0, 0;\n\t"
-        "add.u64 xl0, al0, 0;\n\t"
-        "add.u64 xh1, ah1, 0;\n\t"
-        "add.u64 xl1, al1, 0;\n\t"
-        "add.u64 yh, bh, 0;\n\t"
-        "add.u64 yl, bl, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk1 bra.uni NEXT1;\n\t"
-        "add.u64 xh0, ah0, 2;\n\t"
-        "add.u64 xl0, al0, 2;\n\t"
-        "add.u64 xh1, ah1, 2;\n\t"
-        "add.u64 xl1, al1, 2;\n\t"
-        "add.u64 yh, bh, 2;\n\t"
-        "add.u64 yl, bl, 2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk2 bra.uni NEXT1;\n\t"
-        "add.u64 xh0, ah0, 4;\n\t"
-        "add.u64 xl0, al0, 4;\n\t"
-        "add.u64 xh1, ah1, 4;\n\t"
-        "add.u64 xl1, al1, 4;\n\t"
-        "add.u64 yh, bh, 4;\n\t"
-        "add.u64 yl, bl, 4;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk3 bra.uni NEXT1;\n\t"
-        "add.u64 xh0, ah0, 6;\n\t"
-        "add.u64 xl0, al0, 6;\n\t"
-        "add.u64 xh1, ah1, 6;\n\t"
-        "add.u64 xl1, al1, 6;\n\t"
-        "add.u64 yh, bh, 6;\n\t"
-        "add.u64 yl, bl, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "NEXT1:\n\t"
-        "@!ps2 bra.uni DONE;\n\t"
-        "add.u64 ah0, ah0, ar;\n\t"
-        "add.u64 ah1, ah1, ar;\n\t"
-        "add.u64 al0, al0, ar;\n\t"
-        "add.u64 al1, al1, ar;\n\t"
-        "add.u64 bh, bh, wt;\n\t"
-        "add.u64 bl, bl, wt;\n\t"
-        "add.u64 xh0, ah0, 0;\n\t"
-        "add.u64 xl0, al0, 0;\n\t"
-        "add.u64 xh1, ah1, 0;\n\t"
-        "add.u64 xl1, al1, 0;\n\t"
-        "add.u64 yh, bh, 0;\n\t"
-        "add.u64 yl, bl, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk1 bra.uni NEXT2;\n\t"
-        "add.u64 xh0, ah0, 2;\n\t"
-        "add.u64 xl0, al0, 2;\n\t"
-        "add.u64 xh1, ah1, 2;\n\t"
-        "add.u64 xl1, al1, 2;\n\t"
-        "add.u64 yh, bh, 2;\n\t"
-        "add.u64 yl, bl, 2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk2 bra.uni NEXT2;\n\t"
-        "add.u64 xh0, ah0, 4;\n\t"
-        "add.u64 xl0, al0, 4;\n\t"
-        "add.u64 xh1, ah1, 4;\n\t"
-        "add.u64 xl1, al1, 4;\n\t"
-        "add.u64 yh, bh, 4;\n\t"
-        "add.u64 yl, bl, 4;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk3 bra.uni NEXT2;\n\t"
-        "add.u64 xh0, ah0, 6;\n\t"
-        "add.u64 xl0, al0, 6;\n\t"
-        "add.u64 xh1, ah1, 6;\n\t"
-        "add.u64 xl1, al1, 6;\n\t"
-        "add.u64 yh, bh, 6;\n\t"
-        "add.u64 yl, bl, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xl0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xl1, yh, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yl, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yl, %9, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "NEXT2:\n\t"
-        "DONE:\n\t"
-        "}"
-        ::"r"(d_tmem0), "r"(bn), "l"(a_hi), "r"(a_tile16), "r"(a_box16), "r"(row16), "l"(b_hi), "r"(w_tap16), "r"(w_plane16),
-          "r"(idesc), "r"(acc), "r"(ksteps), "r"(ntile), "r"(ntaps)
-        : "memory");
-}
-__device__ __forceinline__ void umma_stage_x1(uint32_t d_tmem0, uint32_t bn, uint64_t a_hi, uint32_t a_tile16, uint32_t a_box16,
-                                              uint32_t row16, uint64_t b_hi, uint32_t w_tap16, uint32_t w_plane16, uint32_t idesc,
-                                              uint32_t acc, int ksteps, int ntile, int ntaps) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pacc, pt, pk1, pk2, pk3, pt1, ps1, ps2;\n\t"
-        ".reg .b32 d0, d1;\n\t"
-        ".reg .b64 ah0, ah1, al0, al1, bh, bl, at, ab, ar, wt, wb;\n\t"
-        ".reg .b64 xh0, xh1, xl0, xl1, yh, yl;\n\t"
-        "setp.ne.b32 pacc, %10, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "setp.gt.s32 pk1, %11, 1;\n\t"
-        "setp.gt.s32 pk2, %11, 2;\n\t"
-        "setp.gt.s32 pk3, %11, 3;\n\t"
-        "setp.gt.s32 pt1, %12, 1;\n\t"
-        "setp.gt.s32 ps1, %13, 1;\n\t"
-        "setp.gt.s32 ps2, %13, 2;\n\t"
-        "mov.b32 d0, %0;\n\t"
-        "add.u32 d1, d0, %1;\n\t"
-        "cvt.u64.u32 at, %3;\n\t"
-        "cvt.u64.u32 ab, %4;\n\t"
-        "cvt.u64.u32 ar, %5;\n\t"
-        "cvt.u64.u32 wt, %7;\n\t"
-        "cvt.u64.u32 wb, %8;\n\t"
-        "mov.b64 ah0, %2;\n\t"
-        "add.u64 ah1, ah0, at;\n\t"
-        "add.u64 al0, ah0, ab;\n\t"
-        "add.u64 al1, ah1, ab;\n\t"
-        "mov.b64 bh, %6;\n\t"
-        "add.u64 bl, bh, wb;\n\t"
-        "add.u64 xh0, ah0, 0;\n\t"
-        "add.u64 xh1, ah1, 0;\n\t"
-        "add.u64 yh, bh, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pacc;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pacc;\n\t"
-        "@!pk1 bra.uni NEXT0;\n\t"
-        "add.u64 xh0, ah0, 2;\n\t"
-        "add.u64 xh1, ah1, 2;\n\t"
-        "add.u64 yh, bh, 2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk2 bra.uni NEXT0;\n\t"
-        "add.u64 xh0, ah0, 4;\n\t"
-        "add.u64 xh1, ah1, 4;\n\t"
-        "add.u64 yh, bh, 4;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk3 bra.uni NEXT0;\n\t"
-        "add.u64 xh0, ah0, 6;\n\t"
-        "add.u64 xh1, ah1, 6;\n\t"
-        "add.u64 yh, bh, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "NEXT0:\n\t"
-        "@!ps1 bra.uni DONE;\n\t"
-        "add.u64 ah0, ah0, ar;\n\t"
-        "add.u64 ah1, ah1, ar;\n\t"
-        "add.u64 al0, al0, ar;\n\t"
-        "add.u64 al1, al1, ar;\n\t"
-        "add.u64 bh, bh, wt;\n\t"
-        "add.u64 bl, bl, wt;\n\t"
-        "add.u64 xh0, ah0, 0;\n\t"
-        "add.u64 xh1, ah1, 0;\n\t"
-        "add.u64 yh, bh, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk1 bra.uni NEXT1;\n\t"
-        "add.u64 xh0, ah0, 2;\n\t"
-        "add.u64 xh1, ah1, 2;\n\t"
-        "add.u64 yh, bh, 2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk2 bra.uni NEXT1;\n\t"
-        "add.u64 xh0, ah0, 4;\n\t"
-        "add.u64 xh1, ah1, 4;\n\t"
-        "add.u64 yh, bh, 4;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk3 bra.uni NEXT1;\n\t"
-        "add.u64 xh0, ah0, 6;\n\t"
-        "add.u64 xh1, ah1, 6;\n\t"
-        "add.u64 yh, bh, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "NEXT1:\n\t"
-        "@!ps2 bra.uni DONE;\n\t"
-        "add.u64 ah0, ah0, ar;\n\t"
-        "add.u64 ah1, ah1, ar;\n\t"
-        "add.u64 al0, al0, ar;\n\t"
-        "add.u64 al1, al1, ar;\n\t"
-        "add.u64 bh, bh, wt;\n\t"
-        "add.u64 bl, bl, wt;\n\t"
-        "add.u64 xh0, ah0, 0;\n\t"
-        "add.u64 xh1, ah1, 0;\n\t"
-        "add.u64 yh, bh, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk1 bra.uni NEXT2;\n\t"
-        "add.u64 xh0, ah0, 2;\n\t"
-        "add.u64 xh1, ah1, 2;\n\t"
-        "add.u64 yh, bh, 2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk2 bra.uni NEXT2;\n\t"
-        "add.u64 xh0, ah0, 4;\n\t"
-        "add.u64 xh1, ah1, 4;\n\t"
-        "add.u64 yh, bh, 4;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "@!pk3 bra.uni NEXT2;\n\t"
-        "add.u64 xh0, ah0, 6;\n\t"
-        "add.u64 xh1, ah1, 6;\n\t"
-        "add.u64 yh, bh, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d0], xh0, yh, %9, pt;\n\t"
-        "@pt1 tcgen05.mma.cta_group::1.kind::f16 [d1], xh1, yh, %9, pt;\n\t"
-        "NEXT2:\n\t"
-        "DONE:\n\t"
-        "}"
-        ::"r"(d_tmem0), "r"(bn), "l"(a_hi), "r"(a_tile16), "r"(a_box16), "r"(row16), "l"(b_hi), "r"(w_tap16), "r"(w_plane16),
-          "r"(idesc), "r"(acc), "r"(ksteps), "r"(ntile), "r"(ntaps)
         : "memory");
 }
 // wgrad: all MMAs of one 64-pixel-row stage -- up to 3 dx taps (one accumulator each, `ncol` TMEM columns apart) x 4
@@ -653,16 +318,6 @@ __device__ __forceinline__ void umma_wgrad_x1(uint32_t d0, uint32_t ncol, uint64
         ::"r"(d0), "r"(ncol), "l"(m_hi), "l"(m_lo), "l"(n_hi), "l"(n_lo), "r"(m_shift16), "r"(n_shift16), "r"(idesc), "r"(acc),
           "r"(ntaps)
         : "memory");
-}
-// one lane of a fully converged warp (always the same one)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok));
-    return ok != 0;
 }
 // mbarrier arrives once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -871,15 +526,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t base = ring + stage_bytes * st;
                     int ksteps = (p.K - kc * p.bk + 15) / 16;
                     if (ksteps > p.bk / 16) ksteps = p.bk / 16;
-                    if (elect_one()) {
+                    if (umma::elect_one()) {
                         const uint64_t a_hi = ((uint64_t)d_hi << 32) | (d_lo | ((base & 0x3FFFFu) >> 4));
                         const uint64_t b_hi = ((uint64_t)d_hi << 32) | (d_lo | (((base + a_part) & 0x3FFFFu) >> 4));
                         if (p.dbg & 8) {
+                        } else if (p.planes == 2 && ntile == 1) {
+                            // one row tile per stage (wide N): 6-18 MMAs, the straight-line specialisations issue them
+                            // ~1.4x faster than the predicated block (tools/micro/stage_bench.cu)
+                            umma::umma_stage_x3_fast(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi,
+                                                     w_tap >> 4, w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
                         } else if (p.planes == 2) {
-                            umma_stage_x3(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
+                            umma::umma_stage_x3(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
                                           w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
                         } else {
-                            umma_stage_x1(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
+                            umma::umma_stage_x1(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
                                           w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
                         }
                         umma_commit(b_empty + 8u * st);
@@ -1132,7 +792,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
             const uint32_t base = ring + stage_bytes * st;
             const uint32_t z_hi = base, z_lo = base + dz_plane;
             const uint32_t a_hi = base + 2u * dz_plane, a_lo = a_hi + a_plane;
-            if (elect_one()) {
+            if (umma::elect_one()) {
                 const uint64_t dzh = ((uint64_t)hi_word << 32) | (lbo_z | ((z_hi & 0x3FFFFu) >> 4));
                 const uint64_t dzl = ((uint64_t)hi_word << 32) | (lbo_z | ((z_lo & 0x3FFFFu) >> 4));
                 const uint64_t dah = ((uint64_t)hi_word << 32) | (lbo_a | ((a_hi & 0x3FFFFu) >> 4));
