@@ -480,52 +480,77 @@ int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, in
     return 0;
 }
 
-// dzf over FULL-RES interior pixels: each pixel decides whether it is the (first) arg-max of its window
+// One thread per POOLED pixel and float4 of channels: it reads its window of zf once (2 or 4 pixels), routes the
+// gradient to the first maximum in scan order and writes all window positions of dzf (zeros elsewhere).  Full-res
+// pixels that no window covers (odd trailing row / column, floor mode) get zeros from the thread of the adjacent
+// window.  (The previous version walked full-res pixels and re-read the window four times: 3.4 TB/s.)
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restrict__ zf, Geo g, int pool_h,
                    void* dzf, int fmt) {
-    EW_PROLOGUE
-    if (!cok) return;
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= g.Cs / 4) return;
+    const int c0 = cv * 4;
     const long long plane = g.rows * g.Cs;
-    EW_PIXEL_LOOP {
-        const unsigned img = (unsigned)(g.Hp * g.Wp);
-        const int n = (int)((unsigned long long)row / img);
-        const unsigned rr = (unsigned)(row - (long long)n * img);
-        const int y = (int)(rr / (unsigned)g.Wp) - g.padH, x = (int)(rr % (unsigned)g.Wp) - g.padW;
-        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-        int py = y / pool_h, px = x / 2;
-        if (py < gp.H && px < gp.W) {
-            long long r00 = geo_row(g, n, py * pool_h, px * 2);
-            int my = y - py * pool_h, mx = x - px * 2;
-            int me = my * 2 + mx;                 // position of this pixel in scan order
-            float v[4][4];
-            int cnt = pool_h == 2 ? 4 : 2;
-            for (int k = 0; k < cnt; ++k) {
-                long long rr = r00 + (k >> 1) * g.Wp + (k & 1);
-                float4 t4 = ld4(zf + rr * g.Cs + c0);
-                v[k][0] = t4.x; v[k][1] = t4.y; v[k][2] = t4.z; v[k][3] = t4.w;
-            }
-            float4 gsrc = ld4(dzp + geo_row(gp, n, py, px) * gp.Cs + c0);
-            float gs[4] = {gsrc.x, gsrc.y, gsrc.z, gsrc.w};
-            float o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int best = 0;
-                float bv = v[0][i];
-                for (int k = 1; k < cnt; ++k)
-                    if (v[k][i] > bv) { bv = v[k][i]; best = k; }
-                o[i] = best == me ? gs[i] : 0.f;
-            }
-            out = make_float4(o[0], o[1], o[2], o[3]);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool odd_w = g.W > 2 * gp.W, odd_h = pool_h == 2 && g.H > 2 * gp.H;
+    for (long long prow = (long long)blockIdx.x * blockDim.y + threadIdx.y; prow < gp.rows;
+         prow += (long long)gridDim.x * blockDim.y) {
+        if (gp.mask != nullptr && !gp.mask[prow]) continue;
+        const unsigned img = (unsigned)(gp.Hp * gp.Wp);
+        const int n = (int)((unsigned long long)prow / img);
+        const unsigned rr = (unsigned)(prow - (long long)n * img);
+        const int py = (int)(rr / (unsigned)gp.Wp) - gp.padH, px = (int)(rr % (unsigned)gp.Wp) - gp.padW;
+        const long long r00 = geo_row(g, n, py * pool_h, 2 * px);
+        const float4 gsrc = ld4(dzp + prow * gp.Cs + c0);
+        const float4 v0 = ld4(zf + r00 * g.Cs + c0), v1 = ld4(zf + (r00 + 1) * g.Cs + c0);
+        float4 v2 = zero, v3 = zero;
+        if (pool_h == 2) {
+            v2 = ld4(zf + (r00 + g.Wp) * g.Cs + c0);
+            v3 = ld4(zf + (r00 + g.Wp + 1) * g.Cs + c0);
         }
-        store_fmt(dzf, fmt, plane, row * g.Cs + c0, out);
+        const float a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w};
+        const float a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w};
+        const float gs[4] = {gsrc.x, gsrc.y, gsrc.z, gsrc.w};
+        float o[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int best = 0;
+            float bv = a0[i];
+            if (a1[i] > bv) { bv = a1[i]; best = 1; }
+            if (pool_h == 2) {
+                if (a2[i] > bv) { bv = a2[i]; best = 2; }
+                if (a3[i] > bv) { bv = a3[i]; best = 3; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k][i] = best == k ? gs[i] : 0.f;
+        }
+        store_fmt(dzf, fmt, plane, r00 * g.Cs + c0, make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
+        store_fmt(dzf, fmt, plane, (r00 + 1) * g.Cs + c0, make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+        if (pool_h == 2) {
+            store_fmt(dzf, fmt, plane, (r00 + g.Wp) * g.Cs + c0, make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
+            store_fmt(dzf, fmt, plane, (r00 + g.Wp + 1) * g.Cs + c0, make_float4(o[3][0], o[3][1], o[3][2], o[3][3]));
+        }
+        // uncovered trailing column / row / corner
+        const bool last_x = odd_w && px == gp.W - 1, last_y = odd_h && py == gp.H - 1;
+        if (last_x) {
+            store_fmt(dzf, fmt, plane, (r00 + 2) * g.Cs + c0, zero);
+            if (pool_h == 2) store_fmt(dzf, fmt, plane, (r00 + g.Wp + 2) * g.Cs + c0, zero);
+        }
+        if (last_y) {
+            store_fmt(dzf, fmt, plane, (r00 + 2 * g.Wp) * g.Cs + c0, zero);
+            store_fmt(dzf, fmt, plane, (r00 + 2 * g.Wp + 1) * g.Cs + c0, zero);
+            if (last_x) store_fmt(dzf, fmt, plane, (r00 + 2 * g.Wp + 2) * g.Cs + c0, zero);
+        }
     }
 }
 
 int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h, void* dzf,
                      int fmt, cudaStream_t s) {
     EW_CHECK(gf);
-    EwShape sh = ew_shape(gf);
+    EW_CHECK(gp);
+    FSB_REQUIRE(gf.W - 2 * gp.W <= 1 && gf.W >= 2 * gp.W && (pool_h == 1 ? gf.H == gp.H : (gf.H - 2 * gp.H <= 1 && gf.H >= 2 * gp.H)),
+                "maxpool_backward: geometries are not a floor-mode 2x pooling pair");
+    EwShape sh = ew_shape(gp);
     maxpool_bwd_kernel<<<sh.grid, sh.block, 0, s>>>(dzp, gp, zf, gf, pool_h, dzf, fmt);
     FSB_LAUNCHED();
     return 0;
