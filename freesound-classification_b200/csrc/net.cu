@@ -9,6 +9,8 @@
 //   15 res.conv3.w 16 res.conv3.b 17 res.bn3.w 18 res.bn3.b 19 res.prelu1.w 20 res.prelu2.w 21 res.prelu3.w
 // then the head: bn0.w bn0.b lin1.w lin1.b bn2.w bn2.b prelu.w lin5.w lin5.b
 // BN buffer order: per block bn_in, bn_a, bn1, bn2, bn3 ; head bn0, bn2.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -101,6 +103,14 @@ struct fsb_net {
     ConvGeom lin1, lin5;
     void *pk_l1, *pk_l5, *head_scratch;
     Geo g_head, g_cls;
+
+    // backward side stream: weight-gradient GEMMs (tensor pipe) overlap the BatchNorm-backward passes (HBM) of the
+    // critical path.  Fork / join with events, so the caller still sees plain stream semantics.
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> fork_events;
+    size_t fork_used = 0;
+    cudaEvent_t join_event = nullptr, pack_event = nullptr;
+    void* conv0_scratch = nullptr;
 
     // profiling
     bool profiling = false;
@@ -241,7 +251,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
                 B.du = b.take<float>((size_t)B.g_in.rows * B.g_in.Cs);
                 max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.entry));
             } else {
-                max_wgrad = std::max(max_wgrad, conv0_bwd_scratch_bytes(B.g));
+                net->conv0_scratch = b.take_bytes(conv0_bwd_scratch_bytes(B.g));
             }
             max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c1));
             max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c2));
@@ -314,6 +324,12 @@ double conv_flops(const ConvGeom& c, const Geo& g) { return 2.0 * c.Cin * c.Cout
         FSB_TRY(expr);                      \
     } while (0)
 
+#define RUN_S(stream, cat, flops, expr)     \
+    do {                                    \
+        Scope _sc(net, stream, cat, flops); \
+        FSB_TRY(expr);                      \
+    } while (0)
+
 const Residual kNoRes = {nullptr, nullptr, nullptr, nullptr};
 const Dropout kNoDrop = {0.f, 0ull};
 
@@ -366,6 +382,10 @@ extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, c
 extern "C" void fsb_net_destroy(fsb_net* net) {
     if (!net) return;
     for (cudaEvent_t e : net->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : net->fork_events) cudaEventDestroy(e);
+    if (net->join_event) cudaEventDestroy(net->join_event);
+    if (net->pack_event) cudaEventDestroy(net->pack_event);
+    if (net->side) cudaStreamDestroy(net->side);
     delete net;
 }
 
@@ -395,6 +415,7 @@ extern "C" size_t fsb_net_workspace_bytes(const fsb_net* net, int n, int t, int 
     if (check_shape(net, n, t) != 0) return 0;
     fsb_net tmp = *net;     // carve mutates the plan; run the size query on a copy
     tmp.ev_pool.clear();
+    tmp.fork_events.clear();
     return carve(&tmp, nullptr, n, t, training);
 }
 
@@ -427,6 +448,17 @@ static int bind(fsb_net* net, void* ws, size_t ws_bytes, int n, int t, int train
     return 0;
 }
 
+static int ensure_side_stream(fsb_net* net) {
+    if (!net->side) {
+        int lo = 0, hi = 0;
+        FSB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        FSB_CUDA(cudaStreamCreateWithPriority(&net->side, cudaStreamNonBlocking, lo));     // off the critical path
+        FSB_CUDA(cudaEventCreateWithFlags(&net->join_event, cudaEventDisableTiming));
+        FSB_CUDA(cudaEventCreateWithFlags(&net->pack_event, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, long long signal_stride,
                                const float* const* params, float* const* bn_mean, float* const* bn_var,
                                long long* const* bn_count, int training, unsigned long long dropout_seed,
@@ -442,6 +474,40 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
     net->dropout_seed = dropout_seed;
     const int frames = net->frames;
     int carried_nblk = 0;      // partial records left in net->partials by the previous block's last pass
+
+    // Weight packing (float32 -> bf16 hi/lo K-major tiles) depends on the parameters only: it runs on the side stream
+    // in the shadow of the feature kernel and the block-0 entry conv; the first GEMM waits for it.
+    FSB_TRY(ensure_side_stream(net));
+    {
+        const bool overlap = getenv("FSB200_NO_OVERLAP") == nullptr;
+        cudaStream_t ps = overlap ? net->side : s;
+        if (overlap) {
+            FSB_CUDA(cudaEventRecord(net->pack_event, s));        // orders the packs after the caller's earlier work (optimizer step)
+            FSB_CUDA(cudaStreamWaitEvent(net->side, net->pack_event, 0));
+        }
+        for (int k = 0; k < c.num_blocks; ++k) {
+            BlockPlan& B = net->blocks[k];
+            const float* const* P = params + (size_t)k * P_PER_BLOCK;
+            if (B.pk_entry) RUN_S(ps, CAT_PACK, 0, pack_weights(prec, P[P_CONV_W], P[P_CONV_B], B.entry, B.pk_entry, ps));
+            RUN_S(ps, CAT_PACK, 0, pack_weights(prec, P[P_C1_W], P[P_C1_B], B.c1, B.pk1, ps));
+            RUN_S(ps, CAT_PACK, 0, pack_weights(prec, P[P_C2_W], P[P_C2_B], B.c2, B.pk2, ps));
+            RUN_S(ps, CAT_PACK, 0, pack_weights(prec, P[P_C3_W], P[P_C3_B], B.c3, B.pk3, ps));
+        }
+        {
+            const float* const* P = params + (size_t)c.num_blocks * P_PER_BLOCK;
+            RUN_S(ps, CAT_HEAD, 0, simt_pack_weights(P[H_L1_W], P[H_L1_B], net->lin1, net->pk_l1, ps));
+            RUN_S(ps, CAT_HEAD, 0, simt_pack_weights(P[H_L5_W], P[H_L5_B], net->lin5, net->pk_l5, ps));
+        }
+        if (overlap) FSB_CUDA(cudaEventRecord(net->pack_event, net->side));
+    }
+    bool packs_joined = getenv("FSB200_NO_OVERLAP") != nullptr;
+    auto join_packs = [&]() -> int {
+        if (!packs_joined) {
+            FSB_CUDA(cudaStreamWaitEvent(s, net->pack_event, 0));
+            packs_joined = true;
+        }
+        return 0;
+    };
 
     for (int k = 0; k < c.num_blocks; ++k) {
         BlockPlan& B = net->blocks[k];
@@ -485,7 +551,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
             }
             RUN(CAT_ELT_FWD, 0, bn_act_forward(B.x_in, B.g_in, B.bn_in.coef(nullptr), kNoRes, kNoDrop, B.u, fmt,
                                                nullptr, nullptr, s));
-            RUN(CAT_PACK, 0, pack_weights(prec, P[P_CONV_W], P[P_CONV_B], B.entry, B.pk_entry, s));
+            FSB_TRY(join_packs());
             RUN(CAT_GEMM_FWD, conv_flops(B.entry, B.g_in),
                 conv_gemm_fwd(prec, B.u, B.pk_entry, B.zf, B.entry, nullptr, s));
             RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1,
@@ -502,9 +568,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
         RUN(CAT_ELT_FWD, 0, bn_act_forward(B.zp, B.g, B.bn_a.coef(P[P_PRELUA]), kNoRes, kNoDrop, B.r0, fmt, nullptr,
                                            nullptr, s));
         // resnet block: every conv GEMM gathers the batch statistics of its output in the epilogue
-        RUN(CAT_PACK, 0, pack_weights(prec, P[P_C1_W], P[P_C1_B], B.c1, B.pk1, s));
-        RUN(CAT_PACK, 0, pack_weights(prec, P[P_C2_W], P[P_C2_B], B.c2, B.pk2, s));
-        RUN(CAT_PACK, 0, pack_weights(prec, P[P_C3_W], P[P_C3_B], B.c3, B.pk3, s));
+        FSB_TRY(join_packs());
         int nblk = 0;
         FwdStats st = {net->partials, &B.g, &nblk};
         const FwdStats* stp = training ? &st : nullptr;
@@ -541,8 +605,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
                                  CT ? CT[0] : nullptr, training, CAT_HEAD));
         RUN(CAT_HEAD, 0, bn_act_forward(net->feats, net->g_head, net->hbn0.coef(nullptr), kNoRes, kNoDrop, nullptr,
                                         FMT_F32, net->h0, nullptr, s));
-        RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L1_W], P[H_L1_B], net->lin1, net->pk_l1, s));
-        RUN(CAT_HEAD, 0, simt_pack_weights(P[H_L5_W], P[H_L5_B], net->lin5, net->pk_l5, s));
+        FSB_TRY(join_packs());
         RUN(CAT_HEAD, 0, simt_skinny_fwd(net->h0, net->pk_l1, net->z1h, net->lin1, net->head_scratch, s));
         FSB_TRY(bn_forward_stats(net, s, net->z1h, net->g_head, net->hbn2, P[H_BN2_W], P[H_BN2_B], RM[1], RV[1],
                                  CT ? CT[1] : nullptr, training, CAT_HEAD));
@@ -582,6 +645,23 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
     auto G = [&](int index) { return grads + net->param_offset[index]; };
     // conv / linear biases that feed a batch-statistics BN have an analytically zero gradient
     FSB_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->total_params * sizeof(float), s));
+    FSB_TRY(ensure_side_stream(net));
+    const bool overlap = getenv("FSB200_NO_OVERLAP") == nullptr;
+    cudaStream_t ws = overlap ? net->side : s;       // stream of the weight-gradient GEMMs
+    net->fork_used = 0;
+    // everything enqueued on `s` so far is visible to the side stream from here on
+    auto fork = [&]() -> int {
+        if (!overlap) return 0;
+        if (net->fork_used == net->fork_events.size()) {
+            cudaEvent_t e;
+            FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            net->fork_events.push_back(e);
+        }
+        cudaEvent_t e = net->fork_events[net->fork_used++];
+        FSB_CUDA(cudaEventRecord(e, s));
+        FSB_CUDA(cudaStreamWaitEvent(net->side, e, 0));
+        return 0;
+    };
 
     // ---- head
     {
@@ -612,18 +692,21 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
         Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
         FSB_TRY(bn_backward(net, s, B.d_out, nullptr, B.z3, B.g, B.bn3, P[P_PRELU3], res, kNoDrop, G(pb + P_BN3_W),
                             G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, CAT_ELT_BWD));
-        RUN(CAT_GEMM_WGRAD, conv_flops(B.c3, B.g),
-            conv_gemm_wgrad(prec, B.a2, B.dz3, G(pb + P_C3_W), net->wgrad_scratch, B.c3, s));
+        FSB_TRY(fork());
+        RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c3, B.g),
+              conv_gemm_wgrad(prec, B.a2, B.dz3, G(pb + P_C3_W), net->wgrad_scratch, B.c3, ws));
         RUN(CAT_GEMM_DGRAD, conv_flops(B.c3, B.g), conv_gemm_dgrad(prec, B.dz3, B.pk3, B.da2, B.c3, s));
         FSB_TRY(bn_backward(net, s, B.da2, nullptr, B.z2, B.g, B.bn2, P[P_PRELU2], kNoRes, kNoDrop, G(pb + P_BN2_W),
                             G(pb + P_BN2_B), G(pb + P_PRELU2), B.dz2, fmt, nullptr, CAT_ELT_BWD));
-        RUN(CAT_GEMM_WGRAD, conv_flops(B.c2, B.g),
-            conv_gemm_wgrad(prec, B.a1, B.dz2, G(pb + P_C2_W), net->wgrad_scratch, B.c2, s));
+        FSB_TRY(fork());
+        RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c2, B.g),
+              conv_gemm_wgrad(prec, B.a1, B.dz2, G(pb + P_C2_W), net->wgrad_scratch, B.c2, ws));
         RUN(CAT_GEMM_DGRAD, conv_flops(B.c2, B.g), conv_gemm_dgrad(prec, B.dz2, B.pk2, B.da1, B.c2, s));
         FSB_TRY(bn_backward(net, s, B.da1, nullptr, B.z1, B.g, B.bn1, P[P_PRELU1], kNoRes, kNoDrop, G(pb + P_BN1_W),
                             G(pb + P_BN1_B), G(pb + P_PRELU1), B.dz1, fmt, nullptr, CAT_ELT_BWD));
-        RUN(CAT_GEMM_WGRAD, conv_flops(B.c1, B.g),
-            conv_gemm_wgrad(prec, B.r0, B.dz1, G(pb + P_C1_W), net->wgrad_scratch, B.c1, s));
+        FSB_TRY(fork());
+        RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c1, B.g),
+              conv_gemm_wgrad(prec, B.r0, B.dz1, G(pb + P_C1_W), net->wgrad_scratch, B.c1, ws));
         RUN(CAT_GEMM_DGRAD, conv_flops(B.c1, B.g), conv_gemm_dgrad(prec, B.dz1, B.pk1, B.dr0a, B.c1, s));
         // r0 = prelu_a(bn_a(zp)) ; gradient = conv1 dgrad + residual branch
         FSB_TRY(bn_backward(net, s, B.dr0a, B.dr0b, B.zp, B.g, B.bn_a, P[P_PRELUA], kNoRes, kNoDrop, G(pb + P_BNA_W),
@@ -632,16 +715,21 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
             RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
                 conv0_backward(net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift, B.bn_in.mean,
                                B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, B.g, G(pb + P_CONV_W),
-                               G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->wgrad_scratch, s));
+                               G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->conv0_scratch, s));
         } else {
             RUN(CAT_ELT_BWD, 0, maxpool_backward(B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt, s));
-            RUN(CAT_GEMM_WGRAD, conv_flops(B.entry, B.g_in),
-                conv_gemm_wgrad(prec, B.u, B.dzf, G(pb + P_CONV_W), net->wgrad_scratch, B.entry, s));
+            FSB_TRY(fork());
+            RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.entry, B.g_in),
+                  conv_gemm_wgrad(prec, B.u, B.dzf, G(pb + P_CONV_W), net->wgrad_scratch, B.entry, ws));
             RUN(CAT_GEMM_DGRAD, conv_flops(B.entry, B.g_in), conv_gemm_dgrad(prec, B.dzf, B.pk_entry, B.du, B.entry, s));
             float* dprev = k > 0 ? net->blocks[k - 1].d_out : nullptr;
             FSB_TRY(bn_backward(net, s, B.du, nullptr, B.x_in, B.g_in, B.bn_in, nullptr, kNoRes, kNoDrop,
                                 G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, FMT_F32, nullptr, CAT_ELT_BWD));
         }
+    }
+    if (overlap) {      // join: the caller's stream continues only after the last weight gradient has landed
+        FSB_CUDA(cudaEventRecord(net->join_event, net->side));
+        FSB_CUDA(cudaStreamWaitEvent(s, net->join_event, 0));
     }
     return 0;
 }
