@@ -71,7 +71,7 @@ __global__ void lsep_bwd_kernel(const float* __restrict__ s, const float* __rest
 // ---------------------------------------------------------------------------------------------
 // Adam(amsgrad) multi-tensor
 // ---------------------------------------------------------------------------------------------
-static constexpr int ADAM_CHUNK = 65536;
+static constexpr int ADAM_CHUNK = 8192;
 
 struct AdamRec {
     float* p;
@@ -82,23 +82,49 @@ struct AdamRec {
     long long n;
 };
 
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float& vm, float step_size, float sqrt_bc2,
+                                            float beta1, float beta2, float eps, float wd, float gscale) {
+    g *= gscale;
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    m = m + (g - m) * (1.0f - beta1);                 // torch: exp_avg.lerp_(grad, 1 - beta1)
+    v = v * beta2 + g * g * (1.0f - beta2);
+    vm = fmaxf(vm, v);
+    const float denom = sqrtf(vm) / sqrt_bc2 + eps;
+    p = p - step_size * (m / denom);
+}
+
+// one CTA per (tensor record, 8192-element chunk); float4 accesses when the record's five arrays are 16-byte aligned
 __global__ void __launch_bounds__(256)
 adam_kernel(const AdamRec* __restrict__ table, const int* __restrict__ block_map, float step_size, float sqrt_bc2,
             float beta1, float beta2, float eps, float wd, float gscale) {
     const AdamRec r = table[block_map[2 * blockIdx.x]];
     const long long base = (long long)block_map[2 * blockIdx.x + 1] * ADAM_CHUNK;
     const long long end = base + ADAM_CHUNK < r.n ? base + ADAM_CHUNK : r.n;
-    for (long long i = base + threadIdx.x; i < end; i += 256) {
-        float p = r.p[i];
-        float g = r.g[i] * gscale;
-        if (wd != 0.f) g = fmaf(wd, p, g);
-        float m = r.m[i];
-        m = m + (g - m) * (1.0f - beta1);                 // torch: exp_avg.lerp_(grad, 1 - beta1)
-        float v = r.v[i] * beta2 + g * g * (1.0f - beta2);
-        float vm = fmaxf(r.vmax[i], v);
-        float denom = sqrtf(vm) / sqrt_bc2 + eps;
+    const bool aligned = ((((size_t)r.p | (size_t)r.g | (size_t)r.m | (size_t)r.v | (size_t)r.vmax) & 15) == 0);
+    long long i = base + threadIdx.x;
+    if (aligned) {
+        const long long end4 = base + ((end - base) & ~3ll);
+        for (long long j = base + 4ll * threadIdx.x; j < end4; j += 4 * 256) {
+            float4 p = *reinterpret_cast<float4*>(r.p + j);
+            const float4 g = *reinterpret_cast<const float4*>(r.g + j);
+            float4 m = *reinterpret_cast<float4*>(r.m + j), v = *reinterpret_cast<float4*>(r.v + j),
+                   vm = *reinterpret_cast<float4*>(r.vmax + j);
+            adam_update(p.x, g.x, m.x, v.x, vm.x, step_size, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+            adam_update(p.y, g.y, m.y, v.y, vm.y, step_size, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+            adam_update(p.z, g.z, m.z, v.z, vm.z, step_size, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+            adam_update(p.w, g.w, m.w, v.w, vm.w, step_size, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+            *reinterpret_cast<float4*>(r.m + j) = m;
+            *reinterpret_cast<float4*>(r.v + j) = v;
+            *reinterpret_cast<float4*>(r.vmax + j) = vm;
+            *reinterpret_cast<float4*>(r.p + j) = p;
+        }
+        i = end4 + threadIdx.x;
+    }
+    for (; i < end; i += 256) {
+        float p = r.p[i], m = r.m[i], v = r.v[i], vm = r.vmax[i];
+        adam_update(p, r.g[i], m, v, vm, step_size, sqrt_bc2, beta1, beta2, eps, wd, gscale);
         r.m[i] = m; r.v[i] = v; r.vmax[i] = vm;
-        r.p[i] = p - step_size * (m / denom);
+        r.p[i] = p;
     }
 }
 

@@ -72,7 +72,7 @@ int fsb_lsep_backward(const float* scores, const float* targets, const float* dl
  *   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; vmax = max(vmax, v);
  *   p -= lr/(1-b1^t) * m / (sqrt(vmax)/sqrt(1-b2^t) + eps)
  * `table` is a DEVICE array of n_tensors records {p, g, m, v, vmax (float*), n (int64)} (6 x 8 bytes),
- * `block_map` a DEVICE int32 array of 2*n_blocks entries {tensor index, chunk index}; chunk = 65536
+ * `block_map` a DEVICE int32 array of 2*n_blocks entries {tensor index, chunk index}; chunk = 8192
  * elements (fsb_adam_chunk()).  grad_scale multiplies g first (1/world_size after a SUM allreduce).
  * ------------------------------------------------------------------------------------------------ */
 int fsb_adam_chunk(void);

@@ -260,3 +260,37 @@ def test_fit_validate_predict_roundtrip(tmp_path):
     assert probs.shape == (8, 80) and probs.dtype == np.float32
     assert (probs >= 0).all() and (probs <= 1).all()
     assert set(before) == set(model.state_dict())
+
+
+def test_full_size_determinism_and_backward_linearity():
+    """Size-independent properties at the bench workload (64 x 10 s, canonical width, bf16x3 tensor-core back end, side
+    stream overlap on): two training passes from the same state are bit-identical (every reduction has a fixed order),
+    and the backward pass is exactly linear in the incoming gradient (scaling dlogits by 2 doubles every gradient
+    bit for bit: all backward arithmetic is products and sums of the gradient, and 2x is exact in float32 / bf16)."""
+    cfg = dict(output_dropout=0.0)
+    model = build("TwoDimensionalCNNClassificationModel", cfg, None, "bf16x3")
+    model.train()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    signal = 0.1 * torch.randn(64, 441000, generator=gen, device="cuda")
+    dlogits = torch.randn(64, 80, generator=gen, device="cuda") / 64
+
+    def run(scale):
+        for p in model.parameters():
+            p.grad = None
+        out = model(signal[..., None])["class_logits"]
+        out.backward(dlogits * scale)
+        torch.cuda.synchronize()
+        return out.detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    l1, g1 = run(1.0)
+    model.load_state_dict(sd)              # running statistics back to the same state
+    l2, g2 = run(1.0)
+    assert torch.isfinite(l1).all() and torch.isfinite(g1).all()
+    assert torch.equal(l1, l2)
+    assert torch.equal(g1, g2)
+    model.load_state_dict(sd)
+    l3, g3 = run(2.0)
+    assert torch.equal(l1, l3)
+    assert torch.equal(g3, 2.0 * g1)
+    assert float(g1.abs().max()) > 0

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(fsb200.EXPORTS) == declared
     lib = fsb200.lib()
     assert lib.fsb_version() >= 100
-    assert lib.fsb_adam_chunk() == 65536
+    assert lib.fsb_adam_chunk() == 8192
 
 
 def test_mel_matrix_matches_oracle_and_bands():
