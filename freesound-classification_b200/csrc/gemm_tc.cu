@@ -7,18 +7,20 @@
 // relative error), or hi*hi only in precision 2.
 //
 //   conv_tc_kernel  (forward and dgrad)   D[r, n] = sum_t sum_k A[r + off_t, k] * W_t[n, k]
-//       persistent, warp specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-//       warps 2..5 = epilogue (TMEM -> registers -> swizzled smem panel -> TMA store, one 32-row x 32-column box
-//       per warp, double buffered; BatchNorm column statistics by a register shuffle-transpose reduction).
-//       Two smem rings: an A ring whose stage is
-//       a (128 + 8)-row x 64-channel SWIZZLE_128B box shared by the three dx taps of one dy (the tap
-//       shift is a 128-byte start-address offset of the UMMA descriptor), and a W ring with one
-//       (BN x 64) tile per tap.  Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i
-//       overlap the main loop of tile i + 1.
+//       persistent, warp specialised: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (the whole warp walks
+//       the schedule, one elected lane issues), warps 2..5 = epilogue.  ONE smem ring whose stage is a (dy, k-chunk):
+//       the (128 + 8)-row activation boxes of the group's 1-2 row tiles (hi and lo planes; the three dx taps of a dy
+//       share a box, the tap shift is a one-row start-address offset of the UMMA descriptor) plus the weight tiles
+//       of those taps; 64-channel SWIZZLE_128B or 32-channel SWIZZLE_64B rows, whichever gives >= 2-3 stages.  All
+//       MMAs of a stage are issued from one asm block (umma_issue.cuh).  Two accumulator sets in TMEM let the
+//       epilogue of group i overlap the main loop of group i + 1.  Epilogue: TMEM -> registers in 128-column chunks
+//       -> (+bias) swizzled smem boxes -> TMA stores (32-row x 32-column box per warp, double buffered); BatchNorm
+//       column statistics are summed from the staged boxes, per warp, in a fixed order.
 //   wgrad_tc_kernel                       dW_t[co, ci] = sum_r dZ[r, co] * A[r + off_t, ci]
-//       both operands MN-major (channels contiguous, the reduction runs over pixel rows); one CTA owns a
-//       128(co) x 128(ci) tile for the three dx taps of one dy (3 x 128 TMEM columns) over a slice of
-//       the rows; partial sums go to scratch and are reduced in a fixed order (deterministic).
+//       both operands MN-major (channels contiguous, the reduction runs over pixel rows in 64-row stages); the M side
+//       (128-channel tiles) is dZ or A, whichever wastes less padding; one CTA owns an (M tile, N tile <= 160
+//       channels) pair for the three dx taps of one dy (3 accumulators) over a slice of the rows; partial sums go to
+//       scratch and are reduced in a fixed order (deterministic).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -113,15 +115,7 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, f32 accumulate)
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
+
 // wgrad: all MMAs of one 64-pixel-row stage -- up to 3 dx taps (one accumulator each, `ncol` TMEM columns apart) x 4
 // k-steps (16 rows = 2048 bytes apart in both MN-major operands) x 3 products -- in one asm block (see umma_stage_x3).
 // The tap shift (one smem row = 128 bytes = 8 descriptor units) applies to whichever operand holds the activations.
@@ -358,17 +352,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // pins a value behind every preceding asm volatile (the loads' wait): nothing computed from it can be scheduled earlier
 __device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
 
-// shared-memory matrix descriptor (SWIZZLE_128B; sm_100 descriptor version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(base_off & 7u) << 49;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 // instruction descriptor: D = f32, A = B = bf16, M x N, majors: 0 = K-major, 1 = MN-major
 __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |

@@ -294,3 +294,37 @@ def test_full_size_determinism_and_backward_linearity():
     assert torch.equal(l1, l3)
     assert torch.equal(g3, 2.0 * g1)
     assert float(g1.abs().max()) > 0
+
+
+def test_1d_model_full_size_properties():
+    """BASELINE.json configs[2] at full size (1D CNN on raw STFT win 256 / hop 128, 64 x 10 s clips, canonical width):
+    finite outputs and gradients, bit-identical repeat (fixed reduction orders), and eval-mode logits of a clip that do
+    not depend on its batch neighbours."""
+    cfg = dict(features="stft_256_128", output_dropout=0.0)
+    model = build("HierarchicalCNNClassificationModel", cfg, None, "bf16x3")
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    signal = 0.1 * torch.randn(64, 441000, generator=gen, device="cuda")
+    dlogits = torch.randn(64, 80, generator=gen, device="cuda") / 64
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+
+    def run():
+        model.load_state_dict(sd)
+        model.train()
+        for p in model.parameters():
+            p.grad = None
+        out = model(signal[..., None])["class_logits"]
+        out.backward(dlogits)
+        torch.cuda.synchronize()
+        return out.detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+
+    l1, g1 = run()
+    l2, g2 = run()
+    assert l1.shape == (64, 80) and torch.isfinite(l1).all() and torch.isfinite(g1).all()
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)
+    assert float(g1.abs().max()) > 0
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        full = model(signal[..., None])["class_logits"]
+        part = model(signal[5:9, :, None])["class_logits"]
+    assert rel_err(part.cpu().numpy(), full[5:9].cpu().numpy()) < 1e-5
