@@ -1066,8 +1066,7 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
                           (((size_t)bn * 4 + 15) & ~(size_t)15) /*bias*/ + (size_t)64 * bn /*statistics*/;
     // Stage shape.  Preferred: the three dx taps of a dy share one (128 + 8)-row activation box (a third of the
     // activation fills); wide tiles whose three weight tiles do not fit beside it fall back to one box per tap.
-    // Stage width: 64 channels (SWIZZLE_128B) when three stages and the double-buffered store staging fit, else 32
-    // channels (SWIZZLE_64B); staging falls back to single buffering before the ring drops below two stages.
+    // Stage width: 64 channels (SWIZZLE_128B) when three stages fit, else 32 channels (SWIZZLE_64B, at least two).
     size_t stage = 0, fixed = 0;
     bool ok = false;
     for (int share = (tc_mode() & 1) ? 0 : 1; share >= 0 && !ok; --share) {
@@ -1076,11 +1075,13 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
         for (int g = 0; g < p.ngroups; ++g)
             for (int t = 0; t < p.tpg; ++t) p.wrow[g][t] = tap_of[g][t] * w_npad;
         p.a_box_rows = p.tpg == 1 ? BM : BM + A_HALO;
-        for (int bk = (tc_env("FSB200_TC_BK") == 32 ? 32 : 64); bk >= 32 && !ok; bk -= 32) {
-            stage = ((size_t)p.a_box_rows * T + (size_t)bn * p.tpg) * bk * 2 * 2;
-            for (int nstg = 2; nstg >= 1 && !ok; --nstg) {
-                fixed = fixed0 + (size_t)4 * nstg * EPI_BOX_BYTES;
-                const int need = (bk == 64 && nstg == 2) ? 3 : 2;
+        // double-buffered store staging first (with a single box per warp every panel waits for its TMA store to
+        // drain: the 1x1 layers ran at half speed), then the wider stage
+        for (int nstg = 2; nstg >= 1 && !ok; --nstg) {
+            fixed = fixed0 + (size_t)4 * nstg * EPI_BOX_BYTES;
+            for (int bk = (tc_env("FSB200_TC_BK") == 32 ? 32 : 64); bk >= 32 && !ok; bk -= 32) {
+                stage = ((size_t)p.a_box_rows * T + (size_t)bn * p.tpg) * bk * 2 * 2;
+                const int need = bk == 64 ? 3 : 2;
                 if (fixed + need * stage <= SMEM_LIMIT) { p.bk = bk; p.nstg = nstg; ok = true; }
             }
         }
