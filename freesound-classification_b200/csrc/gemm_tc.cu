@@ -543,6 +543,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t stg0 = epi_stage + (uint32_t)(q * p.nstg) * EPI_BOX_BYTES;
         const unsigned char* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
         double* my_acc = stat_acc + (size_t)q * 2 * p.BN;
+        // per-lane column statistics of this CTA's column tile: compensated float32 sums in registers (a DADD per panel
+        // through shared memory was the top stall of the 1x1 layers); [128-column chunk][32-column panel][sum, sum of squares]
+        float accS[2][4][2], accC[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { (&accS[0][0][0])[i] = 0.f; (&accC[0][0][0])[i] = 0.f; }
         uint32_t sb = 0;                           // staging buffer toggle
         uint32_t it = 0;
         // interior flags of this thread's row in each tile of the NEXT group (global loads issued a group ahead)
@@ -571,7 +576,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(bT_full + 8u * slot, use & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + (set * (uint32_t)p.T + (uint32_t)t) * (uint32_t)p.BN + ((uint32_t)(q * 32) << 16);
-                    for (int c0 = 0; c0 < p.BN; c0 += 128) {
+#pragma unroll
+                    for (int ci = 0; ci < 2; ++ci) {
+                        const int c0 = ci * 128;
+                        if (c0 >= p.BN) break;
                         // ---- this thread's row, columns [c0, c0 + width): one burst of TMEM loads, one wait
                         const int width = min(128, p.BN - c0);               // multiple of 16
                         float v[128];
@@ -630,22 +638,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (p.stats && (wide || lane < 16) && !(p.dbg & 2)) {
                                     // lane l sums column cl0 + l over this warp's interior rows, straight from the staged box
                                     const uint32_t bits = ibits[t];
-                                    float s1 = 0.f, s2 = 0.f;
+                                    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains
                                     if (wide) {
 #pragma unroll
                                         for (int r = 0; r < 32; ++r) {
                                             const float x = stg_g[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
-                                            if ((bits >> r) & 1u) { s1 += x; s2 = fmaf(x, x, s2); }
+                                            if ((bits >> r) & 1u) { s1[r & 3] += x; s2[r & 3] = fmaf(x, x, s2[r & 3]); }
                                         }
                                     } else {
 #pragma unroll
                                         for (int r = 0; r < 32; ++r) {
                                             const float x = stg_g[r * 16 + lane];
-                                            if ((bits >> r) & 1u) { s1 += x; s2 = fmaf(x, x, s2); }
+                                            if ((bits >> r) & 1u) { s1[r & 3] += x; s2[r & 3] = fmaf(x, x, s2[r & 3]); }
                                         }
                                     }
-                                    my_acc[cl0 + lane] += (double)s1;
-                                    my_acc[p.BN + cl0 + lane] += (double)s2;
+                                    const float add[2] = {(s1[0] + s1[1]) + (s1[2] + s1[3]), (s2[0] + s2[1]) + (s2[2] + s2[3])};
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {        // Neumaier-compensated accumulation across tiles
+                                        const float a = accS[ci][pn][h], x = add[h];
+                                        const float tsum = a + x;
+                                        accC[ci][pn][h] += fabsf(a) >= fabsf(x) ? (a - tsum) + x : (x - tsum) + a;
+                                        accS[ci][pn][h] = tsum;
+                                    }
                                 }
                                 sb = (sb + 1u) & (uint32_t)(p.nstg - 1);
                             }
@@ -656,6 +670,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (lane == 0) bulk_wait_all();            // the staged boxes must be written before the CTA retires
         if (p.stats) {
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                for (int pn = 0; pn < 4; ++pn) {
+                    const int cl = ci * 128 + pn * 32 + lane;
+                    if (cl < p.BN) {
+                        my_acc[cl] = (double)accS[ci][pn][0] + (double)accC[ci][pn][0];
+                        my_acc[p.BN + cl] = (double)accS[ci][pn][1] + (double)accC[ci][pn][1];
+                    }
+                }
             // merge the four warps' partials in warp order (deterministic) and publish the CTA record: zero
             // outside this CTA's column tile
             asm volatile("bar.sync 1, 128;" ::: "memory");
