@@ -94,24 +94,15 @@ __device__ __forceinline__ void store_fmt(void* base, int fmt, long long plane_e
 }
 
 // accumulate float4 streams: float32 inside runs of 32 pixels, double across runs
+// Per-thread partial sums of float4 streams.  A thread visits rows / (gridDim.x * blockDim.y) ~ 10^2 pixels, so it sums
+// in float32 (the previous version flushed to double every 32 values, which bought a factor ~3 in the worst-case
+// rounding bound for 20 more registers per stream); the cross-thread and cross-block reductions run in double.
 struct Acc4 {
     float4 f;
     double d[4];
-    int n;
-    __device__ __forceinline__ void init() {
-        f = make_float4(0.f, 0.f, 0.f, 0.f);
-        d[0] = d[1] = d[2] = d[3] = 0.0;
-        n = 0;
-    }
-    __device__ __forceinline__ void add(float4 v) {
-        f.x += v.x; f.y += v.y; f.z += v.z; f.w += v.w;
-        if (++n == 32) flush();
-    }
-    __device__ __forceinline__ void flush() {
-        d[0] += f.x; d[1] += f.y; d[2] += f.z; d[3] += f.w;
-        f = make_float4(0.f, 0.f, 0.f, 0.f);
-        n = 0;
-    }
+    __device__ __forceinline__ void init() { f = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void add(float4 v) { f.x += v.x; f.y += v.y; f.z += v.z; f.w += v.w; }
+    __device__ __forceinline__ void flush() { d[0] = f.x; d[1] = f.y; d[2] = f.z; d[3] = f.w; }
 };
 
 // reduce K Acc4 records across threadIdx.y and write partials[(blockIdx.x*K + k)*Cs + c]
@@ -214,22 +205,24 @@ int pf_stats(const float* x, const Geo& g, double* partials, cudaStream_t s) {
     return 0;
 }
 
-// Fixed-order parallel reduction of per-block partial sums: 32 channels x 32 slices per CTA (1024 threads); every
-// slice walks the blocks b = slice, slice + 32, ... and the 32 slice totals are added in slice order, so the
-// result does not depend on scheduling (deterministic).
-constexpr int FIN_SLICES = 32;
-constexpr int FIN_THREADS = 32 * FIN_SLICES;
+// Fixed-order parallel reduction of per-block partial sums: FIN_CH channels x FIN_SLICES slices per CTA (1024
+// threads); every slice walks the blocks b = slice, slice + FIN_SLICES, ... (at most ~10 loads per thread for the 1184
+// records of an element-wise pass), then two tree levels add the slice totals in a fixed order (deterministic).
+constexpr int FIN_CH = 8;
+constexpr int FIN_SLICES = 128;
+constexpr int FIN_THREADS = FIN_CH * FIN_SLICES;
 
 template <int K>
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int nblk, int Cs, int c,
                                                 double (&out)[K]) {
-    __shared__ double red[K][FIN_SLICES][32];
-    const int slice = threadIdx.x >> 5, cl = threadIdx.x & 31;
+    __shared__ double red[K][FIN_SLICES][FIN_CH];
+    __shared__ double red2[K][8][FIN_CH];
+    const int slice = threadIdx.x / FIN_CH, cl = threadIdx.x % FIN_CH;
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
     if (c < Cs) {
-#pragma unroll 8
+#pragma unroll 4
         for (int b = slice; b < nblk; b += FIN_SLICES) {
 #pragma unroll
             for (int k = 0; k < K; ++k) acc[k] += partials[((long long)b * K + k) * Cs + c];
@@ -238,12 +231,23 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
 #pragma unroll
     for (int k = 0; k < K; ++k) red[k][slice][cl] = acc[k];
     __syncthreads();
+    if (threadIdx.x < 8 * FIN_CH) {            // 8 groups of 16 slices
+        const int g = threadIdx.x / FIN_CH;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < FIN_SLICES / 8; ++j) t += red[k][g * (FIN_SLICES / 8) + j][cl];
+            red2[k][g][cl] = t;
+        }
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double t = 0.0;
-        if (threadIdx.x < 32) {
+        if (threadIdx.x < FIN_CH) {
 #pragma unroll
-            for (int j = 0; j < FIN_SLICES; ++j) t += red[k][j][cl];
+            for (int j = 0; j < 8; ++j) t += red2[k][j][cl];
         }
         out[k] = t;
     }
@@ -254,10 +258,10 @@ bn_finalize_kernel(const double* partials, int nblk, long long count, const floa
                    const float* beta, float* run_mean, float* run_var, long long* bn_count,
                    int training, int C, int Cs, float* scale, float* shift, float* mean,
                    float* invstd) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = blockIdx.x * FIN_CH + (threadIdx.x % FIN_CH);
     double tot[2] = {0.0, 0.0};
     if (training) reduce_partials<2>(partials, nblk, Cs, c, tot);
-    if (threadIdx.x >= 32 || c >= Cs) return;
+    if (threadIdx.x >= FIN_CH || c >= Cs) return;
     if (c >= C) {
         scale[c] = 0.f; shift[c] = 0.f;
         if (mean) mean[c] = 0.f;
@@ -292,7 +296,7 @@ bn_finalize_kernel(const double* partials, int nblk, long long count, const floa
 int bn_finalize(const double* partials, int nblk, long long count, const float* gamma, const float* beta,
                 float* run_mean, float* run_var, long long* bn_count, int training, int C, int Cs,
                 float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
-    bn_finalize_kernel<<<(Cs + 31) / 32, FIN_THREADS, 0, s>>>(partials, nblk, count, gamma, beta, run_mean,
+    bn_finalize_kernel<<<(Cs + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, s>>>(partials, nblk, count, gamma, beta, run_mean,
                                                      run_var, bn_count, training, C, Cs, scale, shift,
                                                      mean, invstd);
     FSB_LAUNCHED();
@@ -831,10 +835,10 @@ int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const 
 __global__ void __launch_bounds__(FIN_THREADS)
 bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs,
                        float* dgamma, float* dbeta, float* dslope, float* c1, float* c2) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = blockIdx.x * FIN_CH + (threadIdx.x % FIN_CH);
     double tot[3];
     reduce_partials<3>(partials, nblk, Cs, c, tot);
-    if (threadIdx.x >= 32 || c >= Cs) return;
+    if (threadIdx.x >= FIN_CH || c >= Cs) return;
     if (c >= C) { c1[c] = 0.f; c2[c] = 0.f; return; }
     if (dbeta) dbeta[c] = (float)tot[0];
     if (dgamma) dgamma[c] = (float)tot[1];
@@ -845,7 +849,7 @@ bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C,
 
 int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, float* dgamma, float* dbeta,
                     float* dslope, float* c1, float* c2, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<(Cs + 31) / 32, FIN_THREADS, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
+    bn_bwd_finalize_kernel<<<(Cs + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
                                                          c1, c2);
     FSB_LAUNCHED();
     return 0;
