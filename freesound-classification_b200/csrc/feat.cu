@@ -45,7 +45,10 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tw = reinterpret_cast<float2*>(smem_raw);            // NFFT
-    float2* buf0 = tw + NFFT;                                    // PAR * M = 1024
+    // per-stage radix-4 twiddles (w^k, w^2k, w^3k), k < Ns, stored contiguously in k: lanes read consecutive
+    // entries.  Reading them from `tw` with the stride (NFFT/4)/Ns put up to 16 lanes on one bank.
+    float2* tws = tw + NFFT;                                     // 3 * (1 + 4 + 16 + ...) <= M entries
+    float2* buf0 = tws + M;                                      // PAR * M = 1024
     float2* buf1 = buf0 + 1024;                                  // 1024
     float* mag = reinterpret_cast<float*>(buf1 + 1024);          // PAR * (BINS + 1)
     float* tile = mag + PAR * (BINS + 1);                        // F_out * (FPB + 1)
@@ -58,6 +61,18 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
     const float* x = pcm + (long long)clip * pcm_stride;
 
     for (int i = tid; i < NFFT; i += FEAT_THREADS) tw[i] = tw_g[i];
+    {
+        int base = 0, Ns = 1;
+#pragma unroll
+        for (int st = 0; st < LOG2M / 2; ++st) {
+            for (int e = tid; e < 3 * Ns; e += FEAT_THREADS) {
+                const int k = e / 3, i = e - 3 * k;
+                tws[base + e] = tw_g[(i + 1) * ((NFFT / 4) / Ns * k)];
+            }
+            base += 3 * Ns;
+            Ns <<= 2;
+        }
+    }
     __syncthreads();
 
     for (int it = 0; it < nfr; it += PAR) {
@@ -87,17 +102,18 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
             const int slot = tid / (M / 4);
             const int j = tid - slot * (M / 4);
             const float2* s0 = nullptr;
-            int Ns = 1;
+            int Ns = 1, tbase = 0;
 #pragma unroll
             for (int st = 0; st < LOG2M / 2; ++st) {
                 s0 = src + slot * M;
                 float2* d0 = dst + slot * M;
                 int k = j & (Ns - 1);
-                int tstep = (NFFT / 4) / Ns * k;             // table index of exp(-2 pi i k/(4 Ns))
+                const float2* t3 = tws + tbase + 3 * k;      // exp(-2 pi i m k/(4 Ns)), m = 1, 2, 3
+                tbase += 3 * Ns;
                 float2 v0 = s0[j];
-                float2 v1 = cmul(s0[j + M / 4], tw[tstep]);
-                float2 v2 = cmul(s0[j + M / 2], tw[2 * tstep]);
-                float2 v3 = cmul(s0[j + 3 * M / 4], tw[3 * tstep]);
+                float2 v1 = cmul(s0[j + M / 4], t3[0]);
+                float2 v2 = cmul(s0[j + M / 2], t3[1]);
+                float2 v3 = cmul(s0[j + 3 * M / 4], t3[2]);
                 float2 a = make_float2(v0.x + v2.x, v0.y + v2.y);
                 float2 b = make_float2(v0.x - v2.x, v0.y - v2.y);
                 float2 c = make_float2(v1.x + v3.x, v1.y + v3.y);
@@ -186,7 +202,7 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
 
 static size_t feat_smem_bytes(int n_fft, int f_out) {
     int m = n_fft / 2, par = 1024 / m, bins = m + 1;
-    return (size_t)n_fft * 8 + 2 * 1024 * 8 + (size_t)par * (bins + 1) * 4 + (size_t)f_out * (FPB + 1) * 4;
+    return (size_t)n_fft * 8 + (size_t)m * 8 + 2 * 1024 * 8 + (size_t)par * (bins + 1) * 4 + (size_t)f_out * (FPB + 1) * 4;
 }
 
 template <int LOG2N>
