@@ -13,8 +13,12 @@
  *   - plain C types only: raw DEVICE pointers, explicit sizes/strides, `void* stream` = cudaStream_t;
  *   - every function returns 0 on success, a non-zero code otherwise (positive = cudaError_t,
  *     negative = FSB_E_*); nothing throws, nothing calls exit(); `fsb_last_error()` gives text;
- *   - kernels are enqueue-only on the caller's stream: no allocation, no synchronisation.  All
- *     device memory (incl. workspace, size from the *_workspace_bytes query) belongs to the caller;
+ *   - calls only enqueue work: no device-memory allocation, no host synchronisation.  All device memory
+ *     (incl. workspace, size from the *_workspace_bytes query) belongs to the caller.  Work is ordered
+ *     on the caller's stream; fsb_net_forward / fsb_net_backward additionally fork part of it (weight
+ *     packing, weight-gradient GEMMs) onto one internal low-priority stream per plan and join it back
+ *     with events before they return control of the stream, so the caller sees plain stream semantics
+ *     (set FSB200_NO_OVERLAP=1 to keep everything on the caller's stream);
  *   - one host thread per device (one process per GPU under torchrun); handles are not thread-safe.
  */
 #ifndef FSB200_H
