@@ -328,3 +328,28 @@ def test_1d_model_full_size_properties():
         full = model(signal[..., None])["class_logits"]
         part = model(signal[5:9, :, None])["class_logits"]
     assert rel_err(part.cpu().numpy(), full[5:9].cpu().numpy()) < 1e-5
+
+
+def test_bucketed_inference_matches_oracle_on_identical_padded_batches():
+    """BASELINE.json configs[4] semantics at small size: variable-length clips, length-bucketed batches, zero padding
+    per batch; every clip's probabilities equal the oracle's on the SAME padded batch (padding changes the global-max
+    features, so batches must be identical), and clips outside the buckets are reported as NaN rows."""
+    from fsb200.inference import pack_batches, pad_batch, predict_bucketed
+    cfg = dict(conv_base_depth=8, growth_rate=1.5)
+    model = build("TwoDimensionalCNNClassificationModel", cfg, None, "bf16x3")
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    config = make_config(**cfg)
+    rng = np.random.RandomState(5)
+    lengths = rng.randint(33 * 1024, 90000, size=11).tolist() + [20000]          # the last clip is below buckets[0]
+    clips = [restate.synth_waveforms(1, n, seed=100 + k)[0] for k, n in enumerate(lengths)]
+    buckets = [33 * 1024, 50000, 70000, 100000]
+    got, stats = predict_bucketed(model, clips, buckets, max_batch_elems=150000, return_stats=True)
+    assert got.shape == (12, 80) and np.isnan(got[11]).all() and stats["dropped"] == 1
+    assert stats["padding_overhead"] >= 0.0 and stats["real_samples"] == sum(lengths[:11])
+    batches, _ = pack_batches(lengths, buckets, 150000)
+    for indices in batches:
+        batch = torch.from_numpy(pad_batch(clips, indices))
+        with torch.no_grad():
+            ref = torch.sigmoid(restate.net2d_forward(sd, config, batch, training=False)).numpy()
+        assert rel_err(got[indices], ref) < 1e-3
+        assert np.array_equal(np.argsort(-got[indices], 1)[:, :3], np.argsort(-ref, 1)[:, :3])

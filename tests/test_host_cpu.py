@@ -198,3 +198,23 @@ def test_data_parallel_gradient_allreduce_gloo(tmp_path):
     assert np.array_equal(s0, s1)                       # every rank holds the same summed gradient
     assert np.allclose(s0, l0 + l1, rtol=0, atol=1e-6 * np.abs(s0).max())
     assert np.abs(l0 - l1).max() > 0                    # the shards really differed
+
+
+def test_bucketed_inference_packing():
+    from fsb200.inference import pack_batches, pad_batch
+    rng = np.random.RandomState(3)
+    lengths = rng.randint(1000, 9000, size=57)
+    buckets = [2000, 4000, 6000, 8000]
+    batches, dropped = pack_batches(lengths, buckets, max_batch_elems=15000)
+    covered = sorted(i for b in batches for i in b)
+    assert sorted(covered + dropped) == list(range(57))                  # every clip is placed or reported
+    assert all(lengths[i] < 2000 or lengths[i] >= 8000 for i in dropped)
+    for b in batches:
+        bins = set(np.digitize(lengths[b], buckets))
+        assert len(bins) == 1                                             # one length bucket per batch
+        assert sum(lengths[i] for i in b[:-1]) < 15000 + max(lengths[b])  # closed by the first clip after the limit
+    clips = [np.full(n, k, np.float32) for k, n in enumerate(lengths)]
+    x = pad_batch(clips, batches[0])
+    assert x.shape == (len(batches[0]), max(lengths[batches[0]]), 1) and x.dtype == np.float32
+    for row, i in enumerate(batches[0]):
+        assert (x[row, :lengths[i], 0] == i).all() and (x[row, lengths[i]:, 0] == 0).all()
