@@ -14,8 +14,9 @@ PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
 
 def default_precision():
-    """GEMM back end: `FSB200_PRECISION` = fp32 (CUDA cores) | bf16x3 (tcgen05, fp32-grade) | bf16."""
-    return os.environ.get("FSB200_PRECISION", "fp32")
+    """GEMM back end: `FSB200_PRECISION` = bf16x3 (default: tcgen05 tensor cores, split-bf16 operands, fp32-grade,
+    logits within 1e-3 of the reference) | fp32 (CUDA-core GEMMs, bit-faithful cross-check) | bf16 (single pass)."""
+    return os.environ.get("FSB200_PRECISION", "bf16x3")
 
 
 def _stream():
