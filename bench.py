@@ -38,6 +38,15 @@ CONV_GFLOP_PER_CLIP = 42.81      # canonical config, fwd + dgrad
 FEAT_MB_PER_CLIP = 1.985         # PCM read + log-mel write
 
 
+DTYPES = {
+    "fp32": "f32",
+    "fp16x3": "fp16x3 (split-half operands hi+lo, three tcgen05 products, f32 accumulate: fp32-grade, fwd and bwd)",
+    "fp16": "fp16 (single tcgen05 pass, f32 accumulate)",
+    "mixed": "fp16x3 forward (split-half operands, three tcgen05 products, f32 accumulate: fp32-grade) + fp16 single-pass "
+             "dgrad/wgrad with per-tensor power-of-two gradient scaling, f32 accumulate",
+}
+
+
 def canonical_config(dropout):
     from oracle.reference_shim import make_config
     return make_config(features="mel_2048_1024_128", num_conv_blocks=5, conv_base_depth=100, growth_rate=1.5,
@@ -321,7 +330,7 @@ def run_ours(args):
     # the per-family times are taken with the side-stream overlap of weight-gradient GEMMs / weight packing switched
     # off, so that each family's CUDA-event time is its own device time (overlapped, the families' times add up to more
     # than the step); `value` / `e2e` above are measured with the overlap on
-    os.environ["FSB200_NO_OVERLAP"] = "1"
+    plan.set_overlap(False)
     if rank == 0:
         plan.set_profiling(True)
     for i in range(nprof):
@@ -332,7 +341,7 @@ def run_ours(args):
                 a = acc.setdefault(name, [0.0, 0.0])
                 a[0] += ms / nprof
                 a[1] += fl / nprof
-    os.environ.pop("FSB200_NO_OVERLAP", None)
+    plan.set_overlap(True)
     if rank == 0:
         plan.set_profiling(False)
         phases = {k: {"ms": round(v[0], 4), "gflop": round(v[1] / 1e9, 2)} for k, v in acc.items()}
@@ -382,8 +391,7 @@ def run_ours(args):
         line = {
             "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, f32 accumulate)",
-                                           "bf16": "bf16"}[args.precision],
+            "vs_baseline": None, "dtype": DTYPES[args.precision],
             "data": "synthetic", "config": workload_config(batch, world, args.precision),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -406,8 +414,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--precision", default=os.environ.get("FSB200_PRECISION", "bf16x3"),
-                    choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FSB200_PRECISION", "mixed"),
+                    choices=["fp32", "fp16x3", "fp16", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

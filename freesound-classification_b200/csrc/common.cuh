@@ -1,7 +1,7 @@
 // Shared definitions for libfsb200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -90,16 +90,40 @@ __device__ __forceinline__ long long geo_q_to_row(const Geo& g, long long q) {
 
 // ---------------------------------------------------------------------------------------------
 // activation storage formats consumed by the GEMM kernels
-//   FMT_F32  : one float32 plane                      (precision 0, CUDA-core GEMM)
-//   FMT_BF16X2: two bf16 planes hi, lo with x ~= hi+lo (precision 1: bf16x3 tcgen05 GEMM;
-//               precision 2 reads the hi plane only)
-// A "plane" is rows*Cs elements; for FMT_BF16X2 the lo plane follows the hi plane.
+//   FMT_F32   : one float32 plane                          (precision 0, CUDA-core GEMM)
+//   FMT_H16X2 : two IEEE-half planes hi, lo with x ~= hi+lo (three-product tcgen05 GEMM: lo*hi + hi*lo + hi*hi keeps
+//               ~2^-22 per product -- float32-grade)
+//   FMT_H16   : the hi plane only                           (single-pass tcgen05 GEMM, ~2^-12 per operand)
+// A "plane" is rows*Cs elements; the lo plane follows the hi plane (buffers are always sized for both).
+// Half (11-bit significand) rather than bfloat16 (8-bit): the single-pass backward of the mixed mode then keeps
+// 2^-12 per operand instead of 2^-9.  The price is range: activations are clamped to +-65504 (post-BatchNorm values
+// are O(1)), and gradient planes are written with a per-tensor power-of-two scale (GradScale below).
 // ---------------------------------------------------------------------------------------------
-enum { FMT_F32 = 0, FMT_BF16X2 = 1 };
+enum { FMT_F32 = 0, FMT_H16X2 = 1, FMT_H16 = 2 };
 
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+__device__ __forceinline__ void split_h16(float x, __half& hi, __half& lo) {
+    const float c = fminf(fmaxf(x, -65504.f), 65504.f);
+    x = (x == x) ? c : x;                       // NaN stays NaN (a diverged run must not be masked)
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+// Per-tensor gradient scale.  `absmax_bits` holds the float32 bit pattern of an upper bound B >= max |dz| of the
+// tensor (0 = unknown / not used).  Writers multiply by 2^(13 - floor(log2 B)) so that the largest magnitude lands in
+// [2^13, 2^14) at most -- a factor 4 below the half maximum, ~28 binades above the smallest normal half -- and the
+// consumers (dgrad epilogue, wgrad finalize) multiply by the inverse.  Powers of two: scaling is exact and the
+// backward pass stays exactly linear in the incoming gradient.
+__host__ __device__ __forceinline__ int gs_exponent(unsigned absmax_bits) {
+    const int e = (int)((absmax_bits >> 23) & 0xFFu);          // biased exponent of B
+    if (absmax_bits == 0u || e == 0 || e == 255) return 0;      // unknown, denormal or non-finite bound: no scaling
+    int k = 13 - (e - 127);
+    return k < -100 ? -100 : (k > 100 ? 100 : k);
+}
+__device__ __forceinline__ float gs_scale(const unsigned* absmax_bits) {
+    return absmax_bits ? __uint_as_float((unsigned)(127 + gs_exponent(*absmax_bits)) << 23) : 1.f;
+}
+__device__ __forceinline__ float gs_inv_scale(const unsigned* absmax_bits) {
+    return absmax_bits ? __uint_as_float((unsigned)(127 - gs_exponent(*absmax_bits)) << 23) : 1.f;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

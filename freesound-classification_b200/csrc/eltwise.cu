@@ -77,19 +77,21 @@ int pf_build_mask(const Geo& g, unsigned char* mask, cudaStream_t s) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-__device__ __forceinline__ void store_fmt(void* base, int fmt, long long plane_elems, long long idx, float4 v) {
+// writes four channels in the destination format; half formats multiply by `scale` first (1 for activations, the
+// tensor's power-of-two GradScale for gradients, common.cuh)
+__device__ __forceinline__ void store_fmt(void* base, int fmt, long long plane_elems, long long idx, float4 v,
+                                          float scale = 1.f) {
     if (fmt == FMT_F32) {
         st4(reinterpret_cast<float*>(base) + idx, v);
     } else {
-        __nv_bfloat16 h[4], l[4];
-        split_bf16(v.x, h[0], l[0]);
-        split_bf16(v.y, h[1], l[1]);
-        split_bf16(v.z, h[2], l[2]);
-        split_bf16(v.w, h[3], l[3]);
-        __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(base) + idx;
-        __nv_bfloat16* lp = hp + plane_elems;
+        __half h[4], l[4];
+        split_h16(v.x * scale, h[0], l[0]);
+        split_h16(v.y * scale, h[1], l[1]);
+        split_h16(v.z * scale, h[2], l[2]);
+        split_h16(v.w * scale, h[3], l[3]);
+        __half* hp = reinterpret_cast<__half*>(base) + idx;
         *reinterpret_cast<uint2*>(hp) = *reinterpret_cast<uint2*>(h);
-        *reinterpret_cast<uint2*>(lp) = *reinterpret_cast<uint2*>(l);
+        if (fmt == FMT_H16X2) *reinterpret_cast<uint2*>(hp + plane_elems) = *reinterpret_cast<uint2*>(l);
     }
 }
 
@@ -105,8 +107,9 @@ struct Acc4 {
     __device__ __forceinline__ void flush() { d[0] = f.x; d[1] = f.y; d[2] = f.z; d[3] = f.w; }
 };
 
-// reduce K Acc4 records across threadIdx.y and write partials[(blockIdx.x*K + k)*Cs + c]
-template <int K>
+// reduce K Acc4 records across threadIdx.y and write partials[(blockIdx.x*K + k)*Cs + c]; the last NMAX records are
+// combined with max instead of + (gradient magnitude bounds)
+template <int K, int NMAX = 0>
 __device__ __forceinline__ void block_reduce_store(Acc4 (&acc)[K], double* partials, int Cs, int c0, bool cok) {
     __shared__ double red[256 * 4];
 #pragma unroll
@@ -122,7 +125,7 @@ __device__ __forceinline__ void block_reduce_store(Acc4 (&acc)[K], double* parti
             for (int y = 0; y < (int)blockDim.y; ++y) {
                 int tt = y * blockDim.x + threadIdx.x;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s[i] += red[tt * 4 + i];
+                for (int i = 0; i < 4; ++i) s[i] = k >= K - NMAX ? fmax(s[i], red[tt * 4 + i]) : s[i] + red[tt * 4 + i];
             }
             double* o = partials + ((long long)blockIdx.x * K + k) * Cs + c0;
 #pragma unroll
@@ -164,9 +167,9 @@ __global__ void zero_border_kernel(float4* buf, Geo g, long long plane_vec, int 
 int pf_zero_border(void* buf, int fmt, const Geo& g, cudaStream_t s) {
     int border_per_img = g.Hp * g.Wp - g.H * g.W;
     if (border_per_img == 0) return 0;
-    // a float4 is 4 float32 or 8 bf16: vec_per_row counts 16-byte units per row per plane
+    // a float4 is 4 float32 or 8 halves: vec_per_row counts 16-byte units per row per plane
     int vec_per_row = fmt == FMT_F32 ? g.Cs / 4 : g.Cs / 8;
-    int nplanes = fmt == FMT_F32 ? 1 : 2;
+    int nplanes = fmt == FMT_H16X2 ? 2 : 1;
     long long plane_vec = g.rows * vec_per_row;
     long long total = (long long)g.N * border_per_img * vec_per_row;
     int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
@@ -176,7 +179,7 @@ int pf_zero_border(void* buf, int fmt, const Geo& g, cudaStream_t s) {
 }
 
 int pf_zero_all(void* buf, int fmt, const Geo& g, cudaStream_t s) {
-    size_t bytes = (size_t)g.rows * g.Cs * 4;   // f32: 4 B/elem ; bf16x2: 2 planes x 2 B/elem
+    size_t bytes = (size_t)g.rows * g.Cs * 4;   // f32: 4 B/elem ; half: 2 planes x 2 B/elem
     (void)fmt;
     FSB_CUDA(cudaMemsetAsync(buf, 0, bytes, s));
     return 0;
@@ -212,7 +215,7 @@ constexpr int FIN_CH = 8;
 constexpr int FIN_SLICES = 128;
 constexpr int FIN_THREADS = FIN_CH * FIN_SLICES;
 
-template <int K>
+template <int K, int NMAX = 0>
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int nblk, int Cs, int c,
                                                 double (&out)[K]) {
     __shared__ double red[K][FIN_SLICES][FIN_CH];
@@ -225,7 +228,10 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
 #pragma unroll 4
         for (int b = slice; b < nblk; b += FIN_SLICES) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += partials[((long long)b * K + k) * Cs + c];
+            for (int k = 0; k < K; ++k) {
+                const double v = partials[((long long)b * K + k) * Cs + c];
+                acc[k] = k >= K - NMAX ? fmax(acc[k], v) : acc[k] + v;      // trailing records: max (magnitude bounds)
+            }
         }
     }
 #pragma unroll
@@ -237,7 +243,10 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
         for (int k = 0; k < K; ++k) {
             double t = 0.0;
 #pragma unroll
-            for (int j = 0; j < FIN_SLICES / 8; ++j) t += red[k][g * (FIN_SLICES / 8) + j][cl];
+            for (int j = 0; j < FIN_SLICES / 8; ++j) {
+                const double v = red[k][g * (FIN_SLICES / 8) + j][cl];
+                t = k >= K - NMAX ? fmax(t, v) : t + v;
+            }
             red2[k][g][cl] = t;
         }
     }
@@ -247,7 +256,7 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
         double t = 0.0;
         if (threadIdx.x < FIN_CH) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t += red2[k][j][cl];
+            for (int j = 0; j < 8; ++j) t = k >= K - NMAX ? fmax(t, red2[k][j][cl]) : t + red2[k][j][cl];
         }
         out[k] = t;
     }
@@ -528,9 +537,10 @@ int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, in
 // window.  (The previous version walked full-res pixels and re-read the window four times: 3.4 TB/s.)
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restrict__ zf, Geo g, int pool_h,
-                   void* dzf, int fmt) {
+                   void* dzf, int fmt, const unsigned* absmax) {
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
     if (cv >= g.Cs / 4) return;
+    const float gscale = gs_scale(absmax);
     const int c0 = cv * 4;
     const long long plane = g.rows * g.Cs;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -566,11 +576,11 @@ maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restric
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k][i] = best == k ? gs[i] : 0.f;
         }
-        store_fmt(dzf, fmt, plane, r00 * g.Cs + c0, make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
-        store_fmt(dzf, fmt, plane, (r00 + 1) * g.Cs + c0, make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+        store_fmt(dzf, fmt, plane, r00 * g.Cs + c0, make_float4(o[0][0], o[0][1], o[0][2], o[0][3]), gscale);
+        store_fmt(dzf, fmt, plane, (r00 + 1) * g.Cs + c0, make_float4(o[1][0], o[1][1], o[1][2], o[1][3]), gscale);
         if (pool_h == 2) {
-            store_fmt(dzf, fmt, plane, (r00 + g.Wp) * g.Cs + c0, make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
-            store_fmt(dzf, fmt, plane, (r00 + g.Wp + 1) * g.Cs + c0, make_float4(o[3][0], o[3][1], o[3][2], o[3][3]));
+            store_fmt(dzf, fmt, plane, (r00 + g.Wp) * g.Cs + c0, make_float4(o[2][0], o[2][1], o[2][2], o[2][3]), gscale);
+            store_fmt(dzf, fmt, plane, (r00 + g.Wp + 1) * g.Cs + c0, make_float4(o[3][0], o[3][1], o[3][2], o[3][3]), gscale);
         }
         // uncovered trailing column / row / corner
         const bool last_x = odd_w && px == gp.W - 1, last_y = odd_h && py == gp.H - 1;
@@ -587,13 +597,13 @@ maxpool_bwd_kernel(const float* __restrict__ dzp, Geo gp, const float* __restric
 }
 
 int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h, void* dzf,
-                     int fmt, cudaStream_t s) {
+                     int fmt, const unsigned* absmax, cudaStream_t s) {
     EW_CHECK(gf);
     EW_CHECK(gp);
     FSB_REQUIRE(gf.W - 2 * gp.W <= 1 && gf.W >= 2 * gp.W && (pool_h == 1 ? gf.H == gp.H : (gf.H - 2 * gp.H <= 1 && gf.H >= 2 * gp.H)),
                 "maxpool_backward: geometries are not a floor-mode 2x pooling pair");
     EwShape sh = ew_shape(gp);
-    maxpool_bwd_kernel<<<sh.grid, sh.block, 0, s>>>(dzp, gp, zf, gf, pool_h, dzf, fmt);
+    maxpool_bwd_kernel<<<sh.grid, sh.block, 0, s>>>(dzp, gp, zf, gf, pool_h, dzf, fmt, absmax);
     FSB_LAUNCHED();
     return 0;
 }
@@ -784,6 +794,7 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict_
                          double* partials) {
     EW_PROLOGUE
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
+    float4 mx = s0, zx = s0;              // max |dy|, max |zhat|: bound of |dz| for the half-precision gradient scale
     if (cok) {
         BwdCoef k = load_bwd<RES>(bn, res, c0);
         // ROWS rows in flight per thread (two loads each in the plain variant): see bn_act_fwd_simple_kernel
@@ -808,13 +819,16 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict_
                     float4 dy, zh, dsl;
                     bwd_compute<RES, DA2>(in[j], k, dr, idx[j], dy, zh, dsl);
                     add4(s0, dy); fma4(s1, dy, zh); add4(s2, dsl);
+                    mx = make_float4(fmaxf(mx.x, fabsf(dy.x)), fmaxf(mx.y, fabsf(dy.y)), fmaxf(mx.z, fabsf(dy.z)),
+                                     fmaxf(mx.w, fabsf(dy.w)));
+                    zx = make_float4(fmaxf(zx.x, fabsf(zh.x)), fmaxf(zx.y, fabsf(zh.y)), fmaxf(zx.z, fabsf(zh.z)),
+                                     fmaxf(zx.w, fabsf(zh.w)));
                 }
         }
     }
-    Acc4 acc[3];
-    acc[0].init(); acc[1].init(); acc[2].init();
-    acc[0].f = s0; acc[1].f = s1; acc[2].f = s2;
-    block_reduce_store<3>(acc, partials, g.Cs, c0, cok);
+    Acc4 acc[5];
+    acc[0].f = s0; acc[1].f = s1; acc[2].f = s2; acc[3].f = mx; acc[4].f = zx;
+    block_reduce_store<5, 2>(acc, partials, g.Cs, c0, cok);
 }
 
 int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
@@ -833,24 +847,32 @@ int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const 
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
-bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs,
-                       float* dgamma, float* dbeta, float* dslope, float* c1, float* c2) {
+bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
+                       float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax) {
     const int c = blockIdx.x * FIN_CH + (threadIdx.x % FIN_CH);
-    double tot[3];
-    reduce_partials<3>(partials, nblk, Cs, c, tot);
+    double tot[5];
+    reduce_partials<5, 2>(partials, nblk, Cs, c, tot);
     if (threadIdx.x >= FIN_CH || c >= Cs) return;
     if (c >= C) { c1[c] = 0.f; c2[c] = 0.f; return; }
     if (dbeta) dbeta[c] = (float)tot[0];
     if (dgamma) dgamma[c] = (float)tot[1];
     if (dslope) dslope[c] = (float)tot[2];
-    c1[c] = (float)(tot[0] / (double)count);
-    c2[c] = (float)(tot[1] / (double)count);
+    const float m1 = (float)(tot[0] / (double)count), m2 = (float)(tot[1] / (double)count);
+    c1[c] = m1;
+    c2[c] = m2;
+    if (absmax) {
+        // |dz| = |scale (dy - c1 - zhat c2)| <= |scale| (max|dy| + |c1| + max|zhat| |c2|); 1.001: float32 rounding of
+        // the apply pass.  Non-negative floats order like their bit patterns, and max is order independent.
+        const float bound = 1.001f * fabsf(bn_scale[c]) * ((float)tot[3] + fabsf(m1) + (float)tot[4] * fabsf(m2));
+        if (bound > 0.f) atomicMax(absmax, __float_as_uint(bound));
+    }
 }
 
-int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, float* dgamma, float* dbeta,
-                    float* dslope, float* c1, float* c2, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<(Cs + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, s>>>(partials, nblk, count, C, Cs, dgamma, dbeta, dslope,
-                                                         c1, c2);
+int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
+                    float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
+                    cudaStream_t s) {
+    bn_bwd_finalize_kernel<<<(Cs + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, s>>>(partials, nblk, count, C, Cs, bn_scale, dgamma,
+                                                                              dbeta, dslope, c1, c2, absmax);
     FSB_LAUNCHED();
     return 0;
 }
@@ -859,9 +881,10 @@ template <bool RES, bool DA2>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2, const float* __restrict__ z,
                         Geo g, BnCoef bn, Residual res, Dropout dr, const float* c1, const float* c2, void* dz,
-                        int fmt, float* dres) {
+                        int fmt, float* dres, const unsigned* absmax) {
     EW_PROLOGUE
     if (!cok) return;
+    const float gscale = gs_scale(absmax);
     BwdCoef k = load_bwd<RES>(bn, res, c0);
     float4 m1 = ld4(c1 + c0), m2 = ld4(c2 + c0);
     const long long plane = g.rows * g.Cs;
@@ -875,31 +898,32 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__
             bwd_compute<RES, DA2>(inA, k, dr, idxA, dy, zh, dsl);
             float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
                                    k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
-            store_fmt(dz, fmt, plane, idxA, o);
+            store_fmt(dz, fmt, plane, idxA, o, gscale);
             if (RES && dres) st4(dres + idxA, dy);
         }
         if (okB) {
             bwd_compute<RES, DA2>(inB, k, dr, idxB, dy, zh, dsl);
             float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
                                    k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
-            store_fmt(dz, fmt, plane, idxB, o);
+            store_fmt(dz, fmt, plane, idxB, o, gscale);
             if (RES && dres) st4(dres + idxB, dy);
         }
     }
 }
 
 int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
-                     Dropout dr, const float* c1, const float* c2, void* dz, int fmt, float* dres, cudaStream_t s) {
+                     Dropout dr, const float* c1, const float* c2, void* dz, int fmt, float* dres,
+                     const unsigned* absmax, cudaStream_t s) {
     EW_CHECK(g);
     FSB_REQUIRE(!(res.zr && dA2), "bn_act_bwd: residual and second gradient are mutually exclusive");
     FSB_REQUIRE(res.zr || !dres, "bn_act_bwd: dres needs a residual branch");
     EwShape sh = ew_shape(g);
     if (res.zr)
-        bn_act_bwd_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
+        bn_act_bwd_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, absmax);
     else if (dA2)
-        bn_act_bwd_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
+        bn_act_bwd_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, absmax);
     else
-        bn_act_bwd_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres);
+        bn_act_bwd_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, absmax);
     FSB_LAUNCHED();
     return 0;
 }
@@ -955,10 +979,10 @@ __global__ void nchw_to_pf_kernel(const float* x, Geo g, void* dst, int fmt) {
         if (fmt == FMT_F32) {
             reinterpret_cast<float*>(dst)[idx] = v;
         } else {
-            __nv_bfloat16 h, l;
-            split_bf16(v, h, l);
-            reinterpret_cast<__nv_bfloat16*>(dst)[idx] = h;
-            reinterpret_cast<__nv_bfloat16*>(dst)[plane + idx] = l;
+            __half h, l;
+            split_h16(v, h, l);
+            reinterpret_cast<__half*>(dst)[idx] = h;
+            if (fmt == FMT_H16X2) reinterpret_cast<__half*>(dst)[plane + idx] = l;
         }
     }
 }

@@ -61,8 +61,9 @@ int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropou
 int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, double* out_stats,
                     cudaStream_t s);
 // dzf (fmt planes, full-res geometry) <- dzp routed to the first maximum of every window
+// absmax (optional): GradScale of the half-precision destination (common.cuh)
 int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h,
-                     void* dzf, int fmt, cudaStream_t s);
+                     void* dzf, int fmt, const unsigned* absmax, cudaStream_t s);
 
 // global max over (H, W) per (n, c): feat[n*feat_stride + feat_off + c], argrow[n*C + c] (padded row)
 // scratch: gmax_scratch_bytes(g) bytes (packed per-(n, c) atomic-max slots)
@@ -74,16 +75,19 @@ int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* 
                   float* dx, cudaStream_t s);
 
 // backward of a = act(BN(z) [+ residual]) given dA = dA1 (+ dA2):
-//   reduce  : partials [nblk][3][Cs] doubles = sum dy, sum dy*zhat, sum dslope
-//   finalize: dgamma, dbeta, dslope (C entries, written) and c1 = mean dy, c2 = mean dy*zhat (Cs)
-//   apply   : dz = scale * (dy - c1 - zhat*c2) -> fmt planes ; dres (float32, optional) = dy
+//   reduce  : partials [nblk][5][Cs] doubles = sum dy, sum dy*zhat, sum dslope, max |dy|, max |zhat|
+//   finalize: dgamma, dbeta, dslope (C entries, written) and c1 = mean dy, c2 = mean dy*zhat (Cs);
+//             absmax (optional, zeroed by the caller): atomicMax of the float32 bits of a bound on |dz| (GradScale)
+//   apply   : dz = scale * (dy - c1 - zhat*c2) -> fmt planes (half formats: times the GradScale of `absmax`);
+//             dres (float32, optional) = dy
 int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn,
                       Residual res, Dropout dr, double* partials, cudaStream_t s);
-int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, float* dgamma,
-                    float* dbeta, float* dslope, float* c1, float* c2, cudaStream_t s);
+int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
+                    float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
+                    cudaStream_t s);
 int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn,
                      Residual res, Dropout dr, const float* c1, const float* c2, void* dz, int fmt,
-                     float* dres, cudaStream_t s);
+                     float* dres, const unsigned* absmax, cudaStream_t s);
 
 // column sums of a dense (rows, C) matrix with row stride ld (final Linear bias gradient)
 int colsum(const float* x, long long rows, int C, int ld, float* out, cudaStream_t s);

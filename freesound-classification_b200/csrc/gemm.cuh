@@ -4,8 +4,9 @@
 //     dW_t        = sum_r A[r + off_t, :]^T dZ[r, :]               (wgrad)
 // over padded-flat NHWC tensors (common.cuh).  Two back ends implement it:
 //   precision 0 : float32 CUDA-core tiles            (gemm_simt.cu)
-//   precision 1 : bf16x3 split tcgen05 / TMEM / TMA  (gemm_tc.cu)   -- fp32-grade accuracy
-//   precision 2 : single-pass bf16 tcgen05           (gemm_tc.cu)
+//   precision 1 : split-half (hi + lo) tcgen05 / TMEM / TMA, three products  (gemm_tc.cu)   -- fp32-grade accuracy
+//   precision 2 : single-pass half tcgen05                                   (gemm_tc.cu)
+// (the network-level "mixed" mode runs forward GEMMs at precision 1 and backward GEMMs at precision 2, net.cu)
 // Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.Conv1d / nn.Linear
 // (networks/classifiers.py:526-531, :75-80, :544-549) and their autograd backward.
 #pragma once
@@ -32,7 +33,7 @@ inline ConvGeom make_conv_geom(const Geo& g, int Cin, int Cout, int kh, int kw) 
     return c;
 }
 
-inline int act_fmt(int precision) { return precision == 0 ? FMT_F32 : FMT_BF16X2; }
+inline int act_fmt(int precision) { return precision == 0 ? FMT_F32 : (precision == 1 ? FMT_H16X2 : FMT_H16); }
 
 // bytes of the packed-weight record (forward pack + dgrad pack + padded bias)
 size_t packed_weight_bytes(int precision, const ConvGeom& c);
@@ -49,12 +50,15 @@ struct FwdStats {
 };
 int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
                   cudaStream_t s);
-int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
+// dz_absmax (optional, tensor-core back ends): GradScale of dZ (common.cuh) -- dZ holds 2^k * gradient, the result is
+// multiplied by 2^-k
+int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c,
+                    const unsigned* dz_absmax, cudaStream_t s);
 
 size_t wgrad_scratch_bytes(int precision, const ConvGeom& c);
 // dw: torch layout (Cout, Cin, taps), fully overwritten
 int conv_gemm_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,
-                    cudaStream_t s);
+                    const unsigned* dz_absmax, cudaStream_t s);
 
 // --- per-backend entry points -------------------------------------------------------------------
 size_t simt_packed_weight_bytes(const ConvGeom& c);
@@ -73,9 +77,10 @@ int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* 
 int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
            cudaStream_t s);
 int tc_max_ctas();
-int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s);
+int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, const unsigned* dz_absmax,
+             cudaStream_t s);
 size_t tc_wgrad_scratch_bytes(const ConvGeom& c);
 int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,
-             cudaStream_t s);
+             const unsigned* dz_absmax, cudaStream_t s);
 
 }  // namespace fsb

@@ -265,8 +265,10 @@ simt_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dZ, lon
 
 // dw[co][ci][t] = sum_split P[split][t][ci][co]   (fixed order: deterministic).  Threads walk P in its own
 // order (co fastest) so every split plane is read coalesced; the `splits` loads of a thread are independent.
-__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ P, int splits, ConvGeom c, float* dw) {
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ P, int splits, ConvGeom c, float* dw,
+                                                             const unsigned* dz_absmax) {
     const long long plane = (long long)c.ntaps * c.CsIn * c.CsOut;
+    const float unscale = gs_inv_scale(dz_absmax);      // dZ was written with its power-of-two GradScale (common.cuh)
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane;
          i += (long long)gridDim.x * blockDim.x) {
         const int co = (int)(i % c.CsOut);
@@ -277,14 +279,14 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
         float s = 0.f;
 #pragma unroll 8
         for (int sp = 0; sp < splits; ++sp) s += P[sp * plane + i];
-        dw[((long long)co * c.Cin + ci) * c.ntaps + t] = s;
+        dw[((long long)co * c.Cin + ci) * c.ntaps + t] = s * unscale;
     }
 }
 
-int wgrad_finalize(const float* P, int splits, const ConvGeom& c, float* dw, cudaStream_t s) {
+int wgrad_finalize(const float* P, int splits, const ConvGeom& c, float* dw, const unsigned* dz_absmax, cudaStream_t s) {
     long long total = (long long)c.ntaps * c.CsIn * c.CsOut;
     int blocks = (int)((total + 255) / 256 > 2368 ? 2368 : (total + 255) / 256);
-    wgrad_finalize_kernel<<<blocks, 256, 0, s>>>(P, splits, c, dw);
+    wgrad_finalize_kernel<<<blocks, 256, 0, s>>>(P, splits, c, dw, dz_absmax);
     FSB_LAUNCHED();
     return 0;
 }
@@ -299,7 +301,7 @@ int simt_wgrad(const float* A, const float* dZ, float* dw, void* scratch, const 
     dim3 grid((c.CsIn + 63) / 64, (c.CsOut + 63) / 64, c.ntaps * splits);
     simt_wgrad_kernel<<<grid, 256, 0, s>>>(A, dZ, c.rows, c.CsIn, c.CsOut, t, splits, rows_per_split, (float*)scratch);
     FSB_LAUNCHED();
-    return wgrad_finalize((const float*)scratch, splits, c, dw, s);
+    return wgrad_finalize((const float*)scratch, splits, c, dw, nullptr, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -320,16 +322,18 @@ int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, co
     }
     return 0;
 }
-int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s) {
-    return precision == 0 ? simt_dgrad((const float*)dZ, packed, dA, c, s) : tc_dgrad(precision, dZ, packed, dA, c, s);
+int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c,
+                    const unsigned* dz_absmax, cudaStream_t s) {
+    return precision == 0 ? simt_dgrad((const float*)dZ, packed, dA, c, s)
+                          : tc_dgrad(precision, dZ, packed, dA, c, dz_absmax, s);
 }
 size_t wgrad_scratch_bytes(int precision, const ConvGeom& c) {
     return precision == 0 ? simt_wgrad_scratch_bytes(c) : tc_wgrad_scratch_bytes(c);
 }
 int conv_gemm_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,
-                    cudaStream_t s) {
+                    const unsigned* dz_absmax, cudaStream_t s) {
     return precision == 0 ? simt_wgrad((const float*)A, (const float*)dZ, dw, scratch, c, s)
-                          : tc_wgrad(precision, A, dZ, dw, scratch, c, s);
+                          : tc_wgrad(precision, A, dZ, dw, scratch, c, dz_absmax, s);
 }
 
 }  // namespace fsb

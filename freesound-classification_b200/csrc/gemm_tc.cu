@@ -1,10 +1,10 @@
-// tcgen05 / TMEM / TMA back end of the row-shifted GEMM (precision 1 = bf16x3 split, 2 = single bf16).
+// tcgen05 / TMEM / TMA back end of the row-shifted GEMM (precision 1 = three-product split half, 2 = single pass).
 //
 // Every convolution of the network is a sum of row-shifted GEMMs over padded-flat NHWC tensors
-// (gemm.cuh).  Activations arrive as two bf16 planes (hi, lo with x ~= hi + lo, common.cuh); weights are
-// packed once per step into K-major bf16 hi/lo tiles.  Products are formed on the 5th-generation tensor
-// cores as   hi*hi + hi*lo + lo*hi   with float32 accumulation in TMEM (each product keeps ~2^-16
-// relative error), or hi*hi only in precision 2.
+// (gemm.cuh).  Activations arrive as two IEEE-half planes (hi, lo with x ~= hi + lo, common.cuh); weights are
+// packed once per step into K-major half hi/lo tiles.  Products are formed on the 5th-generation tensor
+// cores as   hi*hi + hi*lo + lo*hi   with float32 accumulation in TMEM (each product keeps ~2^-22
+// relative error), or hi*hi only in precision 2 (2^-12 per operand; the backward GEMMs of the mixed mode).
 //
 //   conv_tc_kernel  (forward and dgrad)   D[r, n] = sum_t sum_k A[r + off_t, k] * W_t[n, k]
 //       persistent, warp specialised: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (the whole warp walks
@@ -25,17 +25,20 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
+#include <array>
+#include <map>
+
 #include "gemm.cuh"
 #include "umma_issue.cuh"
 
 namespace fsb {
 
-int wgrad_finalize(const float* P, int splits, const ConvGeom& c, float* dw, cudaStream_t s);
+int wgrad_finalize(const float* P, int splits, const ConvGeom& c, float* dw, const unsigned* dz_absmax, cudaStream_t s);
 
 namespace {
 
 constexpr int BM = 128;            // UMMA M (cta_group::1)
-constexpr int BK = 64;             // channels per smem row: 64 bf16 = 128 bytes = one swizzle span
+constexpr int BK = 64;             // channels per smem row: 64 halves = 128 bytes = one swizzle span
 constexpr int A_HALO = 8;          // extra rows of the A box (row shifts 0..2 used)
 constexpr int TC_THREADS = 192;    // 6 warps
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -352,9 +355,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // pins a value behind every preceding asm volatile (the loads' wait): nothing computed from it can be scheduled earlier
 __device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
 
-// instruction descriptor: D = f32, A = B = bf16, M x N, majors: 0 = K-major, 1 = MN-major
+// instruction descriptor: D = f32 (bit 4), A = B = f16 (format fields [7,10) and [10,13) = 0), M x N, majors: 0 = K-major,
+// 1 = MN-major
 __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -378,7 +382,7 @@ struct ConvTcParams {
     int w_lo_row;          // row offset of the lo plane in the packed weight matrix
     int a_box_rows;        // 128 (tpg == 1) or 136
     int nstages;           // ring depth
-    int planes;            // 2 = bf16x3, 1 = bf16 (hi only)
+    int planes;            // 2 = hi + lo planes (three products), 1 = hi only (single pass)
     int nstg;              // epilogue staging buffers per warp: 2 (double buffered) or 1 (smem is tight)
     int base_off_mode;     // 1: descriptor base_offset = row shift, 0: always 0
     float* Z;
@@ -387,8 +391,7 @@ struct ConvTcParams {
     // optional fused BatchNorm statistics of Z over interior pixels: partials[blockIdx.x][2][ldz] (doubles)
     double* stats;
     const unsigned char* mask;   // interior mask of the output geometry (nullptr = every row is interior)
-    int dbg;                     // timing experiments only (FSB200_TC_DBG): 1 = no TMA store, 2 = no statistics, 4 = no staging,
-                                 // 8 = no MMAs, 16 = no activation loads, 32 = no weight loads
+    const unsigned* out_scale;   // GradScale of the A operand (dgrad): the output is multiplied by its inverse; nullptr = 1
 };
 
 constexpr int EPI_BOX_BYTES = 4096;             // one staged box: 32 rows x 128 bytes; 4 epilogue warps x nstg boxes
@@ -402,10 +405,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t row_bytes = (uint32_t)p.bk * 2u;                 // 128 or 64
     const uint32_t a_box = (uint32_t)p.a_box_rows * row_bytes;      // one plane of one tile
-    const uint32_t a_tile = a_box * 2u;                             // hi + lo
+    const uint32_t a_tile = a_box * (uint32_t)p.planes;             // hi (+ lo)
     const uint32_t a_part = a_tile * (uint32_t)p.T;
     const uint32_t w_plane = (uint32_t)p.BN * row_bytes;
-    const uint32_t w_tap = w_plane * 2u;
+    const uint32_t w_tap = w_plane * (uint32_t)p.planes;
     const uint32_t stage_bytes = a_part + w_tap * (uint32_t)p.tpg;  // multiple of 1 KB
     const uint32_t ring = smem_base;
     const uint32_t epi_stage = (ring + stage_bytes * p.nstages + 1023u) & ~1023u;     // SWIZZLE_128B store boxes
@@ -459,18 +462,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(b_empty + 8u * st, ph ^ 1u);
                         const uint32_t full = b_full + 8u * st;
-                        const uint32_t a_bytes = (p.dbg & 16) ? 0u : a_box * (uint32_t)(p.planes * ntile);
-                        const uint32_t w_bytes = (p.dbg & 32) ? 0u : w_plane * (uint32_t)(p.planes * p.tpg);
-                        if (a_bytes + w_bytes) mbar_expect_tx(full, a_bytes + w_bytes);
-                        else mbar_arrive(full);
+                        mbar_expect_tx(full, a_box * (uint32_t)(p.planes * ntile) + w_plane * (uint32_t)(p.planes * p.tpg));
                         const uint32_t base = ring + stage_bytes * st;
-                        for (int t = 0; t < ntile && a_bytes; ++t) {
+                        for (int t = 0; t < ntile; ++t) {
                             const uint32_t dst = base + a_tile * (uint32_t)t;
                             const int r0 = (mt_first + t) * BM + p.goff[g];
                             tma_load_3d(dst, &tmA, kc * p.bk, r0, 0, full);
                             if (p.planes == 2) tma_load_3d(dst + a_box, &tmA, kc * p.bk, r0, 1, full);
                         }
-                        for (int s = 0; s < p.tpg && w_bytes; ++s) {
+                        for (int s = 0; s < p.tpg; ++s) {
                             const uint32_t wd = base + a_part + w_tap * (uint32_t)s;
                             const int wr = p.wrow[g][s] + nt * p.BN;
                             tma_load_2d(wd, &tmW, kc * p.bk, wr, full);
@@ -512,19 +512,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (umma::elect_one()) {
                         const uint64_t a_hi = ((uint64_t)d_hi << 32) | (d_lo | ((base & 0x3FFFFu) >> 4));
                         const uint64_t b_hi = ((uint64_t)d_hi << 32) | (d_lo | (((base + a_part) & 0x3FFFFu) >> 4));
-                        if (p.dbg & 8) {
-                        } else if (p.planes == 2 && ntile == 1) {
-                            // one row tile per stage (wide N): 6-18 MMAs, the straight-line specialisations issue them
-                            // ~1.4x faster than the predicated block (tools/micro/stage_bench.cu)
-                            umma::umma_stage_x3_fast(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi,
-                                                     w_tap >> 4, w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
-                        } else if (p.planes == 2) {
-                            umma::umma_stage_x3(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
-                                          w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
-                        } else {
-                            umma::umma_stage_x1(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi, w_tap >> 4,
-                                          w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
-                        }
+                        const bool ok = p.planes == 2
+                            ? umma::umma_stage_x3(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi,
+                                                  w_tap >> 4, w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg)
+                            : umma::umma_stage_x1(d_tmem0, (uint32_t)p.BN, a_hi, a_tile >> 4, a_box >> 4, row_bytes >> 4, b_hi,
+                                                  w_tap >> 4, w_plane >> 4, idesc, sidx == 0 ? 0u : 1u, ksteps, ntile, p.tpg);
+                        if (!ok) __trap();               // stage shape without an issue block: host-side planning bug
                         umma_commit(b_empty + 8u * st);
                         if (sidx == last_stage)
                             for (int t = 0; t < ntile; ++t) umma_commit(bT_full + 8u * (set * MAX_T + (uint32_t)t));
@@ -543,6 +536,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t stg0 = epi_stage + (uint32_t)(q * p.nstg) * EPI_BOX_BYTES;
         const unsigned char* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
         double* my_acc = stat_acc + (size_t)q * 2 * p.BN;
+        const float oscale = gs_inv_scale(p.out_scale);
         // per-lane column statistics of this CTA's column tile: compensated float32 sums in registers (a DADD per panel
         // through shared memory was the top stall of the 1x1 layers); [128-column chunk][32-column panel][sum, sum of squares]
         float accS[2][4][2], accC[2][4][2];
@@ -611,7 +605,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (pn * 32 < width) {
                                 const bool wide = width - pn * 32 >= 32;           // 32 or 16 columns
                                 // the staging buffer about to be overwritten was read by the TMA store issued nstg panels ago
-                                if (lane == 0 && !(p.dbg & 1)) {
+                                if (lane == 0) {
                                     if (p.nstg == 2) bulk_wait_read<1>();
                                     else bulk_wait_read<0>();
                                 }
@@ -621,21 +615,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const uint32_t rb = wide ? 128u : 64u;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    if ((wide || j < 4) && !(p.dbg & 4)) {
+                                    if (wide || j < 4) {
                                         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cl0 + 4 * j);
                                         const uint32_t ch = wide ? (uint32_t)((j ^ (lane & 7)) << 4) : (uint32_t)(j << 4);
                                         const float* vv = v + pn * 32 + 4 * j;
-                                        st_shared_v4(stg + (uint32_t)lane * rb + ch, vv[0] + b4.x, vv[1] + b4.y, vv[2] + b4.z,
-                                                     vv[3] + b4.w);
+                                        st_shared_v4(stg + (uint32_t)lane * rb + ch, fmaf(vv[0], oscale, b4.x), fmaf(vv[1], oscale, b4.y),
+                                                     fmaf(vv[2], oscale, b4.z), fmaf(vv[3], oscale, b4.w));
                                     }
                                 }
                                 fence_async_smem();
                                 __syncwarp();
-                                if (lane == 0 && m0 + q * 32 < p.rows && !(p.dbg & 1)) {
+                                if (lane == 0 && m0 + q * 32 < p.rows) {
                                     tma_store_2d(wide ? &tmZ32 : &tmZ16, stg, nt * p.BN + cl0, (int)m0 + q * 32);
                                     bulk_commit();
                                 }
-                                if (p.stats && (wide || lane < 16) && !(p.dbg & 2)) {
+                                if (p.stats && (wide || lane < 16)) {
                                     // lane l sums column cl0 + l over this warp's interior rows, straight from the staged box
                                     const uint32_t bits = ibits[t];
                                     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains
@@ -734,7 +728,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
     const int cz = p.swap ? p.bn : 128, ca = p.swap ? 128 : p.bn;
     const uint32_t nbz = (uint32_t)(cz + 63) / 64u, nba = (uint32_t)(ca + 63) / 64u;
     const uint32_t dz_plane = nbz * dz_box, a_plane = nba * a_box;
-    const uint32_t stage_bytes = (dz_plane + a_plane) * 2u;   // hi + lo (lo unused when planes == 1)
+    const uint32_t stage_bytes = (dz_plane + a_plane) * (uint32_t)p.planes;   // [dZ hi (, lo)][A hi (, lo)]
     const uint32_t ring = smem_base;
     const uint32_t bars = ring + stage_bytes * p.nstages;
     const uint32_t b_full = bars, b_empty = b_full + 8u * p.nstages, b_done = b_empty + 8u * p.nstages;
@@ -779,7 +773,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
                 const uint32_t base = ring + stage_bytes * st;
                 for (int pl = 0; pl < p.planes; ++pl) {
                     const uint32_t dzd = base + pl * dz_plane;
-                    const uint32_t ad = base + 2u * dz_plane + pl * a_plane;
+                    const uint32_t ad = base + (uint32_t)p.planes * dz_plane + pl * a_plane;
                     for (uint32_t b = 0; b < nbz; ++b) tma_load_3d(dzd + b * dz_box, &tmDZ, co0 + 64 * (int)b, r, pl, b_full + 8u * st);
                     for (uint32_t b = 0; b < nba; ++b) tma_load_3d(ad + b * a_box, &tmA, ci0 + 64 * (int)b, r + p.goff[g], pl, b_full + 8u * st);
                 }
@@ -798,7 +792,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
             tc_fence_after();
             const uint32_t base = ring + stage_bytes * st;
             const uint32_t z_hi = base, z_lo = base + dz_plane;
-            const uint32_t a_hi = base + 2u * dz_plane, a_lo = a_hi + a_plane;
+            const uint32_t a_hi = base + (uint32_t)p.planes * dz_plane, a_lo = a_hi + a_plane;
             if (umma::elect_one()) {
                 const uint64_t dzh = ((uint64_t)hi_word << 32) | (lbo_z | ((z_hi & 0x3FFFFu) >> 4));
                 const uint64_t dzl = ((uint64_t)hi_word << 32) | (lbo_z | ((z_lo & 0x3FFFFu) >> 4));
@@ -866,7 +860,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: torch (Cout, Cin, taps) float32 -> bf16 hi/lo K-major tiles for forward and dgrad
+// weight packing: torch (Cout, Cin, taps) float32 -> half hi/lo K-major tiles for forward and dgrad
 // ---------------------------------------------------------------------------------------------
 struct TcPackLayout {
     int bn_f, nt_f, npad_f, kpad_f;      // forward : N = Cout, K = Cin
@@ -896,7 +890,7 @@ TcPackLayout pack_layout(const ConvGeom& c) {
 }
 
 __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, ConvGeom c, TcPackLayout L,
-                               __nv_bfloat16* fwd, __nv_bfloat16* dgr, float* pb) {
+                               __half* fwd, __half* dgr, float* pb) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     for (long long i = i0; i < (long long)L.fwd_elems; i += stride) {
@@ -905,8 +899,8 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restr
         int n = (int)(u % L.npad_f);
         int t = (int)(u / L.npad_f);
         float v = (n < c.Cout && k < c.Cin) ? w[((long long)n * c.Cin + k) * c.ntaps + t] : 0.f;
-        __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
+        __half hi, lo;
+        split_h16(v, hi, lo);
         fwd[i] = hi;
         fwd[L.fwd_elems + i] = lo;
     }
@@ -916,8 +910,8 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restr
         int n = (int)(u % L.npad_d);           // input channel
         int t = (int)(u / L.npad_d);
         float v = (k < c.Cout && n < c.Cin) ? w[((long long)k * c.Cin + n) * c.ntaps + t] : 0.f;
-        __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
+        __half hi, lo;
+        split_h16(v, hi, lo);
         dgr[i] = hi;
         dgr[L.dgr_elems + i] = lo;
     }
@@ -939,7 +933,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     return fn;
 }
 
-// activation planes: (C, rows, 2 planes) bf16, box (64, box_rows, 1)
+// activation planes: (C, rows, 2 planes) half, box (64, box_rows, 1)
 int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int box_rows, int bk = BK) {
     auto fn = encode_fn();
     if (!fn) {
@@ -950,7 +944,7 @@ int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int b
     cuuint64_t strides[2] = {(cuuint64_t)Cs * 2, (cuuint64_t)rows * Cs * 2};
     cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -961,7 +955,7 @@ int make_act_map(CUtensorMap* m, const void* base, long long rows, int Cs, int b
     return 0;
 }
 
-// packed weights: (Kpad, total_rows) bf16, box (64, box_rows)
+// packed weights: (Kpad, total_rows) half, box (64, box_rows)
 int make_w_map(CUtensorMap* m, const void* base, long long total_rows, int kpad, int box_rows, int bk = BK) {
     auto fn = encode_fn();
     if (!fn) {
@@ -972,7 +966,7 @@ int make_w_map(CUtensorMap* m, const void* base, long long total_rows, int kpad,
     cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
     cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1004,22 +998,27 @@ int make_out_map(CUtensorMap* m, const float* base, long long rows, int ldz, int
     return 0;
 }
 
-int tc_env(const char* name) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : 0;
-}
-
-int tc_mode() {
-    // debugging switches: bit 0 = one TMA box per tap (no dx sharing), bit 1 = set the descriptor base_offset to
-    // the row shift (measured on B200: the swizzle is a function of the absolute smem address, so a
-    // 128-byte-shifted start address needs base_offset 0; base_offset = shift gives wrong results)
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("FSB200_TC_MODE");
-        mode = e ? atoi(e) : 0;
+// FSB200_* tuning switches, read once per process
+struct TcEnv {
+    int mode;      // FSB200_TC_MODE: bit 0 = one TMA box per tap (no dx sharing), bit 1 = descriptor base_offset = row
+                   // shift (measured on B200: the swizzle is a function of the absolute smem address, so a
+                   // 128-byte-shifted start address needs base_offset 0; base_offset = shift gives wrong results)
+    int t1;        // FSB200_TC_T=1: one row tile per group
+    int bk32;      // FSB200_TC_BK=32: 32-channel stages
+    int wg_swap;   // FSB200_WG_SWAP: 1 / 2 force the wgrad operand orientation
+};
+const TcEnv& tc_env() {
+    static TcEnv e = {-1, 0, 0, 0};
+    if (e.mode < 0) {
+        auto rd = [](const char* n) { const char* v = getenv(n); return v ? atoi(v) : 0; };
+        e.t1 = rd("FSB200_TC_T") == 1;
+        e.bk32 = rd("FSB200_TC_BK") == 32;
+        e.wg_swap = rd("FSB200_WG_SWAP");
+        e.mode = rd("FSB200_TC_MODE");
     }
-    return mode;
+    return e;
 }
+int tc_mode() { return tc_env().mode; }
 
 int num_sms() {
     static int n = 0;
@@ -1056,10 +1055,35 @@ void group_taps(const ConvGeom& c, int sign, bool share, int& ngroups, int& tpg,
     }
 }
 
-int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
-                   const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
-                   const FwdStats* st, cudaStream_t s) {
+// One planned launch (kernel parameters + the four tensor maps); planning costs a few microseconds of host time per
+// launch (four cuTensorMapEncodeTiled calls), so plans are cached per (operand pointers, shape): the workspace of a
+// bound network is stable across steps and every step replays the same ~60 entries.
+struct ConvLaunch {
     ConvTcParams p;
+    CUtensorMap tmA, tmW, tmZ32, tmZ16;
+    int grid;
+    size_t smem;
+};
+typedef std::array<uint64_t, 16> LaunchKey;
+
+template <typename V>
+struct LaunchCache {
+    std::map<LaunchKey, V> map;
+    V* find(const LaunchKey& k) {
+        auto it = map.find(k);
+        return it == map.end() ? nullptr : &it->second;
+    }
+    V* insert(const LaunchKey& k, const V& v) {
+        if (map.size() > 8192) map.clear();          // variable-length batches: bounded growth
+        return &map.emplace(k, v).first->second;
+    }
+};
+LaunchCache<ConvLaunch> g_conv_cache;
+
+int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
+                 const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
+                 const FwdStats* st, const unsigned* out_scale) {
+    ConvTcParams& p = L.p;
     memset(&p, 0, sizeof(p));
     p.rows = rows;
     p.m_tiles = (int)((rows + BM - 1) / BM);
@@ -1072,6 +1096,7 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     p.Z = Z;
     p.ldz = ldz;
     p.bias = bias;
+    p.out_scale = out_scale;
     if (st) {
         const Geo& g = *st->g;
         FSB_REQUIRE(g.rows == rows && g.Cs == ldz, "conv_tc: statistics geometry does not match the output");
@@ -1083,7 +1108,7 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     // one; never more tiles per group than needed to give every CTA a group.
     const int ctas_per_col = num_sms() / p.n_tiles;
     int T = 4 * bn <= 512 ? 2 : 1;
-    if (tc_env("FSB200_TC_T") == 1) T = 1;
+    if (tc_env().t1) T = 1;
     while (T > 1 && (p.m_tiles + T - 1) / T < ctas_per_col) --T;
     const int nbuf = 2 * T * bn <= 512 ? 2 : 1;
     const size_t fixed0 = 1024 /*align*/ + 1024 /*staging align*/ + 256 /*barriers*/ +
@@ -1103,8 +1128,8 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
         // drain: the 1x1 layers ran at half speed), then the wider stage
         for (int nstg = 2; nstg >= 1 && !ok; --nstg) {
             fixed = fixed0 + (size_t)4 * nstg * EPI_BOX_BYTES;
-            for (int bk = (tc_env("FSB200_TC_BK") == 32 ? 32 : 64); bk >= 32 && !ok; bk -= 32) {
-                stage = ((size_t)p.a_box_rows * T + (size_t)bn * p.tpg) * bk * 2 * 2;
+            for (int bk = (tc_env().bk32 ? 32 : 64); bk >= 32 && !ok; bk -= 32) {
+                stage = ((size_t)p.a_box_rows * T + (size_t)bn * p.tpg) * bk * 2 * p.planes;
                 const int need = bk == 64 ? 3 : 2;
                 if (fixed + need * stage <= SMEM_LIMIT) { p.bk = bk; p.nstg = nstg; ok = true; }
             }
@@ -1113,26 +1138,43 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     FSB_REQUIRE(ok, "conv_tc: tile does not fit in shared memory (BN=%d)", bn);
     p.T = T;
     p.nbuf = nbuf;
-    p.dbg = tc_env("FSB200_TC_DBG");
     p.nstages = (int)((SMEM_LIMIT - fixed) / stage);
     if (p.nstages > 8) p.nstages = 8;
-    const size_t smem = fixed + stage * p.nstages;
-    CUtensorMap tmA, tmW, tmZ32, tmZ16;
-    FSB_TRY(make_act_map(&tmA, A, rows, K, p.a_box_rows, p.bk));
-    FSB_TRY(make_w_map(&tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn, p.bk));
-    FSB_TRY(make_out_map(&tmZ32, Z, rows, ldz, 32, true));
-    FSB_TRY(make_out_map(&tmZ16, Z, rows, ldz, 16, false));
+    L.smem = fixed + stage * p.nstages;
+    FSB_TRY(make_act_map(&L.tmA, A, rows, K, p.a_box_rows, p.bk));
+    FSB_TRY(make_w_map(&L.tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn, p.bk));
+    FSB_TRY(make_out_map(&L.tmZ32, Z, rows, ldz, 32, true));
+    FSB_TRY(make_out_map(&L.tmZ16, Z, rows, ldz, 16, false));
+    // every CTA owns one column tile: the grid is a multiple of n_tiles
+    const int n_groups = (p.m_tiles + T - 1) / T;
+    L.grid = (n_groups < ctas_per_col ? n_groups : ctas_per_col) * p.n_tiles;
+    return 0;
+}
+
+int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
+                   const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
+                   const FwdStats* st, const unsigned* out_scale, cudaStream_t s) {
+    const LaunchKey key = {(uint64_t)(uintptr_t)A, (uint64_t)(uintptr_t)wpacked, (uint64_t)(uintptr_t)Z, (uint64_t)rows,
+                           (uint64_t)(uintptr_t)bias, (uint64_t)(uintptr_t)(st ? st->partials : nullptr),
+                           (uint64_t)(uintptr_t)(st ? st->g->mask : nullptr), (uint64_t)(uintptr_t)out_scale,
+                           ((uint64_t)(uint32_t)K << 32) | (uint32_t)ldz, ((uint64_t)(uint32_t)bn << 32) | (uint32_t)nt,
+                           ((uint64_t)(uint32_t)w_kpad << 32) | (uint32_t)w_npad,
+                           ((uint64_t)(uint32_t)precision << 32) | (uint32_t)(sign + 1),
+                           ((uint64_t)(uint32_t)c.ntaps << 32) | (uint32_t)c.offs[0], (uint64_t)(uint32_t)c.offs[1], 0, 0};
+    ConvLaunch* L = g_conv_cache.find(key);
+    if (!L) {
+        ConvLaunch fresh;
+        FSB_TRY(plan_conv_tc(fresh, precision, A, wpacked, w_kpad, w_npad, bn, nt, bias, Z, rows, K, ldz, c, sign, st, out_scale));
+        L = g_conv_cache.insert(key, fresh);
+    }
     static bool attr_set = false;
     if (!attr_set) {
         FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    // every CTA owns one column tile: the grid is a multiple of n_tiles
-    const int n_groups = (p.m_tiles + T - 1) / T;
-    int grid = (n_groups < ctas_per_col ? n_groups : ctas_per_col) * p.n_tiles;
-    conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmW, tmZ32, tmZ16, p);
+    conv_tc_kernel<<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
     FSB_LAUNCHED();
-    if (st) *st->nblk = grid;
+    if (st) *st->nblk = L->grid;
     return 0;
 }
 
@@ -1150,8 +1192,8 @@ int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* 
     char* base = tc_pack_base(packed);
     size_t total = L.fwd_elems > L.dgr_elems ? L.fwd_elems : L.dgr_elems;
     int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
-    tc_pack_kernel<<<blocks, 256, 0, s>>>(w, bias, c, L, (__nv_bfloat16*)(base + L.off_fwd),
-                                          (__nv_bfloat16*)(base + L.off_dgr), (float*)(base + L.off_bias));
+    tc_pack_kernel<<<blocks, 256, 0, s>>>(w, bias, c, L, (__half*)(base + L.off_fwd), (__half*)(base + L.off_dgr),
+                                          (float*)(base + L.off_bias));
     FSB_LAUNCHED();
     return 0;
 }
@@ -1163,14 +1205,15 @@ int tc_fwd(int precision, const void* A, const void* packed, float* Z, const Con
     TcPackLayout L = pack_layout(c);
     const char* base = tc_pack_base(packed);
     return launch_conv_tc(precision, A, base + L.off_fwd, L.kpad_f, L.npad_f, L.bn_f, L.nt_f,
-                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, st, s);
+                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, st, nullptr, s);
 }
 
-int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, cudaStream_t s) {
+int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, const unsigned* dz_absmax,
+             cudaStream_t s) {
     TcPackLayout L = pack_layout(c);
     const char* base = tc_pack_base(packed);
     return launch_conv_tc(precision, dZ, base + L.off_dgr, L.kpad_d, L.npad_d, L.bn_d, L.nt_d, nullptr, dA, c.rows,
-                          c.CsOut, c.CsIn, c, -1, nullptr, s);
+                          c.CsOut, c.CsIn, c, -1, nullptr, dz_absmax, s);
 }
 
 struct WgradShape {
@@ -1198,8 +1241,8 @@ static WgradShape wgrad_shape(const ConvGeom& c) {
         cost[sw] = (long long)mt[sw] * nt[sw] * (bn[sw] > 88 ? bn[sw] : 88);
     }
     w.swap = cost[1] < cost[0] ? 1 : 0;
-    if (tc_env("FSB200_WG_SWAP") == 1) w.swap = 0;
-    if (tc_env("FSB200_WG_SWAP") == 2) w.swap = 1;
+    if (tc_env().wg_swap == 1) w.swap = 0;
+    if (tc_env().wg_swap == 2) w.swap = 1;
     w.m_tiles = mt[w.swap]; w.n_tiles = nt[w.swap]; w.bn = bn[w.swap];
     const int items = w.ngroups * w.m_tiles * w.n_tiles;
     long long chunks = (c.rows + WG_R - 1) / WG_R;
@@ -1216,8 +1259,17 @@ size_t tc_wgrad_scratch_bytes(const ConvGeom& c) {
     return (size_t)wgrad_shape(c).splits * c.ntaps * c.CsIn * c.CsOut * sizeof(float);
 }
 
-int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c, cudaStream_t s) {
+namespace {
+struct WgradLaunch {
     WgradTcParams p;
+    CUtensorMap tmDZ, tmA;
+    int grid;
+    size_t smem;
+};
+LaunchCache<WgradLaunch> g_wgrad_cache;
+
+int plan_wgrad_tc(WgradLaunch& L, int precision, const void* A, const void* dZ, void* scratch, const ConvGeom& c) {
+    WgradTcParams& p = L.p;
     memset(&p, 0, sizeof(p));
     const WgradShape w = wgrad_shape(c);
     group_taps(c, +1, !(tc_mode() & 1), p.ngroups, p.tpg, p.goff, p.tap_of);
@@ -1230,23 +1282,38 @@ int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scra
     p.planes = precision == 1 ? 2 : 1;
     p.P = (float*)scratch;
     const int cz = p.swap ? p.bn : 128, ca = p.swap ? 128 : p.bn;
-    const size_t stage = (size_t)(((cz + 63) / 64) * WG_R * 128 + ((ca + 63) / 64) * (WG_R + A_HALO) * 128) * 2;
+    const size_t stage = (size_t)(((cz + 63) / 64) * WG_R * 128 + ((ca + 63) / 64) * (WG_R + A_HALO) * 128) * p.planes;
     p.nstages = (int)((SMEM_LIMIT - 1024 - 256) / stage);
-    if (p.nstages > 4) p.nstages = 4;
+    if (p.nstages > 6) p.nstages = 6;
     FSB_REQUIRE(p.nstages >= 2 && p.tpg * p.bn <= 512, "wgrad_tc: tile does not fit (bn=%d)", p.bn);
-    const size_t smem = 1024 + 256 + stage * p.nstages;
-    CUtensorMap tmDZ, tmA;
-    FSB_TRY(make_act_map(&tmDZ, dZ, c.rows, c.CsOut, WG_R));
-    FSB_TRY(make_act_map(&tmA, A, c.rows, c.CsIn, WG_R + A_HALO));
+    L.smem = 1024 + 256 + stage * p.nstages;
+    FSB_TRY(make_act_map(&L.tmDZ, dZ, c.rows, c.CsOut, WG_R));
+    FSB_TRY(make_act_map(&L.tmA, A, c.rows, c.CsIn, WG_R + A_HALO));
+    L.grid = p.ngroups * p.m_tiles * p.n_tiles * p.splits;
+    return 0;
+}
+}  // namespace
+
+int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,
+             const unsigned* dz_absmax, cudaStream_t s) {
+    const LaunchKey key = {(uint64_t)(uintptr_t)A, (uint64_t)(uintptr_t)dZ, (uint64_t)(uintptr_t)scratch, (uint64_t)c.rows,
+                           ((uint64_t)(uint32_t)c.CsIn << 32) | (uint32_t)c.CsOut,
+                           ((uint64_t)(uint32_t)c.ntaps << 32) | (uint32_t)c.offs[0], (uint64_t)(uint32_t)c.offs[1],
+                           (uint64_t)(uint32_t)precision, 0, 0, 0, 0, 0, 0, 0, 0};
+    WgradLaunch* L = g_wgrad_cache.find(key);
+    if (!L) {
+        WgradLaunch fresh;
+        FSB_TRY(plan_wgrad_tc(fresh, precision, A, dZ, scratch, c));
+        L = g_wgrad_cache.insert(key, fresh);
+    }
     static bool attr_set = false;
     if (!attr_set) {
         FSB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    const int grid = p.ngroups * p.m_tiles * p.n_tiles * p.splits;
-    wgrad_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmDZ, tmA, p);
+    wgrad_tc_kernel<<<L->grid, TC_THREADS, L->smem, s>>>(L->tmDZ, L->tmA, L->p);
     FSB_LAUNCHED();
-    return wgrad_finalize((const float*)scratch, p.splits, c, dw, s);
+    return wgrad_finalize((const float*)scratch, L->p.splits, c, dw, dz_absmax, s);
 }
 
 }  // namespace fsb

@@ -88,6 +88,7 @@ struct fsb_net {
     size_t ws_bytes = 0;
     int N = 0, T = 0, training = 0, frames = 0;
     bool tables_ready = false, fwd_done = false;
+    bool overlap = true;        // side-stream overlap of weight packing / weight-gradient GEMMs (fsb_net_set_overlap)
     unsigned long long dropout_seed = 0;
 
     // carved buffers
@@ -111,6 +112,10 @@ struct fsb_net {
     size_t fork_used = 0;
     cudaEvent_t join_event = nullptr, pack_event = nullptr;
     void* conv0_scratch = nullptr;
+    unsigned* gscale = nullptr;     // [num_blocks][B_PER_BLOCK] GradScale slots (common.cuh), zeroed at the start of backward
+
+    // precision of the forward / backward GEMMs (cfg.precision 3 = mixed: three-product forward, single-pass backward)
+    int prec_f = 0, prec_b = 0;
 
     // profiling
     bool profiling = false;
@@ -159,12 +164,12 @@ void carve_bn(Bump& b, BnBuf& bn, int C) {
     bn.c2 = b.take<float>(bn.Cs);
 }
 
-size_t plane_bytes(const Geo& g) { return (size_t)g.rows * g.Cs * 4; }   // f32 plane == 2 bf16 planes
+size_t plane_bytes(const Geo& g) { return (size_t)g.rows * g.Cs * 4; }   // f32 plane == hi + lo half planes
 
 // Carves every buffer for (N, T); with base == nullptr this is the size query.
 size_t carve(fsb_net* net, char* base, int N, int T, int training) {
     const fsb_net_config& c = net->cfg;
-    const int prec = c.precision;
+    const int prec = net->prec_f;            // packed-weight / scratch sizes do not depend on the number of products
     Bump b{base, 0};
     int frames = 1 + T / c.hop;
     net->frames = frames;
@@ -256,8 +261,8 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
             max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c1));
             max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c2));
         }
-        max_partials = std::max(max_partials, (size_t)ew_num_blocks(B.g_in) * 3 * B.g_in.Cs);
-        max_partials = std::max(max_partials, (size_t)ew_num_blocks(B.g) * 3 * B.g.Cs);
+        max_partials = std::max(max_partials, (size_t)ew_num_blocks(B.g_in) * 5 * B.g_in.Cs);
+        max_partials = std::max(max_partials, (size_t)ew_num_blocks(B.g) * 5 * B.g.Cs);
         Hin = H; Win = W;
     }
     // head
@@ -285,11 +290,12 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
         max_wgrad = std::max(max_wgrad, simt_wgrad_scratch_bytes(net->lin1));
         max_wgrad = std::max(max_wgrad, simt_wgrad_scratch_bytes(net->lin5));
     }
-    max_partials = std::max(max_partials, (size_t)ew_num_blocks(net->g_head) * 3 * net->g_head.Cs);
+    max_partials = std::max(max_partials, (size_t)ew_num_blocks(net->g_head) * 5 * net->g_head.Cs);
     for (int k = 0; k < c.num_blocks; ++k)
         max_partials = std::max(max_partials, (size_t)256 * 2 * net->blocks[k].g.Cs);   // one record per GEMM CTA
     net->partials = b.take<double>(max_partials);
     net->wgrad_scratch = b.take_bytes(max_wgrad + 256);
+    net->gscale = b.take<unsigned>((size_t)c.num_blocks * B_PER_BLOCK);
     return align_up(b.off, 256);
 }
 
@@ -356,12 +362,14 @@ extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, c
                               const int* fb_start, const int* fb_len, int fb_nnz, fsb_net** out) {
     FSB_REQUIRE(cfg && out, "net_create: null argument");
     FSB_REQUIRE(cfg->num_blocks >= 1 && cfg->num_blocks <= FSB_MAX_BLOCKS, "net_create: num_blocks out of range");
-    FSB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, "net_create: precision must be 0, 1 or 2");
+    FSB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 3, "net_create: precision must be 0 (fp32), 1 (fp16x3), 2 (fp16) or 3 (mixed)");
     FSB_REQUIRE(cfg->feat_mode == 1 || cfg->feat_mode == 2, "net_create: feat_mode must be 1 (stft) or 2 (mel)");
     FSB_REQUIRE(cfg->start_deep_supervision_on < cfg->num_blocks, "net_create: no deep-supervision head");
     FSB_REQUIRE(cfg->dropout_p >= 0.f && cfg->dropout_p < 1.f, "net_create: dropout must be in [0, 1)");
     fsb_net* net = new fsb_net();
     net->cfg = *cfg;
+    net->prec_f = cfg->precision == 3 ? 1 : cfg->precision;
+    net->prec_b = cfg->precision == 3 ? 2 : cfg->precision;
     if (cfg->feat_mode == 2) {
         FSB_REQUIRE(fb_vals && fb_off && fb_start && fb_len && fb_nnz > 0, "net_create: mel mode needs a filterbank");
         int n_mel = cfg->n_features;
@@ -375,6 +383,7 @@ extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, c
     net->Ds = round_up(net->D, 16);
     net->CsCls = round_up(cfg->n_classes, 16);
     build_param_table(net);
+    net->overlap = getenv("FSB200_NO_OVERLAP") == nullptr;      // read once; fsb_net_set_overlap changes it later
     *out = net;
     return 0;
 }
@@ -468,7 +477,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
     FSB_TRY(fsb_device_ok());
     FSB_TRY(bind(net, workspace, workspace_bytes, n, t, training ? 1 : 0, s));
     const fsb_net_config& c = net->cfg;
-    const int prec = c.precision, fmt = act_fmt(prec);
+    const int prec = net->prec_f, fmt = act_fmt(prec);
     net->recs.clear();
     net->ev_used = 0;
     net->dropout_seed = dropout_seed;
@@ -479,7 +488,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
     // in the shadow of the feature kernel and the block-0 entry conv; the first GEMM waits for it.
     FSB_TRY(ensure_side_stream(net));
     {
-        const bool overlap = getenv("FSB200_NO_OVERLAP") == nullptr;
+        const bool overlap = net->overlap;
         cudaStream_t ps = overlap ? net->side : s;
         if (overlap) {
             FSB_CUDA(cudaEventRecord(net->pack_event, s));        // orders the packs after the caller's earlier work (optimizer step)
@@ -500,7 +509,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
         }
         if (overlap) FSB_CUDA(cudaEventRecord(net->pack_event, net->side));
     }
-    bool packs_joined = getenv("FSB200_NO_OVERLAP") != nullptr;
+    bool packs_joined = !net->overlap;
     auto join_packs = [&]() -> int {
         if (!packs_joined) {
             FSB_CUDA(cudaStreamWaitEvent(s, net->pack_event, 0));
@@ -620,14 +629,16 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
 }
 
 // =================================================================================================
+// absmax (optional): GradScale slot of the gradient tensor this BatchNorm emits (half-precision planes are written
+// with its power-of-two scale; float32 outputs ignore it but the slot is still filled for a later converter)
 static int bn_backward(fsb_net* net, cudaStream_t s, const float* dA1, const float* dA2, const float* z, const Geo& g,
                        BnBuf& bn, const float* slope, Residual res, Dropout dr, float* dgamma, float* dbeta,
-                       float* dslope, void* dz, int fmt, float* dres, int cat) {
+                       float* dslope, void* dz, int fmt, float* dres, unsigned* absmax, int cat) {
     BnCoef coef = bn.coef(slope);
     RUN(cat, 0, bn_act_bwd_reduce(dA1, dA2, z, g, coef, res, dr, net->partials, s));
-    RUN(cat, 0, bn_bwd_finalize(net->partials, ew_num_blocks(g), g.pixels, bn.C, bn.Cs, dgamma, dbeta, dslope, bn.c1,
-                                bn.c2, s));
-    if (dz) RUN(cat, 0, bn_act_bwd_apply(dA1, dA2, z, g, coef, res, dr, bn.c1, bn.c2, dz, fmt, dres, s));
+    RUN(cat, 0, bn_bwd_finalize(net->partials, ew_num_blocks(g), g.pixels, bn.C, bn.Cs, bn.scale, dgamma, dbeta, dslope,
+                                bn.c1, bn.c2, absmax, s));
+    if (dz) RUN(cat, 0, bn_act_bwd_apply(dA1, dA2, z, g, coef, res, dr, bn.c1, bn.c2, dz, fmt, dres, absmax, s));
     return 0;
 }
 
@@ -640,13 +651,22 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
     }
     cudaStream_t s = (cudaStream_t)stream;
     const fsb_net_config& c = net->cfg;
-    const int prec = c.precision, fmt = act_fmt(prec);
+    // gradient planes carry hi + lo only when the backward GEMMs form three products; the forward activations read by
+    // the weight-gradient GEMMs always have their hi plane
+    const int prec = net->prec_b, fmt = act_fmt(prec);
+    // Entry-conv dgrad of the 1D model keeps three products even in the mixed mode.  Its output du feeds a BatchNorm
+    // WITHOUT activation, whose d(beta) = sum_r du[r] telescopes to border terms only (sum_r dz = 0 after the
+    // BatchNorm above), while the half rounding errors of dz accumulate over ALL rows: relative error
+    // ~2^-12 sqrt(rows / border rows) = 2^-12 sqrt(W / 2) in 1D (4e-2 measured at W = 3446), but only
+    // 2^-12 sqrt(HW / 2(H + W)) <= 2^-12 * 5.7 in 2D.
+    const int prec_e = (!c.two_d && prec == 2) ? 1 : prec, fmt_e = act_fmt(prec_e);
     const int n = net->N;
     auto G = [&](int index) { return grads + net->param_offset[index]; };
     // conv / linear biases that feed a batch-statistics BN have an analytically zero gradient
     FSB_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->total_params * sizeof(float), s));
+    FSB_CUDA(cudaMemsetAsync(net->gscale, 0, (size_t)c.num_blocks * B_PER_BLOCK * sizeof(unsigned), s));
     FSB_TRY(ensure_side_stream(net));
-    const bool overlap = getenv("FSB200_NO_OVERLAP") == nullptr;
+    const bool overlap = net->overlap;
     cudaStream_t ws = overlap ? net->side : s;       // stream of the weight-gradient GEMMs
     net->fork_used = 0;
     // everything enqueued on `s` so far is visible to the side stream from here on
@@ -673,11 +693,11 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
         RUN(CAT_HEAD, 0, simt_skinny_dgrad(net->dzl, net->pk_l5, net->dh1, net->lin5, net->head_scratch, s));
         Dropout dr = {c.dropout_p, net->dropout_seed};
         FSB_TRY(bn_backward(net, s, net->dh1, nullptr, net->z1h, net->g_head, net->hbn2, P[H_PRELU], kNoRes, dr,
-                            G(hb + H_BN2_W), G(hb + H_BN2_B), G(hb + H_PRELU), net->dz1h, FMT_F32, nullptr, CAT_HEAD));
+                            G(hb + H_BN2_W), G(hb + H_BN2_B), G(hb + H_PRELU), net->dz1h, FMT_F32, nullptr, nullptr, CAT_HEAD));
         RUN(CAT_HEAD, 0, simt_wgrad(net->h0, net->dz1h, G(hb + H_L1_W), net->wgrad_scratch, net->lin1, s));
         RUN(CAT_HEAD, 0, simt_skinny_dgrad(net->dz1h, net->pk_l1, net->dh0, net->lin1, net->head_scratch, s));
         FSB_TRY(bn_backward(net, s, net->dh0, nullptr, net->feats, net->g_head, net->hbn0, nullptr, kNoRes, kNoDrop,
-                            G(hb + H_BN0_W), G(hb + H_BN0_B), nullptr, net->dfeats, FMT_F32, nullptr, CAT_HEAD));
+                            G(hb + H_BN0_W), G(hb + H_BN0_B), nullptr, net->dfeats, FMT_F32, nullptr, nullptr, CAT_HEAD));
     }
 
     // ---- conv blocks, last to first
@@ -685,46 +705,47 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
         BlockPlan& B = net->blocks[k];
         const int pb = k * P_PER_BLOCK;
         const float* const* P = params + pb;
+        unsigned* const GS = net->gscale + (size_t)k * B_PER_BLOCK;     // GradScale slots of dz3 / dz2 / dz1 / dzp (-> dzf)
         if (k == c.num_blocks - 1) FSB_CUDA(cudaMemsetAsync(B.d_out, 0, (size_t)B.g.rows * B.g.Cs * 4, s));
         if (B.head_off >= 0)
             RUN(CAT_ELT_BWD, 0, gmax_backward(net->dfeats, net->Ds, B.head_off, B.argrow, B.g, B.d_out, s));
         // out = prelu3(bn3(z3) + r0)
         Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
         FSB_TRY(bn_backward(net, s, B.d_out, nullptr, B.z3, B.g, B.bn3, P[P_PRELU3], res, kNoDrop, G(pb + P_BN3_W),
-                            G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, CAT_ELT_BWD));
+                            G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, GS + B_3, CAT_ELT_BWD));
         FSB_TRY(fork());
         RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c3, B.g),
-              conv_gemm_wgrad(prec, B.a2, B.dz3, G(pb + P_C3_W), net->wgrad_scratch, B.c3, ws));
-        RUN(CAT_GEMM_DGRAD, conv_flops(B.c3, B.g), conv_gemm_dgrad(prec, B.dz3, B.pk3, B.da2, B.c3, s));
+              conv_gemm_wgrad(prec, B.a2, B.dz3, G(pb + P_C3_W), net->wgrad_scratch, B.c3, GS + B_3, ws));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c3, B.g), conv_gemm_dgrad(prec, B.dz3, B.pk3, B.da2, B.c3, GS + B_3, s));
         FSB_TRY(bn_backward(net, s, B.da2, nullptr, B.z2, B.g, B.bn2, P[P_PRELU2], kNoRes, kNoDrop, G(pb + P_BN2_W),
-                            G(pb + P_BN2_B), G(pb + P_PRELU2), B.dz2, fmt, nullptr, CAT_ELT_BWD));
+                            G(pb + P_BN2_B), G(pb + P_PRELU2), B.dz2, fmt, nullptr, GS + B_2, CAT_ELT_BWD));
         FSB_TRY(fork());
         RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c2, B.g),
-              conv_gemm_wgrad(prec, B.a1, B.dz2, G(pb + P_C2_W), net->wgrad_scratch, B.c2, ws));
-        RUN(CAT_GEMM_DGRAD, conv_flops(B.c2, B.g), conv_gemm_dgrad(prec, B.dz2, B.pk2, B.da1, B.c2, s));
+              conv_gemm_wgrad(prec, B.a1, B.dz2, G(pb + P_C2_W), net->wgrad_scratch, B.c2, GS + B_2, ws));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c2, B.g), conv_gemm_dgrad(prec, B.dz2, B.pk2, B.da1, B.c2, GS + B_2, s));
         FSB_TRY(bn_backward(net, s, B.da1, nullptr, B.z1, B.g, B.bn1, P[P_PRELU1], kNoRes, kNoDrop, G(pb + P_BN1_W),
-                            G(pb + P_BN1_B), G(pb + P_PRELU1), B.dz1, fmt, nullptr, CAT_ELT_BWD));
+                            G(pb + P_BN1_B), G(pb + P_PRELU1), B.dz1, fmt, nullptr, GS + B_1, CAT_ELT_BWD));
         FSB_TRY(fork());
         RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c1, B.g),
-              conv_gemm_wgrad(prec, B.r0, B.dz1, G(pb + P_C1_W), net->wgrad_scratch, B.c1, ws));
-        RUN(CAT_GEMM_DGRAD, conv_flops(B.c1, B.g), conv_gemm_dgrad(prec, B.dz1, B.pk1, B.dr0a, B.c1, s));
+              conv_gemm_wgrad(prec, B.r0, B.dz1, G(pb + P_C1_W), net->wgrad_scratch, B.c1, GS + B_1, ws));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c1, B.g), conv_gemm_dgrad(prec, B.dz1, B.pk1, B.dr0a, B.c1, GS + B_1, s));
         // r0 = prelu_a(bn_a(zp)) ; gradient = conv1 dgrad + residual branch
         FSB_TRY(bn_backward(net, s, B.dr0a, B.dr0b, B.zp, B.g, B.bn_a, P[P_PRELUA], kNoRes, kNoDrop, G(pb + P_BNA_W),
-                            G(pb + P_BNA_B), G(pb + P_PRELUA), B.dzp, FMT_F32, nullptr, CAT_ELT_BWD));
+                            G(pb + P_BNA_B), G(pb + P_PRELUA), B.dzp, FMT_F32, nullptr, GS + B_A, CAT_ELT_BWD));
         if (c.two_d && k == 0) {
             RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
                 conv0_backward(net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift, B.bn_in.mean,
                                B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, B.g, G(pb + P_CONV_W),
                                G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->conv0_scratch, s));
         } else {
-            RUN(CAT_ELT_BWD, 0, maxpool_backward(B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt, s));
+            RUN(CAT_ELT_BWD, 0, maxpool_backward(B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt_e, GS + B_A, s));
             FSB_TRY(fork());
             RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.entry, B.g_in),
-                  conv_gemm_wgrad(prec, B.u, B.dzf, G(pb + P_CONV_W), net->wgrad_scratch, B.entry, ws));
-            RUN(CAT_GEMM_DGRAD, conv_flops(B.entry, B.g_in), conv_gemm_dgrad(prec, B.dzf, B.pk_entry, B.du, B.entry, s));
+                  conv_gemm_wgrad(prec, B.u, B.dzf, G(pb + P_CONV_W), net->wgrad_scratch, B.entry, GS + B_A, ws));
+            RUN(CAT_GEMM_DGRAD, conv_flops(B.entry, B.g_in), conv_gemm_dgrad(prec_e, B.dzf, B.pk_entry, B.du, B.entry, GS + B_A, s));
             float* dprev = k > 0 ? net->blocks[k - 1].d_out : nullptr;
             FSB_TRY(bn_backward(net, s, B.du, nullptr, B.x_in, B.g_in, B.bn_in, nullptr, kNoRes, kNoDrop,
-                                G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, FMT_F32, nullptr, CAT_ELT_BWD));
+                                G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, FMT_F32, nullptr, nullptr, CAT_ELT_BWD));
         }
     }
     if (overlap) {      // join: the caller's stream continues only after the last weight gradient has landed
@@ -782,6 +803,12 @@ extern "C" int fsb_net_read_activation(fsb_net* net, int which, float* dst, long
     return pf_to_nchw(B.out, B.g, dst, s);
 }
 
+extern "C" int fsb_net_set_overlap(fsb_net* net, int on) {
+    FSB_REQUIRE(net, "set_overlap: null handle");
+    net->overlap = on != 0;
+    return 0;
+}
+
 extern "C" int fsb_net_set_profiling(fsb_net* net, int on) {
     net->profiling = on != 0;
     return 0;
@@ -808,7 +835,7 @@ extern "C" size_t fsb_conv_workspace_bytes(int n, int cin, int cout, int h, int 
     Geo go = make_geo(n, h, w, cout, gi.padH, gi.padW);
     ConvGeom c = make_conv_geom(gi, cin, cout, kh, kw);
     size_t pk = std::max(packed_weight_bytes(0, c), packed_weight_bytes(1, c));
-    size_t wg = std::max(wgrad_scratch_bytes(0, c), wgrad_scratch_bytes(1, c));
+    size_t wg = std::max(wgrad_scratch_bytes(0, c), wgrad_scratch_bytes(1, c));     // the tensor-core sizes do not depend on the product count
     return 2 * plane_bytes(gi) + 2 * plane_bytes(go) + pk + wg + 4096;
 }
 
@@ -826,6 +853,8 @@ extern "C" int fsb_conv_forward(const float* x, const float* w, const float* b, 
     cudaStream_t s = (cudaStream_t)stream;
     Geo gi, go;
     ConvGeom c;
+    FSB_REQUIRE(precision >= 0 && precision <= 3, "conv: precision must be 0..3");
+    if (precision == 3) precision = 1;      // mixed: three-product forward
     FSB_TRY(conv_unit_setup(n, cin, cout, h, wd, kh, kw, gi, go, c));
     FSB_REQUIRE(ws_bytes >= fsb_conv_workspace_bytes(n, cin, cout, h, wd, kh, kw), "conv: workspace too small");
     FSB_TRY(fsb_device_ok());
@@ -847,6 +876,8 @@ extern "C" int fsb_conv_backward(const float* x, const float* w, const float* dy
     cudaStream_t s = (cudaStream_t)stream;
     Geo gi, go;
     ConvGeom c;
+    FSB_REQUIRE(precision >= 0 && precision <= 3, "conv: precision must be 0..3");
+    if (precision == 3) precision = 2;      // mixed: single-pass backward
     FSB_TRY(conv_unit_setup(n, cin, cout, h, wd, kh, kw, gi, go, c));
     FSB_REQUIRE(ws_bytes >= fsb_conv_workspace_bytes(n, cin, cout, h, wd, kh, kw), "conv: workspace too small");
     FSB_TRY(fsb_device_ok());
@@ -862,9 +893,9 @@ extern "C" int fsb_conv_backward(const float* x, const float* w, const float* dy
     FSB_TRY(nchw_to_pf(x, gi, A, fmt, s));
     FSB_TRY(nchw_to_pf(dy, go, dZ, fmt, s));
     FSB_TRY(pack_weights(precision, w, nullptr, c, pk, s));
-    FSB_TRY(conv_gemm_dgrad(precision, dZ, pk, dA, c, s));
+    FSB_TRY(conv_gemm_dgrad(precision, dZ, pk, dA, c, nullptr, s));
     FSB_TRY(pf_to_nchw(dA, gi, dx, s));
-    FSB_TRY(conv_gemm_wgrad(precision, A, dZ, dw, scratch, c, s));
+    FSB_TRY(conv_gemm_wgrad(precision, A, dZ, dw, scratch, c, nullptr, s));
     // bias gradient: sum of dy over (n, h, w) -- dy is NCHW here
     if (db) {
         float* dyf = (float*)dZ;

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "fsb_net_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fsb_net_read_activation": (c_int, [c_void_p, c_int, c_void_p, c_ll, ctypes.POINTER(c_ll), c_void_p, c_void_p]),
     "fsb_net_set_profiling": (c_int, [c_void_p, c_int]),
+    "fsb_net_set_overlap": (c_int, [c_void_p, c_int]),
     "fsb_net_get_timings": (c_int, [c_void_p, c_int, ctypes.POINTER(c_char_p), ctypes.POINTER(c_float),
                                     ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
     "fsb_launch_count": (c_ll, [c_int]),

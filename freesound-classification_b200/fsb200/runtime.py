@@ -10,13 +10,17 @@ import torch
 from . import _lib
 from ._lib import NetConfig, check, lib
 
-PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+# GEMM back ends of the conv layers (fsb_net_config.precision).  "bf16x3" / "bf16" are the round-1 names of the
+# three-product / single-pass modes (the operand format is IEEE half since round 2) and stay accepted.
+PRECISIONS = {"fp32": 0, "fp16x3": 1, "fp16": 2, "mixed": 3, "bf16x3": 1, "bf16": 2}
 
 
 def default_precision():
-    """GEMM back end: `FSB200_PRECISION` = bf16x3 (default: tcgen05 tensor cores, split-bf16 operands, fp32-grade,
-    logits within 1e-3 of the reference) | fp32 (CUDA-core GEMMs, bit-faithful cross-check) | bf16 (single pass)."""
-    return os.environ.get("FSB200_PRECISION", "bf16x3")
+    """GEMM back end: `FSB200_PRECISION` =
+    mixed  (default) tcgen05 tensor cores; forward with split-half operands and three products (fp32-grade: logits
+           within 1e-3 of the reference), backward GEMMs single pass with per-tensor gradient scaling;
+    fp16x3 three products in forward AND backward; fp32 CUDA-core GEMMs (cross-check); fp16 single pass everywhere."""
+    return os.environ.get("FSB200_PRECISION", "mixed")
 
 
 def _stream():
@@ -282,6 +286,9 @@ class NetPlan:
 
     def set_profiling(self, on):
         lib().fsb_net_set_profiling(self.handle, 1 if on else 0)
+
+    def set_overlap(self, on):
+        check(lib().fsb_net_set_overlap(self.handle, 1 if on else 0), "net_set_overlap")
 
     def timings(self):
         cap = 16

@@ -18,7 +18,8 @@
  *     on the caller's stream; fsb_net_forward / fsb_net_backward additionally fork part of it (weight
  *     packing, weight-gradient GEMMs) onto one internal low-priority stream per plan and join it back
  *     with events before they return control of the stream, so the caller sees plain stream semantics
- *     (set FSB200_NO_OVERLAP=1 to keep everything on the caller's stream);
+ *     (FSB200_NO_OVERLAP=1 at plan creation, or fsb_net_set_overlap(net, 0), keeps everything on the caller's
+ *     stream);
  *   - one host thread per device (one process per GPU under torchrun); handles are not thread-safe.
  */
 #ifndef FSB200_H
@@ -63,7 +64,8 @@ int    fsb_feat_forward(const float* pcm, int n, long long pcm_stride, int t, in
 /* ------------------------------------------------------------------------------------------------
  * LSEP loss.  Replaces networks/losses.py:47-58 (6 elementwise torch kernels over (N,C,C)).
  *   scores, targets (N, C) float32 contiguous; loss (N) per-sample; general pairwise form
- *   (mask t_j < t_i), no max-shift -- overflow behaviour identical to the reference.
+ *   (mask t_j < t_i), no max-shift, like the reference: a score gap above ~88 overflows float32.  The kernel then
+ *   returns +inf where the reference's masked product yields NaN (inf * 0) -- both are non-finite, the value differs.
  *   backward: dscores[n,:] = dloss[n] * dL_n/ds
  * ------------------------------------------------------------------------------------------------ */
 int fsb_lsep_forward(const float* scores, const float* targets, int n, int c, float* loss, void* stream);
@@ -111,8 +113,13 @@ typedef struct fsb_net_config {
     int start_deep_supervision_on;
     int n_classes;
     float dropout_p;
-    int precision;             /* 0 = fp32 CUDA-core GEMMs, 1 = bf16x3 tcgen05 (fp32-grade),
-                                  2 = bf16 tcgen05 single pass (fast, not parity grade)           */
+    int precision;             /* GEMM back end of the conv layers:
+                                  0 = fp32 CUDA-core GEMMs (cross-check path),
+                                  1 = tcgen05, split-half operands x = hi + lo, three products, f32 accumulate
+                                      (fp32-grade, forward AND backward),
+                                  2 = tcgen05 single half pass everywhere (fast, logits NOT parity grade),
+                                  3 = mixed (default of the Python layer): forward as 1, backward GEMMs (dgrad,
+                                      wgrad) as 2 with per-tensor power-of-two gradient scaling              */
 } fsb_net_config;
 
 typedef struct fsb_net fsb_net;   /* opaque */
@@ -153,6 +160,9 @@ int fsb_net_read_activation(fsb_net* net, int which, float* dst, long long dst_c
 /* per-phase device timings of the last forward+backward (CUDA events on the launch stream);
  * enable with fsb_net_set_profiling(net, 1).  names/ms are HOST arrays of capacity `cap`.         */
 int fsb_net_set_profiling(fsb_net* net, int on);
+/* side-stream overlap of weight packing / weight-gradient GEMMs (default on unless FSB200_NO_OVERLAP was set when the
+ * plan was created); results are bit-identical either way */
+int fsb_net_set_overlap(fsb_net* net, int on);
 int fsb_net_get_timings(fsb_net* net, int cap, const char** names, float* ms, double* flops, int* count);
 /* number of kernels this library launched since the counter was last reset (bench `gpu_launches`) */
 long long fsb_launch_count(int reset);

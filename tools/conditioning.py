@@ -1,8 +1,10 @@
-"""How ill-conditioned is the canonical-width parity problem (8 untrained clips x 1.5 s)?  Runs the CPU ORACLE in
+"""How ill-conditioned is the canonical-width parity problem (default 8 untrained clips x 1.5 s; pass n and t for other
+sizes, e.g. `python tools/conditioning.py 1e-5 64 441000` for the bench workload -- needs ~35 GB of host memory)?  Runs the CPU ORACLE in
 float64, in float32, and in float64 with the input features perturbed by `noise` relative, and prints how far
 logits and gradients move.  Measured in the build container (seed 21): float32 vs float64 logits 3e-6; 1e-5 feature
 noise -> logits 4e-4, gradient tensors 3-5e-2 (L2).  This sets the gradient gates of
-tests/test_gpu_network.py::test_canonical_width_against_oracle.   usage: python tools/conditioning.py [noise]"""
+tests/test_gpu_network.py::test_canonical_width_against_oracle and of tests/test_gpu_fullsize.py.
+usage: python tools/conditioning.py [noise [n t [seeds...]]]"""
 import os
 import sys
 
@@ -14,10 +16,12 @@ from oracle import restate  # noqa: E402
 from oracle.reference_shim import make_config  # noqa: E402
 
 noise = float(sys.argv[1]) if len(sys.argv) > 1 else 1e-5
-config = make_config()
-n, t = 8, 66150
+config = make_config(output_dropout=0.0)
+n, t = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (8, 66150)
+seeds = [int(a) for a in sys.argv[4:]] or [21, 22]
 sd = restate.init_state_dict(config, two_d=True, seed=42)
-for seed in (21, 22):
+print("n = %d clips x t = %d samples, feature noise %.0e" % (n, t, noise))
+for seed in seeds:
     wav = restate.synth_waveforms(n, t, seed=seed)
     labels = torch.from_numpy(restate.synth_labels(n, 80, seed=seed))
     feats = restate.features(torch.from_numpy(wav)[..., None], config["data"]["features"])
@@ -45,3 +49,6 @@ for seed in (21, 22):
     for k in ["conv_modules.0.1.weight", "conv_modules.0.3.bias", "conv_modules.2.5.bn3.bias",
               "conv_modules.4.5.conv1.weight", "output_transform.1.weight"]:
         print("   %-34s float32 %.2e   noise %.2e" % (k, l2(g32[k], g64[k]), l2(gn[k], g64[k])))
+    big = [k for k in g64 if g64[k].numel() >= 64 and float(g64[k].norm()) > 0]
+    print("   worst tensor (>= 64 elements): float32 %.2e   noise %.2e" % (
+        max(l2(g32[k], g64[k]) for k in big), max(l2(gn[k], g64[k]) for k in big)))
