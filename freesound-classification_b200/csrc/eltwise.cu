@@ -616,6 +616,7 @@ int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo
 __device__ __forceinline__ unsigned long long gmax_pack(float v, int row) {
     unsigned u = __float_as_uint(v);
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (v != v) u = 0xFFFFFFFFu;          // NaN is the maximum (torch.max propagates it: a diverged run stays visible)
     return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
 }
 
@@ -638,7 +639,7 @@ gmax_fwd_kernel(const float* __restrict__ x, Geo g, unsigned long long* packed) 
             float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (v[i] > bv[i]) { bv[i] = v[i]; bi[i] = (int)row; }
+                if (v[i] > bv[i] || (v[i] != v[i] && bv[i] == bv[i]) || bi[i] == 0x7fffffff) { bv[i] = v[i]; bi[i] = (int)row; }
         }
     }
     __shared__ float sv[256 * 4];
@@ -654,7 +655,10 @@ gmax_fwd_kernel(const float* __restrict__ x, Geo g, unsigned long long* packed) 
             for (int y = 0; y < (int)blockDim.y; ++y) {
                 int tt = (y * blockDim.x + threadIdx.x) * 4 + i;
                 // first maximum in scan order: larger value wins, ties go to the smaller row
-                if (sv[tt] > b || (sv[tt] == b && si[tt] < r)) { b = sv[tt]; r = si[tt]; }
+                const bool nan_new = sv[tt] != sv[tt], nan_old = b != b;
+                if (si[tt] != 0x7fffffff &&
+                    (r == 0x7fffffff || (nan_new && (!nan_old || si[tt] < r)) ||
+                     (!nan_old && (sv[tt] > b || (sv[tt] == b && si[tt] < r))))) { b = sv[tt]; r = si[tt]; }
             }
             int c = c0 + i;
             if (c < g.C && r != 0x7fffffff) atomicMax(packed + (long long)n * g.Cs + c, gmax_pack(b, r));
@@ -669,8 +673,9 @@ __global__ void gmax_unpack_kernel(const unsigned long long* __restrict__ packed
     int n = (int)(i / g.C), c = (int)(i % g.C);
     unsigned long long pk = packed[(long long)n * g.Cs + c];
     unsigned u = (unsigned)(pk >> 32);
+    const bool is_nan = u == 0xFFFFFFFFu;
     u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-    feat[(long long)n * feat_stride + feat_off + c] = __uint_as_float(u);
+    feat[(long long)n * feat_stride + feat_off + c] = is_nan ? __int_as_float(0x7FC00000) : __uint_as_float(u);
     argrow[i] = (int)(0xFFFFFFFFu - (unsigned)(pk & 0xFFFFFFFFull));
 }
 

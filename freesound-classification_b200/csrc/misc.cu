@@ -26,45 +26,180 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// STABLE: the reference's `lsep_loss_stable` (networks/losses.py:25-44) -- shift by m = max over ALL pairs of
+// (s_j - s_i) = max s - min s, L = m + log(e^-m + sum e^(d - m)): finite where the plain form overflows.
+template <bool STABLE>
+__device__ __forceinline__ float lsep_shift(const float* sr, int c, int lane) {
+    if (!STABLE) return 0.f;
+    float hi = -INFINITY, lo = INFINITY;
+    for (int j = lane; j < c; j += 32) { hi = fmaxf(hi, sr[j]); lo = fminf(lo, sr[j]); }
+    return warp_max(hi) + warp_max(-lo);
+}
+
+template <bool STABLE>
 __global__ void lsep_fwd_kernel(const float* __restrict__ s, const float* __restrict__ t, int n, int c, float* loss) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
     const float* sr = s + (long long)warp * c;
     const float* tr = t + (long long)warp * c;
+    const float m = lsep_shift<STABLE>(sr, c, lane);
     float acc = 0.f;
     for (int i = 0; i < c; ++i) {
         float si = sr[i], ti = tr[i];
         for (int j = lane; j < c; j += 32)
-            if (tr[j] < ti) acc += expf(sr[j] - si);
+            if (tr[j] < ti) acc += expf(sr[j] - si - m);
     }
     acc = warp_sum(acc);
-    if (lane == 0) loss[warp] = logf(1.0f + acc);
+    if (lane == 0) loss[warp] = STABLE ? m + logf(expf(-m) + acc) : logf(1.0f + acc);
 }
 
 // dL/ds_k = ( sum_{i: t_k < t_i} e^{s_k - s_i}  -  sum_{j: t_j < t_k} e^{s_j - s_k} ) / (1 + S)
+// (STABLE: numerator and denominator both carry the factor e^-m)
+template <bool STABLE>
 __global__ void lsep_bwd_kernel(const float* __restrict__ s, const float* __restrict__ t, const float* __restrict__ dloss,
                                 int n, int c, float* ds) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
     const float* sr = s + (long long)warp * c;
     const float* tr = t + (long long)warp * c;
+    const float m = lsep_shift<STABLE>(sr, c, lane);
     float total = 0.f;
     for (int k = lane; k < c; k += 32) {
         float sk = sr[k], tk = tr[k];
         for (int i = 0; i < c; ++i)
-            if (tk < tr[i]) total += expf(sk - sr[i]);
+            if (tk < tr[i]) total += expf(sk - sr[i] - m);
     }
     total = warp_sum(total);
-    float inv = dloss[warp] / (1.0f + total);
+    float inv = dloss[warp] / ((STABLE ? expf(-m) : 1.0f) + total);
     for (int k = lane; k < c; k += 32) {
         float sk = sr[k], tk = tr[k];
         float g = 0.f;
         for (int i = 0; i < c; ++i) {
             float ti = tr[i];
-            if (tk < ti) g += expf(sk - sr[i]);
-            else if (ti < tk) g -= expf(sr[i] - sk);
+            if (tk < ti) g += expf(sk - sr[i] - m);
+            else if (ti < tk) g -= expf(sr[i] - sk - m);
         }
         ds[(long long)warp * c + k] = g * inv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lwlrap (ops/utils.py:17-26): sklearn's label_ranking_average_precision_score(truth > 0, scores,
+// sample_weight = #positives) over the rows with >= 1 positive.  Per row: for every relevant label j,
+// rank_j = #{k : score_k >= score_j} (ties share the worst rank, sklearn's rankdata(.., "max")), L_j the same count over
+// relevant k; the row scores mean_j(L_j / rank_j), or exactly 1 when every label is relevant.  With weight = #positives
+// the weighted mean is  sum_rows sum_j L_j / rank_j  /  sum_rows #positives: one warp per row writes its numerator and
+// weight (doubles), a fixed-order pass adds them (deterministic).
+// ---------------------------------------------------------------------------------------------
+__global__ void lwlrap_rows_kernel(const float* __restrict__ truth, const float* __restrict__ scores, int n, int c,
+                                   double* row_num, double* row_den) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const float* tr = truth + (long long)warp * c;
+    const float* sr = scores + (long long)warp * c;
+    double num = 0.0;
+    int npos = 0;
+    for (int j = lane; j < c; j += 32) {
+        if (tr[j] > 0.f) {
+            const float sj = sr[j];
+            int rank = 0, rel = 0;
+            for (int k = 0; k < c; ++k) {
+                const bool ge = sr[k] >= sj;
+                rank += ge;
+                rel += ge && tr[k] > 0.f;
+            }
+            num += (double)rel / (double)rank;
+            ++npos;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        num += __shfl_xor_sync(0xffffffffu, num, o);
+        npos += __shfl_xor_sync(0xffffffffu, npos, o);
+    }
+    if (lane == 0) {
+        if (npos == c) num = (double)npos;           // every label relevant: sklearn scores the row 1
+        row_num[warp] = num;
+        row_den[warp] = (double)npos;
+    }
+}
+
+__global__ void lwlrap_sum_kernel(const double* row_num, const double* row_den, int n, double* out, int accumulate) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = accumulate ? out[0] : 0.0, b = accumulate ? out[1] : 0.0;
+        for (int i = 0; i < n; ++i) { a += row_num[i]; b += row_den[i]; }
+        out[0] = a;
+        out[1] = b;
+        out[2] = b > 0.0 ? a / b : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batch assembly over a device-resident PCM pool: SampleLongAudio crop (ops/transforms.py:292-309)
+// -> MixUp (ops/transforms.py:44-65, ops/audio.py:32-52) -> zero-pad collate (ops/padding.py:8-32) in one pass.
+// All random draws (coin, partner, alpha, offsets, crop starts) are made on the host in the reference's order and arrive
+// as per-row records; the device does the PCM traffic.
+//   equal lengths   : out = (a + b) / 2
+//   unequal lengths : out = alpha * longer, then out[offset : offset + len(shorter)] = (1 - alpha) * shorter  (the
+//                     reference's `=+` ASSIGNS; quirk kept)
+//   labels          : clip(l1 + l2, 0, 1)
+// ---------------------------------------------------------------------------------------------
+struct AssembleRow {
+    long long a_off;      // first sample of the (cropped) primary clip in the pool
+    long long b_off;      // first sample of the (cropped) partner clip, unused when b_len < 0
+    double alpha;         // unequal branch: scale of the longer clip
+    double one_minus;     // unequal branch: scale of the shorter clip (1 - alpha, evaluated on the host)
+    int a_len, b_len;     // lengths after cropping; b_len < 0: no MixUp for this row
+    int a_label, b_label; // rows of the label pool
+    int mix_offset;       // unequal branch: where the shorter clip lands inside the longer one
+    int pad_;
+};
+
+__global__ void __launch_bounds__(256)
+assemble_kernel(const float* __restrict__ pool, const float* __restrict__ label_pool, const AssembleRow* __restrict__ rows,
+                int c, long long t_out, float pad_value, float* __restrict__ out, float* __restrict__ labels_out) {
+    const AssembleRow r = rows[blockIdx.y];
+    float* o = out + (long long)blockIdx.y * t_out;
+    const float* a = pool + r.a_off;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long k0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r.b_len < 0) {
+        for (long long k = k0; k < t_out; k += stride) o[k] = k < r.a_len ? a[k] : pad_value;
+    } else {
+        const float* b = pool + r.b_off;
+        if (r.a_len == r.b_len) {
+            for (long long k = k0; k < t_out; k += stride) o[k] = k < r.a_len ? (a[k] + b[k]) / 2.0f : pad_value;
+        } else {
+            const bool a_long = r.a_len > r.b_len;
+            const float* lg = a_long ? a : b;
+            const float* sh = a_long ? b : a;
+            const int n_long = a_long ? r.a_len : r.b_len, n_short = a_long ? r.b_len : r.a_len;
+            // float32 arithmetic with the scalars rounded to float32: what numpy evaluates for the reference's
+            // `longer *= a` / `shorter * (1 - a)` (a is a Python float: float32 array op, under value-based casting and
+            // under NEP 50 alike); 1 - a is formed in float64 first
+            const float alpha = (float)r.alpha, one_minus = (float)r.one_minus;
+            for (long long k = k0; k < t_out; k += stride) {
+                float v = pad_value;
+                if (k < n_long) {
+                    const long long j = k - r.mix_offset;
+                    v = (j >= 0 && j < n_short) ? sh[j] * one_minus : lg[k] * alpha;
+                }
+                o[k] = v;
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < c; k += blockDim.x) {
+            float l = label_pool[(long long)r.a_label * c + k];
+            if (r.b_len >= 0) l = fminf(fmaxf(l + label_pool[(long long)r.b_label * c + k], 0.f), 1.f);
+            labels_out[(long long)blockIdx.y * c + k] = l;
+        }
     }
 }
 
@@ -195,7 +330,7 @@ extern "C" long long fsb_launch_count(int reset) {
 extern "C" int fsb_lsep_forward(const float* scores, const float* targets, int n, int c, float* loss, void* stream) {
     FSB_REQUIRE(n > 0 && c > 0, "lsep: empty input");
     int blocks = (n * 32 + 127) / 128;
-    lsep_fwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(scores, targets, n, c, loss);
+    lsep_fwd_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(scores, targets, n, c, loss);
     FSB_LAUNCHED();
     return 0;
 }
@@ -204,7 +339,51 @@ extern "C" int fsb_lsep_backward(const float* scores, const float* targets, cons
                                  float* dscores, void* stream) {
     FSB_REQUIRE(n > 0 && c > 0, "lsep: empty input");
     int blocks = (n * 32 + 127) / 128;
-    lsep_bwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(scores, targets, dloss, n, c, dscores);
+    lsep_bwd_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(scores, targets, dloss, n, c, dscores);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+extern "C" int fsb_lsep_stable_forward(const float* scores, const float* targets, int n, int c, float* loss, void* stream) {
+    FSB_REQUIRE(n > 0 && c > 0, "lsep: empty input");
+    int blocks = (n * 32 + 127) / 128;
+    lsep_fwd_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(scores, targets, n, c, loss);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+extern "C" int fsb_lsep_stable_backward(const float* scores, const float* targets, const float* dloss, int n, int c,
+                                        float* dscores, void* stream) {
+    FSB_REQUIRE(n > 0 && c > 0, "lsep: empty input");
+    int blocks = (n * 32 + 127) / 128;
+    lsep_bwd_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(scores, targets, dloss, n, c, dscores);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+extern "C" size_t fsb_lwlrap_scratch_bytes(int n) { return (size_t)(n > 0 ? n : 0) * 2 * sizeof(double); }
+
+extern "C" int fsb_lwlrap(const float* truth, const float* scores, int n, int c, int accumulate, void* scratch,
+                          double* out, void* stream) {
+    FSB_REQUIRE(n > 0 && c > 0 && truth && scores && scratch && out, "lwlrap: bad arguments");
+    double* row_num = (double*)scratch;
+    double* row_den = row_num + n;
+    int blocks = (n * 32 + 127) / 128;
+    lwlrap_rows_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(truth, scores, n, c, row_num, row_den);
+    FSB_LAUNCHED();
+    lwlrap_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(row_num, row_den, n, out, accumulate);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+extern "C" int fsb_assemble_batch(const float* pool, const float* label_pool, const void* rows, int n, int c,
+                                  long long t_out, float pad_value, float* out, float* labels_out, void* stream) {
+    FSB_REQUIRE(pool && label_pool && rows && out && labels_out, "assemble: null argument");
+    FSB_REQUIRE(n > 0 && n <= 65535 && t_out > 0 && c > 0, "assemble: bad shape (n=%d, t_out=%lld)", n, t_out);
+    static_assert(sizeof(AssembleRow) == 56, "AssembleRow must match the 56-byte host record");
+    dim3 grid(148, n);
+    assemble_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pool, label_pool, (const AssembleRow*)rows, c, t_out, pad_value,
+                                                           out, labels_out);
     FSB_LAUNCHED();
     return 0;
 }

@@ -34,6 +34,12 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_ll, c_void_p]),
     "fsb_lsep_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "fsb_lsep_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "fsb_lsep_stable_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "fsb_lsep_stable_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "fsb_lwlrap_scratch_bytes": (c_size_t, [c_int]),
+    "fsb_lwlrap": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fsb_assemble_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_float, c_void_p, c_void_p,
+                                   c_void_p]),
     "fsb_adam_chunk": (c_int, []),
     "fsb_adam_amsgrad_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                                       c_float, c_float, c_void_p]),

@@ -8,6 +8,8 @@ per batch exactly like `make_collate_fn`, run through the model in eval mode, an
 scattered back to the original clip order.  Batches are independent, so with `torch.distributed` initialised every rank
 takes a contiguous share of the batches and the results are summed with one all-reduce.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -46,27 +48,66 @@ def pad_batch(clips, indices, padding_value=0.0):
     return out
 
 
+def device_batch(clips, indices, device, padding_value=0.0):
+    """The zero-padded batch `(len(indices), T_max, 1)` of `make_collate_fn`, built directly in device memory.
+
+    * clips that already live on the device as views of ONE buffer (a resident PCM pool) are gathered and padded by
+      the batch-assembly kernel (`fsb_assemble_batch`, one launch);
+    * host clips (numpy arrays or -- preferably pinned -- CPU tensors) are copied row by row with asynchronous
+      host-to-device copies into a pre-filled batch: no padded copy is ever materialised on the host."""
+    device = torch.device(device)
+    srcs = [clips[i] if isinstance(clips[i], torch.Tensor)
+            else torch.from_numpy(np.ascontiguousarray(clips[i], dtype=np.float32)) for i in indices]
+    srcs = [c.reshape(-1) for c in srcs]
+    n, t_max = len(srcs), max(int(c.numel()) for c in srcs)
+    pooled = all(c.is_cuda and c.dtype == torch.float32 and c.is_contiguous() for c in srcs)
+    if pooled:
+        storages = {c.untyped_storage().data_ptr() for c in srcs}
+        pooled = len(storages) == 1
+    if pooled:
+        from ._lib import check, lib
+        from .assemble import ROW_DTYPE
+        from .runtime import _ptr, _stream
+        base = srcs[0].untyped_storage().data_ptr()
+        rows = np.zeros(n, dtype=ROW_DTYPE)
+        rows["a_off"] = [(c.data_ptr() - base) // 4 for c in srcs]
+        rows["a_len"] = [int(c.numel()) for c in srcs]
+        rows["b_len"] = -1
+        rows_dev = torch.from_numpy(rows.view(np.uint8).reshape(n, ROW_DTYPE.itemsize)).to(device, non_blocking=True)
+        out = torch.empty((n, t_max, 1), dtype=torch.float32, device=device)
+        dummy = torch.zeros((n + 1, 1), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib().fsb_assemble_batch(ctypes.c_void_p(base), _ptr(dummy), _ptr(rows_dev), n, 1, t_max,
+                                           float(padding_value), _ptr(out), _ptr(dummy[1:]), _stream()), "assemble_batch")
+        return out
+    out = torch.full((n, t_max, 1), float(padding_value), dtype=torch.float32, device=device)
+    for row, c in enumerate(srcs):
+        out[row, :c.numel(), 0].copy_(c, non_blocking=True)
+    return out
+
+
 def predict_bucketed(model, clips, buckets, max_batch_elems, padding_value=0.0, return_stats=False):
     """Sigmoid class probabilities (n_clips, n_classes) float32 for a list of 1-D waveforms.
 
     model: an `_AcceleratedCNN` (eval mode is set here); buckets / max_batch_elems: as in `BucketingSampler`.
+    clips: numpy arrays, CPU tensors (pinned memory makes the copies asynchronous) or CUDA tensors.
     Clips that fall outside the buckets get NaN rows (the reference would silently skip them).
     With an initialised process group the batches are sharded over the ranks and the result is all-reduced."""
-    lengths = [len(c) for c in clips]
+    lengths = [int(c.numel()) if isinstance(c, torch.Tensor) else len(c) for c in clips]
     batches, dropped = pack_batches(lengths, buckets, max_batch_elems)
     rank, world_size = fdist.world()
     begin, end = fdist.shard_range(len(batches), rank, world_size)
     n_classes = model.config.data._n_classes
     device = torch.device(model.device)
     probs = torch.zeros((len(clips), n_classes), dtype=torch.float32, device=device)
-    padded = real = 0
+    # padded-sample overhead of the WHOLE sweep (all ranks' batches)
+    padded = sum(len(b) * max(lengths[i] for i in b) for b in batches)
+    real = sum(lengths[i] for b in batches for i in b)
     model.eval()
     with torch.no_grad():
         for indices in batches[begin:end]:
-            batch = pad_batch(clips, indices, padding_value)
-            padded += batch.shape[0] * batch.shape[1]
-            real += sum(lengths[i] for i in indices)
-            logits = model(torch.from_numpy(batch).to(device, non_blocking=True))["class_logits"]
+            batch = device_batch(clips, indices, device, padding_value)
+            logits = model(batch)["class_logits"]
             probs[torch.as_tensor(indices, device=device)] = torch.sigmoid(logits)
     if world_size > 1:
         torch.distributed.all_reduce(probs)

@@ -106,15 +106,17 @@ class FeatureExtractor:
 # ----------------------------------------------------------------------------------------------
 class _LsepFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scores, targets):
+    def forward(ctx, scores, targets, stable):
         require_cuda(scores, "input")
         s = scores.contiguous().float()
         t = targets.contiguous().float()
         n, c = s.shape
         loss = torch.empty(n, dtype=torch.float32, device=s.device)
+        fn = lib().fsb_lsep_stable_forward if stable else lib().fsb_lsep_forward
         with torch.cuda.device(s.device):
-            check(lib().fsb_lsep_forward(_ptr(s), _ptr(t), n, c, _ptr(loss), _stream()), "lsep_forward")
+            check(fn(_ptr(s), _ptr(t), n, c, _ptr(loss), _stream()), "lsep_forward")
         ctx.save_for_backward(s, t)
+        ctx.stable = stable
         return loss
 
     @staticmethod
@@ -123,13 +125,56 @@ class _LsepFunction(torch.autograd.Function):
         n, c = s.shape
         dloss = dloss.contiguous().float()
         ds = torch.empty_like(s)
+        fn = lib().fsb_lsep_stable_backward if ctx.stable else lib().fsb_lsep_backward
         with torch.cuda.device(s.device):
-            check(lib().fsb_lsep_backward(_ptr(s), _ptr(t), _ptr(dloss), n, c, _ptr(ds), _stream()), "lsep_backward")
-        return ds, None
+            check(fn(_ptr(s), _ptr(t), _ptr(dloss), n, c, _ptr(ds), _stream()), "lsep_backward")
+        return ds, None, None
 
 
-def lsep_per_sample(scores, targets):
-    return _LsepFunction.apply(scores, targets)
+def lsep_per_sample(scores, targets, stable=False):
+    return _LsepFunction.apply(scores, targets, stable)
+
+
+# ----------------------------------------------------------------------------------------------
+# lwlrap on the device
+# ----------------------------------------------------------------------------------------------
+class DeviceLwlrap:
+    """Label-weighted label-ranking average precision without leaving the GPU (`fsb_lwlrap`).
+
+    `update(truth, scores)` adds one batch to the running {numerator, weight}; `compute()` reads the whole-set value
+    (one 24-byte device->host copy); `batch(truth, scores)` returns the per-batch value as a 0-dim float64 DEVICE
+    tensor (no sync) -- `train_epoch` copies it to pinned memory asynchronously."""
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self.total = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self._scratch = None
+
+    def _run(self, truth, scores, out, accumulate):
+        require_cuda(scores, "scores")
+        t = truth.to(self.device).contiguous().float()
+        s = scores.contiguous().float()
+        n, c = s.shape
+        need = lib().fsb_lwlrap_scratch_bytes(n)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().fsb_lwlrap(_ptr(t), _ptr(s), n, c, 1 if accumulate else 0, _ptr(self._scratch), _ptr(out),
+                                   _stream()), "lwlrap")
+
+    def reset(self):
+        self.total.zero_()
+
+    def update(self, truth, scores):
+        self._run(truth, scores, self.total, True)
+
+    def batch(self, truth, scores):
+        out = torch.empty(3, dtype=torch.float64, device=self.device)
+        self._run(truth, scores, out, False)
+        return out[2]
+
+    def compute(self):
+        return float(self.total.cpu()[2])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -204,6 +249,7 @@ class NetPlan:
         self.total_params = sum(self.param_numel)
         self.workspace = None
         self._ws_key = None
+        self.forward_id = 0             # generation of the activations currently held by the workspace
         self.grad_flat = None
         self.grad_views = None
         self._param_ptrs = (ctypes.c_void_p * self.num_params)()
@@ -248,6 +294,7 @@ class NetPlan:
             signal = signal.float().contiguous()
         n, t = signal.shape
         ws = self._ensure_workspace(n, t, training)
+        self.forward_id += 1            # any earlier forward's activations are gone from here on
         logits = torch.empty((n, self.cfg.n_classes), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(lib().fsb_net_forward(self.handle, _ptr(signal), n, t, signal.stride(0), self._param_ptrs,
@@ -306,27 +353,40 @@ class _NetFunction(torch.autograd.Function):
     backward() writes every parameter gradient into the plan's persistent flat buffer and installs views of
     it as `p.grad` directly (autograd's AccumulateGrad would clone each of the ~120 views); when a parameter
     already holds a gradient (accumulation_steps > 1) the step's gradient goes to a temporary buffer and
-    is added."""
+    is added.  Consequences, all checked here rather than silently wrong:
+      * the activations live in ONE plan-owned workspace, so only the most recent training forward can be
+        differentiated -- a backward through an older forward raises;
+      * parameter gradients are delivered through `.grad`, not through autograd's return values
+        (`torch.autograd.grad(..., params)` is not supported); parameters with `requires_grad=False` are skipped."""
 
     @staticmethod
     def forward(ctx, plan, signal, dropout_seed, *params):
         ctx.plan = plan
         ctx.params = params
-        return plan.forward(signal, True, dropout_seed)
+        out = plan.forward(signal, True, dropout_seed)
+        ctx.forward_id = plan.forward_id
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
         plan, params = ctx.plan, ctx.params
-        accumulate = any(p.grad is not None for p in params)
+        if ctx.forward_id != plan.forward_id:
+            raise RuntimeError(
+                "backward through a stale forward: the plan keeps the activations of its most recent forward only "
+                "(forward #%d was overwritten by #%d); call backward before the next forward of this model"
+                % (ctx.forward_id, plan.forward_id))
+        wanted = [p.requires_grad for p in params]
+        accumulate = any(p.grad is not None for p, w in zip(params, wanted) if w)
         flat = plan.backward(dlogits, fresh=accumulate)
         if accumulate:
             off = 0
-            for p, n in zip(params, plan.param_numel):
-                g = flat[off:off + n].view(p.shape)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.add_(g)
+            for p, n, w in zip(params, plan.param_numel, wanted):
+                if w:
+                    g = flat[off:off + n].view(p.shape)
+                    if p.grad is None:
+                        p.grad = g.clone()
+                    else:
+                        p.grad.add_(g)
                 off += n
         else:
             if plan.grad_views is None or len(plan.grad_views) != len(params):
@@ -335,8 +395,9 @@ class _NetFunction(torch.autograd.Function):
                     views.append(flat[off:off + n].view(p.shape))
                     off += n
                 plan.grad_views = views
-            for p, g in zip(params, plan.grad_views):
-                p.grad = g
+            for p, g, w in zip(params, plan.grad_views, wanted):
+                if w:
+                    p.grad = g
             plan.last_flat_grad = flat
         return (None, None, None) + (None,) * len(params)
 

@@ -221,6 +221,18 @@ class _AcceleratedCNN(nn.Module):
     def _loss(self, class_logits, labels, average):
         return lsep_loss(class_logits, labels, average=average)
 
+    def _sync_replicas(self):
+        """Data parallel: every replica starts from rank 0's parameters AND BatchNorm buffers.  Only gradients are
+        exchanged afterwards, so replicas that were built under different RNG states (or loaded different
+        checkpoints) would otherwise diverge silently."""
+        from fsb200 import dist as fdist
+        if fdist.world()[1] == 1:
+            return
+        import torch.distributed as dist
+        with torch.no_grad():
+            for t in list(self.parameters()) + list(self.buffers()):
+                dist.broadcast(t.data, src=0)
+
     def _sync_gradients(self):
         """Data parallel: ONE all-reduce (SUM) of the flat gradient, averaged inside the Adam kernel."""
         from fsb200 import dist as fdist
@@ -247,10 +259,10 @@ class _AcceleratedCNN(nn.Module):
         pending = None
 
         def resolve(item, pb):
-            ev, losses_h, loss_h, probs_h, labels_h, batch_idx, step, first_signal = item
+            ev, losses_h, loss_h, metric_h, batch_idx, step, first_signal = item
             ev.synchronize()
             training_losses.extend(losses_h.numpy().copy())
-            metric = lwlrap(labels_h.numpy(), probs_h.numpy())
+            metric = float(metric_h)
             history.append(metric)
             pb.update()
             pb.set_description("Loss: {:.4f}, Metric: {:.4f}".format(float(loss_h), np.mean(history)))
@@ -284,19 +296,20 @@ class _AcceleratedCNN(nn.Module):
                     self.optimizer.zero_grad()
 
                 with torch.no_grad():
-                    probs = torch.sigmoid(class_logits.detach())
+                    # per-batch lwlrap of sigmoid(logits) (reference :687-690) computed on the device: only the
+                    # per-sample losses, the loss and the metric (8 bytes) travel to the host, asynchronously
+                    probs = torch.sigmoid(class_logits.detach()).reshape(labels.shape)
+                    metric_d = self._lwlrap_meter().batch(labels, probs)
                     losses_d = loss_vec.detach() if loss_vec is not None else loss.detach().reshape(1)
                     losses_h = torch.empty(losses_d.shape, dtype=torch.float32, pin_memory=True)
                     loss_h = torch.empty((), dtype=torch.float32, pin_memory=True)
-                    probs_h = torch.empty(probs.shape, dtype=torch.float32, pin_memory=True)
-                    labels_h = torch.empty(labels.shape, dtype=torch.float32, pin_memory=True)
+                    metric_h = torch.empty((), dtype=torch.float64, pin_memory=True)
                     losses_h.copy_(losses_d, non_blocking=True)
                     loss_h.copy_(loss.detach(), non_blocking=True)
-                    probs_h.copy_(probs, non_blocking=True)
-                    labels_h.copy_(labels, non_blocking=True)
+                    metric_h.copy_(metric_d, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record()
-                item = (ev, losses_h, loss_h, probs_h, labels_h, batch_idx, self.global_step,
+                item = (ev, losses_h, loss_h, metric_h, batch_idx, self.global_step,
                         signal if batch_idx == 0 else None)
                 if pending is not None:
                     resolve(pending, pb)
@@ -306,11 +319,18 @@ class _AcceleratedCNN(nn.Module):
         if self.two_d:
             self.add_histogram_summaries(training_losses, self.train_writer, self.global_step)
 
+    def _lwlrap_meter(self):
+        if getattr(self, "_lwlrap_dev", None) is None:
+            self._lwlrap_dev = runtime.DeviceLwlrap(self.device)
+        return self._lwlrap_dev
+
     def evaluate(self, loader, verbose=False, write_summary=False, epoch=None):
-        """Reference :709-763."""
+        """Reference :709-763: eval-mode forward, `loss * len(batch) / len(dataset)` accumulated over the batches,
+        whole-set lwlrap of sigmoid(logits).  Loss terms and the lwlrap numerator / weight are accumulated on the
+        device; the host reads them once at the end (the reference syncs per batch and runs sklearn on the host)."""
         self.eval()
-        valid_loss = 0
-        all_class_probs, all_labels, losses = [], [], []
+        meter = runtime.DeviceLwlrap(self.device)
+        valid_loss_d = torch.zeros((), dtype=torch.float64, device=self.device)
         with torch.no_grad():
             for batch_idx, sample in enumerate(loader):
                 signal = sample["signal"].to(self.device)
@@ -319,14 +339,10 @@ class _AcceleratedCNN(nn.Module):
                 if not self.two_d:
                     class_logits = class_logits.squeeze()
                 loss = self._loss(class_logits, labels, average=True)
-                losses.append((loss, len(labels) / len(loader.dataset)))
-                all_class_probs.append(torch.sigmoid(class_logits))
-                all_labels.append(labels)
-            for loss, multiplier in losses:       # one host sync for the whole set instead of one per batch
-                valid_loss += loss.item() * multiplier
-            all_class_probs = torch.cat([p.reshape(-1, p.shape[-1]) for p in all_class_probs]).cpu().numpy()
-            all_labels = torch.cat([l.reshape(-1, l.shape[-1]) for l in all_labels]).cpu().numpy()
-            metric = lwlrap(all_labels, all_class_probs)
+                valid_loss_d += loss.double() * (len(labels) / len(loader.dataset))
+                meter.update(labels, torch.sigmoid(class_logits).reshape(labels.shape))
+            valid_loss = float(valid_loss_d)
+            metric = meter.compute()
             if write_summary:
                 self.add_scalar_summaries(valid_loss, metric, writer=self.valid_writer, global_step=self.global_step)
             if verbose:
@@ -358,6 +374,7 @@ class _AcceleratedCNN(nn.Module):
         self.valid_writer = _summary_writer(os.path.join(self.experiment.summaries, "fold_{}".format(fold), "valid"))
         os.makedirs(os.path.join(self.experiment.checkpoints, "fold_{}".format(fold)), exist_ok=True)
 
+        from fsb200 import dist as fdist
         self.global_step = 0
         self.make_optimizer(max_steps=len(train_loader) * epochs)
         scores = []
@@ -369,18 +386,23 @@ class _AcceleratedCNN(nn.Module):
             self.train_epoch(train_loader, epoch, log_interval, write_summary=True)
             validation_score = self.validation(valid_loader, epoch)
             scores.append(validation_score)
-            if epoch % self.config.train._save_every == 0:
+            # data parallel: rank 0 writes the checkpoints (its BatchNorm running statistics; every rank would
+            # otherwise race on the same file with its own per-rank statistics)
+            writer_rank = fdist.world()[0] == 0
+            if epoch % self.config.train._save_every == 0 and writer_rank:
                 print("\nSaving model on epoch", epoch)
                 torch.save(self.state_dict(), os.path.join(
                     self.experiment.checkpoints, "fold_{}".format(fold), "model_on_epoch_{}.pth".format(epoch)))
             if validation_score > best_score:
-                torch.save(self.state_dict(), os.path.join(
-                    self.experiment.checkpoints, "fold_{}".format(fold), "best_model.pth"))
+                if writer_rank:
+                    torch.save(self.state_dict(), os.path.join(
+                        self.experiment.checkpoints, "fold_{}".format(fold), "best_model.pth"))
                 best_score = validation_score
         return scores
 
     def make_optimizer(self, max_steps):
         """Reference :870-880."""
+        self._sync_replicas()
         optimizer = OPTIMIZERS[self.config.train.optimizer]
         optimizer = optimizer(self.parameters(), self.config.train.learning_rate,
                               weight_decay=self.config.train.weight_decay)

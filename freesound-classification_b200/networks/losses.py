@@ -3,25 +3,29 @@ is on the training path; it runs as a warp-per-sample CUDA kernel (forward and b
 import torch
 
 
-def lsep_loss(input, target, average=True):
-    """`log(1 + sum_{i,j: t_j < t_i} exp(s_j - s_i))` per sample (reference :47-58); mean over the
-    batch when `average`, else the per-sample vector."""
+def _lsep(input, target, average, stable):
     from fsb200.runtime import lsep_per_sample
     if not input.is_cuda:
         raise RuntimeError("lsep_loss: CUDA tensors only (this package has no CPU path)")
     squeeze = input.dim() == 1
     if squeeze:                         # the 1D model squeezes a batch of one (reference :268)
         input, target = input[None], target[None]
-    lsep = lsep_per_sample(input, target.to(input.device))
+    lsep = lsep_per_sample(input, target.to(input.device), stable)
     if average:
         return lsep.mean()
     return lsep[0] if squeeze else lsep
 
 
+def lsep_loss(input, target, average=True):
+    """`log(1 + sum_{i,j: t_j < t_i} exp(s_j - s_i))` per sample (reference :47-58); mean over the
+    batch when `average`, else the per-sample vector."""
+    return _lsep(input, target, average, False)
+
+
 def lsep_loss_stable(input, target, average=True):
-    """Max-shifted variant kept for API parity (reference :25-44); mathematically identical to
-    `lsep_loss` wherever the latter does not overflow, so it shares the kernel."""
-    return lsep_loss(input, target, average)
+    """The reference's max-shifted variant (:25-44): `m + log(exp(-m) + sum exp(d - m))` with
+    `m = max_{i,j}(s_j - s_i)` -- equal to `lsep_loss` where that does not overflow, finite beyond."""
+    return _lsep(input, target, average, True)
 
 
 def binary_cross_entropy(input, target, raw=True):

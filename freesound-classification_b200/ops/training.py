@@ -51,6 +51,10 @@ class FusedAdam(Optimizer):
         return (torch.from_numpy(table).to(dev), torch.tensor(blocks, dtype=torch.int32, device=dev).contiguous(),
                 len(blocks))
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._table = self._table_key = None       # the moments were replaced: rebuild the device pointer table
+
     @torch.no_grad()
     def step(self, closure=None):
         from fsb200._lib import check, lib
@@ -73,12 +77,21 @@ class FusedAdam(Optimizer):
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
                     st["max_exp_avg_sq"] = torch.zeros_like(p)
-            key = (gi, tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist))
+                else:
+                    for name in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):     # loaded state: kernel layout
+                        t = st[name]
+                        if t.device != p.device or t.dtype != torch.float32 or not t.is_contiguous():
+                            st[name] = t.to(device=p.device, dtype=torch.float32).contiguous()
+            # the device pointer table bakes in parameter, gradient AND state addresses: all of them key the cache
+            # (load_state_dict / state resets replace the moment tensors without touching the parameters)
+            key = (gi, tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                              self.state[p]["exp_avg_sq"].data_ptr(), self.state[p]["max_exp_avg_sq"].data_ptr())
+                             for p in plist))
             if key != self._table_key:
                 self._table = self._build_table(group, plist)
                 self._table_key = key
             table, block_map, n_blocks = self._table
-            step = self.state[plist[0]]["step"] + 1
+            step = int(self.state[plist[0]]["step"]) + 1       # torch.optim.Adam checkpoints carry a tensor `step`
             for p in plist:
                 self.state[p]["step"] = step
             beta1, beta2 = group["betas"]

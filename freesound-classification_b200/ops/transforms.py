@@ -1,8 +1,9 @@
-"""dict -> dict sample transforms with the reference's signatures (ops/transforms.py of the
-reference).  The transforms on the accelerated path are implemented here (`AudioFeatures`,
-`MixUp`, collate-side helpers); file / sox based augmentations (`LoadAudio`,
-`AudioAugmentation`, `FlipAudio`, `ShuffleAudio`, `CutOut`, `SampleSegment`, `STFT`) are out of
-scope and are forwarded to a reference checkout when one is on sys.path.
+"""dict -> dict sample transforms with the reference's signatures (ops/transforms.py of the reference).  Implemented
+here: the transforms SURVEY.md section 8 puts on the accelerated path -- `AudioFeatures` (A1), `MixUp` (A16),
+`SampleLongAudio` (f1) -- plus the `Compose` driver the training loop calls.  Every other name of the reference's module
+(`MapLabels`, `OneOf`, `DropFields`, `RenameFields`, `Identity`, and the file / sox based `LoadAudio`,
+`AudioAugmentation`, `FlipAudio`, `ShuffleAudio`, `CutOut`, `SampleSegment`, `STFT`) is forwarded to a reference checkout
+that sits after this package on sys.path.
 """
 import importlib.util
 import os
@@ -16,147 +17,103 @@ SAMPLE_RATE = 44100
 
 
 class Augmentation:
-    """Base class: `Compose.switch_off_augmentations` sets `p = 0` on every instance."""
-    pass
-
-
-class MapLabels:
-
-    def __init__(self, class_map, drop_raw=True):
-        self.class_map = class_map
-
-    def __call__(self, dataset, **inputs):
-        labels = np.zeros(len(self.class_map), dtype=np.float32)
-        for c in inputs["raw_labels"]:
-            labels[self.class_map[c]] = 1.0
-        transformed = dict(inputs)
-        transformed["labels"] = labels
-        transformed.pop("raw_labels")
-        return transformed
+    """Marker base class: `Compose.switch_off_augmentations` zeroes `p` on every instance (reference :17-18)."""
 
 
 class MixUp(Augmentation):
-    """With probability p mix the sample with `dataset.random_clean_sample()` (reference :44-65)."""
+    """Row A16.  With probability p the sample is mixed with `dataset.random_clean_sample()` through
+    `ops.audio.mix_audio_and_labels` (reference :44-65); RNG consumption order as in the reference (one
+    `np.random.uniform` for the coin, then the draws inside the mixer).  The on-device equivalent for resident PCM
+    pools is `fsb200.assemble.DeviceBatchAssembler`."""
 
     def __init__(self, p):
         self.p = p
 
     def __call__(self, dataset, **inputs):
-        transformed = dict(inputs)
+        out = dict(inputs)
         if np.random.uniform() < self.p:
-            partner = dataset.random_clean_sample()
-            audio, labels = mix_audio_and_labels(
-                inputs["audio"], partner["audio"], inputs["labels"], partner["labels"])
-            transformed["audio"] = audio
-            transformed["labels"] = labels
-        return transformed
+            other = dataset.random_clean_sample()
+            out["audio"], out["labels"] = mix_audio_and_labels(inputs["audio"], other["audio"], inputs["labels"],
+                                                               other["labels"])
+        return out
 
 
 class AudioFeatures:
-    """Emits `signal = audio[:, None]` (raw PCM): feature extraction itself happens inside the
-    model on the GPU.  The reference additionally computes a scipy STFT for mel features and throws
-    it away (reference :222-228); that dead work is skipped -- the emitted dict is identical."""
+    """Row A1.  Emits `signal = audio[:, None]` (raw PCM): feature extraction itself happens inside the model on the
+    GPU.  The reference additionally computes a scipy STFT for mel features and throws it away (reference :222-228);
+    that dead work is skipped -- the emitted dict is identical.  `n_features` / `padding_value` as in reference
+    :154-203."""
 
     eps = 1e-4
 
     def __init__(self, descriptor, verbose=True):
-        name, *args = descriptor.split("_")
-        self.feature_type = name
-        if name == "stft":
-            n_fft, hop_size = args
-            self.n_fft, self.hop_size = int(n_fft), int(hop_size)
+        kind, *args = descriptor.split("_")
+        self.feature_type = kind
+        self.padding_value = 0.0
+        if kind == "stft":
+            self.n_fft, self.hop_size = int(args[0]), int(args[1])
             self.n_features = self.n_fft // 2 + 1
-            self.padding_value = 0.0
-            if verbose:
-                print("\nUsing STFT features with params:\n", "n_fft: {}, hop_size: {}".format(n_fft, hop_size))
-        elif name == "mel":
-            n_fft, hop_size, n_mel = args
-            self.n_fft, self.hop_size, self.n_mel = int(n_fft), int(hop_size), int(n_mel)
+            note = "Using STFT features with params:\n n_fft: {}, hop_size: {}".format(*args[:2])
+        elif kind == "mel":
+            self.n_fft, self.hop_size, self.n_mel = (int(a) for a in args[:3])
             self.n_features = self.n_mel
-            self.padding_value = 0.0
-            if verbose:
-                print("\nUsing mel features with params:\n",
-                      "n_fft: {}, hop_size: {}, n_mel: {}".format(n_fft, hop_size, n_mel))
-        elif name == "raw":
+            note = "Using mel features with params:\n n_fft: {}, hop_size: {}, n_mel: {}".format(*args[:3])
+        elif kind == "raw":
             self.n_features = 1
-            self.padding_value = 0.0
-            if verbose:
-                print("\nUsing raw waveform features.")
+            note = "Using raw waveform features."
+        else:
+            raise ValueError("unknown feature descriptor %r" % descriptor)
+        if verbose:
+            print("\n" + note)
 
     def __call__(self, dataset, **inputs):
-        transformed = dict(inputs)
-        if self.feature_type in ("stft", "mel", "raw"):
-            transformed["signal"] = np.expand_dims(inputs["audio"], -1)
-        return transformed
+        out = dict(inputs)
+        out["signal"] = np.expand_dims(inputs["audio"], -1)
+        return out
 
 
 class SampleLongAudio:
+    """SURVEY 8(f1).  Clips longer than `max_length` seconds are cut to a uniformly drawn window of exactly
+    `max_length * sr` samples (reference :292-309; one `np.random.randint(0, size - window)` draw).  The device
+    equivalent is the crop field of `fsb200.assemble.DeviceBatchAssembler`."""
 
     def __init__(self, max_length):
         self.max_length = max_length
 
     def __call__(self, dataset, **inputs):
-        transformed = dict(inputs)
-        if (inputs["audio"].size / inputs["sr"]) > self.max_length:
-            max_length = self.max_length * inputs["sr"]
-            start = np.random.randint(0, inputs["audio"].size - max_length)
-            transformed["audio"] = inputs["audio"][start:start + max_length]
-        return transformed
-
-
-class OneOf:
-
-    def __init__(self, transforms):
-        self.transforms = transforms
-
-    def __call__(self, dataset, **inputs):
-        return random.choice(self.transforms)(**inputs)
-
-
-class DropFields:
-
-    def __init__(self, fields):
-        self.to_drop = fields
-
-    def __call__(self, dataset, **inputs):
-        return {name: value for name, value in inputs.items() if name not in self.to_drop}
-
-
-class RenameFields:
-
-    def __init__(self, mapping):
-        self.mapping = mapping
-
-    def __call__(self, dataset, **inputs):
-        transformed = dict(inputs)
-        for old, new in self.mapping.items():
-            transformed[new] = transformed.pop(old)
-        return transformed
+        out = dict(inputs)
+        audio, sr = inputs["audio"], inputs["sr"]
+        if audio.size / sr > self.max_length:
+            window = self.max_length * sr
+            first = np.random.randint(0, audio.size - window)
+            out["audio"] = audio[first:first + window]
+        return out
 
 
 class Compose:
+    """Applies the transforms in order; `switch_off_augmentations()` is what `fit_validate` calls on
+    `train_loader.dataset.transform` (reference networks/classifiers.py:825-826, ops/transforms.py:343-358)."""
 
     def __init__(self, transforms):
         self.transforms = transforms
 
     def switch_off_augmentations(self):
         for t in self.transforms:
-            if isinstance(t, Augmentation) or type(t).__mro__[-2].__name__ == "Augmentation":
+            # augmentations of a reference checkout derive from ITS `Augmentation` class: match by name too
+            if any(base.__name__ == "Augmentation" for base in type(t).__mro__[1:]):
                 t.p = 0.0
 
     def __call__(self, dataset=None, **inputs):
+        sample = inputs
         for t in self.transforms:
-            inputs = t(dataset=dataset, **inputs)
-        return inputs
+            sample = t(dataset=dataset, **sample)
+        return sample
 
 
-class Identity:
-
-    def __call__(self, dataset=None, **inputs):
-        return inputs
-
-
-_FORWARDED = ("LoadAudio", "AudioAugmentation", "FlipAudio", "ShuffleAudio", "CutOut", "SampleSegment", "STFT")
+# Everything else in the reference's module is host plumbing (label mapping, field renames) or file / sox based
+# augmentation outside the accelerated path (SURVEY.md section 8): forwarded to a reference checkout later on sys.path.
+_FORWARDED = ("LoadAudio", "AudioAugmentation", "FlipAudio", "ShuffleAudio", "CutOut", "SampleSegment", "STFT",
+              "MapLabels", "OneOf", "DropFields", "RenameFields", "Identity")
 _reference_module = None
 
 
@@ -178,6 +135,6 @@ def __getattr__(name):
                 break
         else:
             raise AttributeError(
-                "ops.transforms.%s is a file/sox based augmentation outside the accelerated path; put a "
-                "checkout of the reference after this package on sys.path to use it" % name)
+                "ops.transforms.%s is outside the accelerated path and is not re-implemented here; put a checkout of "
+                "the reference after this package on sys.path to use it" % name)
     return getattr(_reference_module, name)

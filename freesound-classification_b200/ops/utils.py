@@ -11,14 +11,15 @@ import torch
 
 
 def lwlrap(truth, scores):
-    """Label-weighted label-ranking average precision (reference ops/utils.py:17-26)."""
+    """Label-weighted label-ranking average precision (reference ops/utils.py:17-26).  Host version (sklearn); the
+    training / evaluation loops use the device kernel behind `fsb200.runtime.DeviceLwlrap`.
+    Scores are widened to float64 first: the scipy pinned by the reference (1.2.1) ranks in float64 whatever the
+    input, current scipy ranks float32 scores in float32 and rounds every L/rank term to 2^-24."""
     from sklearn.metrics import label_ranking_average_precision_score
-    sample_weight = np.sum(truth > 0, axis=1)
-    nonzero_weight_sample_indices = np.flatnonzero(sample_weight > 0)
-    return label_ranking_average_precision_score(
-        truth[nonzero_weight_sample_indices, :] > 0,
-        scores[nonzero_weight_sample_indices, :],
-        sample_weight=sample_weight[nonzero_weight_sample_indices])
+    truth, scores = np.asarray(truth), np.asarray(scores, dtype=np.float64)
+    weight = np.sum(truth > 0, axis=1)
+    keep = np.flatnonzero(weight > 0)
+    return label_ranking_average_precision_score(truth[keep, :] > 0, scores[keep, :], sample_weight=weight[keep])
 
 
 def load_json(file):

@@ -71,6 +71,10 @@ int    fsb_feat_forward(const float* pcm, int n, long long pcm_stride, int t, in
 int fsb_lsep_forward(const float* scores, const float* targets, int n, int c, float* loss, void* stream);
 int fsb_lsep_backward(const float* scores, const float* targets, const float* dloss, int n, int c,
                       float* dscores, void* stream);
+/* networks/losses.py:25-44 (`lsep_loss_stable`): same loss shifted by max_{i,j}(s_j - s_i); finite for any gap */
+int fsb_lsep_stable_forward(const float* scores, const float* targets, int n, int c, float* loss, void* stream);
+int fsb_lsep_stable_backward(const float* scores, const float* targets, const float* dloss, int n, int c,
+                             float* dscores, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Adam(amsgrad=True) multi-tensor step.  Replaces ops/training.py:10 (`torch.optim.Adam`,
@@ -93,6 +97,34 @@ int fsb_adam_amsgrad_step(const void* table, const int* block_map, int n_blocks,
  * ------------------------------------------------------------------------------------------------ */
 int fsb_mixup_equal(const float* pcm, const float* labels, const int* partner, int n, long long t,
                     int c, float* pcm_out, float* labels_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch assembly over a device-resident PCM pool: SampleLongAudio crop (ops/transforms.py:292-309) ->
+ * MixUp, both branches (ops/transforms.py:44-65, ops/audio.py:32-52) -> zero-pad collate
+ * (ops/padding.py:8-32) in one pass.  Random draws are made by the caller (reference RNG order) and passed per
+ * output row as 56-byte records (DEVICE array `rows`, n entries):
+ *     int64  a_off, b_off     first pool sample of the cropped primary / partner clip
+ *     double alpha, one_minus unequal lengths: scale of the longer clip, scale of the shorter clip (1 - alpha formed
+ *                             in float64); both are rounded to float32 and multiplied in float32, as numpy does
+ *     int32  a_len, b_len     lengths after cropping; b_len < 0 = row is not mixed
+ *     int32  a_label, b_label rows of label_pool (n_clips, c)
+ *     int32  mix_offset, pad  unequal lengths: start of the shorter clip inside the longer one
+ * equal lengths -> (a + b) / 2; unequal -> alpha * longer with the window OVERWRITTEN by (1 - alpha) * shorter
+ * (the reference's `=+` assigns); labels clip(l1 + l2, 0, 1).  out (n, t_out) is padded with pad_value.
+ * ------------------------------------------------------------------------------------------------ */
+int fsb_assemble_batch(const float* pool, const float* label_pool, const void* rows, int n, int c,
+                       long long t_out, float pad_value, float* out, float* labels_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * lwlrap on the device.  Replaces ops/utils.py:17-26 (sklearn label_ranking_average_precision_score with
+ * sample_weight = #positives, rows without positives dropped; ties share the worst rank).
+ *   truth, scores (n, c) float32; scratch: fsb_lwlrap_scratch_bytes(n) bytes;
+ *   out: 3 doubles {sum_rows sum_j L_j/rank_j, sum_rows #positives, their ratio = lwlrap}.  accumulate != 0 adds this
+ *   batch to out[0], out[1] first (whole-set lwlrap over many batches, networks/classifiers.py:741-747).
+ * ------------------------------------------------------------------------------------------------ */
+size_t fsb_lwlrap_scratch_bytes(int n);
+int    fsb_lwlrap(const float* truth, const float* scores, int n, int c, int accumulate, void* scratch,
+                  double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-network plan (feature kernel + conv blocks + heads + FC head, forward and backward).

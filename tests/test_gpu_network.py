@@ -12,7 +12,7 @@ from oracle.reference_shim import FakeExperiment, make_config
 
 pytestmark = pytest.mark.gpu
 
-PRECISIONS = ["fp32", "bf16x3"]
+PRECISIONS = ["fp32", "fp16x3", "mixed"]
 
 
 def load(name):

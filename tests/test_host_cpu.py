@@ -96,18 +96,50 @@ def test_mixup_numpy_matches_reference():
 
 
 def test_transforms_host_side():
-    from ops.transforms import AudioFeatures, Compose, DropFields, MixUp, RenameFields
+    from ops.transforms import AudioFeatures, Compose, MixUp, SampleLongAudio
     af = AudioFeatures("mel_2048_1024_128", verbose=False)
     assert af.n_features == 128 and af.padding_value == 0.0
     assert AudioFeatures("stft_256_128", verbose=False).n_features == 129
     audio = np.arange(10, dtype=np.float32)
-    t = Compose([af, RenameFields({"sr": "rate"}), DropFields(("audio",))])
-    out = t(dataset=None, audio=audio, sr=44100)
-    assert out["signal"].shape == (10, 1) and "audio" not in out and out["rate"] == 44100
+    out = Compose([af])(dataset=None, audio=audio, sr=44100)
+    assert out["signal"].shape == (10, 1) and np.array_equal(out["signal"][:, 0], audio) and out["sr"] == 44100
     mix = MixUp(p=1.0)
     t2 = Compose([mix])
     t2.switch_off_augmentations()
     assert mix.p == 0.0
+    # SampleLongAudio: same draw as the reference (np.random.randint(0, size - window)), window of max_length * sr
+    long_audio = np.arange(50, dtype=np.float32)
+    np.random.seed(3)
+    start = np.random.randint(0, 50 - 2 * 10)
+    np.random.seed(3)
+    cut = SampleLongAudio(max_length=2)(dataset=None, audio=long_audio, sr=10)
+    assert np.array_equal(cut["audio"], long_audio[start:start + 20])
+    assert SampleLongAudio(max_length=10)(dataset=None, audio=long_audio, sr=10)["audio"] is long_audio
+
+
+def test_out_of_scope_transforms_forward_to_a_reference_checkout():
+    """Names outside the accelerated path resolve to the reference's own classes when a checkout sits later on
+    sys.path, and raise a clear AttributeError otherwise."""
+    import ops.transforms as T
+    from oracle.reference_shim import find_reference_root
+    root = find_reference_root()
+    if root is None:
+        with pytest.raises(AttributeError):
+            T.RenameFields
+        return
+    import ops
+    saved, saved_mod = list(ops.__path__), T._reference_module
+    try:
+        ops.__path__.append(os.path.join(root, "ops"))
+        T._reference_module = None
+        try:
+            renamed = T.RenameFields({"sr": "rate"})(dataset=None, sr=1, audio=2)
+        except Exception as exc:       # the reference module imports librosa & co at module scope
+            pytest.skip("reference ops/transforms.py is not importable here: %r" % (exc,))
+        assert renamed == {"rate": 1, "audio": 2}
+    finally:
+        ops.__path__[:] = saved
+        T._reference_module = saved_mod
 
 
 @pytest.mark.parametrize("name,cls,cfg", [
