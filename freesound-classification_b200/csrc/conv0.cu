@@ -74,7 +74,7 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ feat, int n
 __global__ void __launch_bounds__(C0_THREADS)
 conv0_fwd_kernel(const float* __restrict__ feat, int N, int H, int W, const float* __restrict__ scale,
                  const float* __restrict__ shift, const float* __restrict__ w, const float* __restrict__ b,
-                 float* __restrict__ zp, Geo gp) {
+                 float* __restrict__ zp, unsigned char* __restrict__ amax, Geo gp) {
     __shared__ float u[2][4][C0_PW];
     const int px0 = blockIdx.x * C0_PX, py = blockIdx.y, n = blockIdx.z;
     load_patch(feat, n, H, W, py, px0, scale[0], shift[0], scale[1], shift[1], 0.f, 0.f, 0.f, 0.f, u, nullptr, nullptr);
@@ -91,6 +91,7 @@ conv0_fwd_kernel(const float* __restrict__ feat, int N, int H, int W, const floa
         }
         for (int p = 0; p < npx; ++p) {
             float best = 0.f;
+            int bpos = 0;
             if (real) {
                 best = -INFINITY;
 #pragma unroll
@@ -105,20 +106,22 @@ conv0_fwd_kernel(const float* __restrict__ feat, int N, int H, int W, const floa
 #pragma unroll
                                 for (int dx = 0; dx < 3; ++dx)
                                     acc = fmaf(wr[ci][dy][dx], u[ci][sy + dy][2 * p + sx + dx], acc);
-                        best = fmaxf(best, acc);
+                        if (acc > best) { best = acc; bpos = sy * 2 + sx; }      // first maximum in window scan order
                     }
             }
-            zp[geo_row(gp, n, py, px0 + p) * gp.Cs + c] = best;
+            const long long o = geo_row(gp, n, py, px0 + p) * gp.Cs + c;
+            zp[o] = best;
+            if (amax) amax[o] = (unsigned char)bpos;      // training: the backward pass routes the gradient by it
         }
     }
 }
 
 int conv0_forward(const float* feat, int N, int H, int W, const float* scale, const float* shift, const float* w,
-                  const float* b, float* zp, const Geo& gp, cudaStream_t s) {
+                  const float* b, float* zp, unsigned char* amax, const Geo& gp, cudaStream_t s) {
     FSB_REQUIRE(gp.H == H / 2 && gp.W == W / 2 && gp.N == N, "conv0: geometry mismatch");
     FSB_REQUIRE(gp.H <= 65535 && N <= 65535, "conv0: grid too large");
     dim3 grid((gp.W + C0_PX - 1) / C0_PX, gp.H, N);
-    conv0_fwd_kernel<<<grid, C0_THREADS, 0, s>>>(feat, N, H, W, scale, shift, w, b, zp, gp);
+    conv0_fwd_kernel<<<grid, C0_THREADS, 0, s>>>(feat, N, H, W, scale, shift, w, b, zp, amax, gp);
     FSB_LAUNCHED();
     return 0;
 }
@@ -133,8 +136,8 @@ size_t conv0_bwd_scratch_bytes(const Geo& gp) { return (size_t)C0B_BLOCKS * C0B_
 __global__ void __launch_bounds__(C0_THREADS)
 conv0_bwd_kernel(const float* __restrict__ feat, int N, int H, int W, const float* __restrict__ scale,
                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                 const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ dzp, Geo gp,
-                 float* __restrict__ partials) {
+                 const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ dzp,
+                 const unsigned char* __restrict__ amax, Geo gp, float* __restrict__ partials) {
     __shared__ __align__(16) float u[2][4][C0_PW];
     __shared__ float xh[2][4][C0_PW];
     __shared__ float valid[4][C0_PW];
@@ -162,10 +165,9 @@ conv0_bwd_kernel(const float* __restrict__ feat, int N, int H, int W, const floa
         // shared-memory gathers, 144 FMAs per (pixel, channel) instead of ~130 FMAs + ~90 shared loads).
         const float sc0 = scale[0], sc1 = scale[1], sh0 = shift[0], sh1 = shift[1];
         const bool fast = sc0 != 0.f && sc1 != 0.f;
-        float wsum0 = 0.f, wsum1 = 0.f;
+        float accV[9], gsum = 0.f;          // sum_q g valid_t over border windows, sum_q g over interior windows
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { wsum0 += wr[0][i / 3][i % 3]; wsum1 += wr[1][i / 3][i % 3]; }
-        float accG0 = 0.f, accG1 = 0.f, accB0 = 0.f, accB1 = 0.f;
+        for (int i = 0; i < 9; ++i) accV[i] = 0.f;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int tx = (int)(tile % tiles_x);
             long long t2 = tile / tiles_x;
@@ -179,75 +181,43 @@ conv0_bwd_kernel(const float* __restrict__ feat, int N, int H, int W, const floa
             if (!real) continue;
             const int npx = min(C0_PX, gp.W - px0);
             if (fast) {
+                // The forward pass stored the arg-max position of every pool window, so the gradient is routed with
+                // 18 FMAs per (pixel, channel) (the previous version recomputed the four conv outputs: 72 FMAs, then
+                // accumulated a one-hot gradient over all four positions: 144 more).  The BatchNorm-input terms are
+                // linear in the accumulated weight gradient and need no per-pixel work:
+                //   sum_q g S_ci = sum_t w[ci][t] acc[ci][t],   sum_q g V_ci = sum_t w[ci][t] (sum_q g valid_t)
+                // where valid_t = 1 for every tap of a window that does not touch the image border.
                 const bool row_border = 2 * py - 1 < 0 || 2 * py + 2 >= H;
-                const float* gptr = dzp + geo_row(gp, n, py, px0) * gp.Cs + c;
-                float g_next = gptr[0];
+                const long long o0 = geo_row(gp, n, py, px0) * gp.Cs + c;
+                float g_next = dzp[o0];
+                int pos_next = amax[o0];
                 for (int p = 0; p < npx; ++p) {
                     const float g = g_next;
-                    if (p + 1 < npx) g_next = gptr[(long long)(p + 1) * gp.Cs];     // prefetch: the load latency hides behind this pixel's FMAs
-                    float up[2][4][4];
+                    const int pos = pos_next;
+                    if (p + 1 < npx) {                   // prefetch: the load latency hides behind this pixel's FMAs
+                        g_next = dzp[o0 + (long long)(p + 1) * gp.Cs];
+                        pos_next = amax[o0 + (long long)(p + 1) * gp.Cs];
+                    }
+                    const int sy = pos >> 1, sx = pos & 1;
+                    const float* u0 = &u[0][sy][2 * p + sx];
+                    const float* u1 = &u[1][sy][2 * p + sx];
 #pragma unroll
-                    for (int ci = 0; ci < 2; ++ci)
+                    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const float2 lo = *reinterpret_cast<const float2*>(&u[ci][r][2 * p]);
-                            const float2 hi = *reinterpret_cast<const float2*>(&u[ci][r][2 * p + 2]);
-                            up[ci][r][0] = lo.x; up[ci][r][1] = lo.y; up[ci][r][2] = hi.x; up[ci][r][3] = hi.y;
+                        for (int dx = 0; dx < 3; ++dx) {
+                            acc[dy * 3 + dx] = fmaf(g, u0[dy * C0_PW + dx], acc[dy * 3 + dx]);
+                            acc[9 + dy * 3 + dx] = fmaf(g, u1[dy * C0_PW + dx], acc[9 + dy * 3 + dx]);
                         }
-                    // conv outputs of the four window positions, evaluated exactly like the forward kernel (bias, then the
-                    // ci = 0 taps, then the ci = 1 taps) so that the arg-max agrees; the per-input-channel partial sums fall out
-                    float S[2][4];
-                    int best = 0;
-                    float bv = -INFINITY;
-#pragma unroll
-                    for (int pos = 0; pos < 4; ++pos) {
-                        const int sy = pos >> 1, sx = pos & 1;
-                        float a = bias;
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) a = fmaf(wr[0][dy][dx], up[0][sy + dy][sx + dx], a);
-                        const float mid = a;
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) a = fmaf(wr[1][dy][dx], up[1][sy + dy][sx + dx], a);
-                        S[0][pos] = mid - bias;
-                        S[1][pos] = a - mid;
-                        if (a > bv) { bv = a; best = pos; }
-                    }
-#pragma unroll
-                    for (int pos = 0; pos < 4; ++pos) {
-                        const int sy = pos >> 1, sx = pos & 1;
-                        const float gk = best == pos ? g : 0.f;
-#pragma unroll
-                        for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-                            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                                for (int dx = 0; dx < 3; ++dx)
-                                    acc[ci * 9 + dy * 3 + dx] = fmaf(gk, up[ci][sy + dy][sx + dx], acc[ci * 9 + dy * 3 + dx]);
-                    }
-                    const float Sb0 = best == 0 ? S[0][0] : best == 1 ? S[0][1] : best == 2 ? S[0][2] : S[0][3];
-                    const float Sb1 = best == 0 ? S[1][0] : best == 1 ? S[1][1] : best == 2 ? S[1][2] : S[1][3];
-                    float V0 = wsum0, V1 = wsum1;
                     const int x0 = 2 * (px0 + p) - 1;
-                    if (row_border || x0 < 0 || x0 + 3 >= W) {      // window touches the image border: sum valid taps only
-                        const int bsy = best >> 1, bsx = best & 1;
-                        V0 = V1 = 0.f;
+                    if (row_border || x0 < 0 || x0 + 3 >= W) {      // window touches the image border: per-tap validity
+                        const float* vv = &valid[sy][2 * p + sx];
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                const float vv = valid[bsy + dy][2 * p + bsx + dx];
-                                V0 = fmaf(wr[0][dy][dx], vv, V0);
-                                V1 = fmaf(wr[1][dy][dx], vv, V1);
-                            }
+                            for (int dx = 0; dx < 3; ++dx) accV[dy * 3 + dx] = fmaf(g, vv[dy * C0_PW + dx], accV[dy * 3 + dx]);
+                    } else {
+                        gsum += g;
                     }
-                    accG0 = fmaf(g, Sb0 - sh0 * V0, accG0);
-                    accG1 = fmaf(g, Sb1 - sh1 * V1, accG1);
-                    accB0 = fmaf(g, V0, accB0);
-                    accB1 = fmaf(g, V1, accB1);
                 }
                 continue;
             }
@@ -285,6 +255,16 @@ conv0_bwd_kernel(const float* __restrict__ feat, int N, int H, int W, const floa
             }
         }
         if (fast && real) {
+            float sgs0 = 0.f, sgs1 = 0.f, accB0 = 0.f, accB1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float w0 = wr[0][t / 3][t % 3], w1 = wr[1][t / 3][t % 3], vg = gsum + accV[t];
+                sgs0 = fmaf(w0, acc[t], sgs0);
+                sgs1 = fmaf(w1, acc[9 + t], sgs1);
+                accB0 = fmaf(w0, vg, accB0);
+                accB1 = fmaf(w1, vg, accB1);
+            }
+            const float accG0 = sgs0 - sh0 * accB0, accG1 = sgs1 - sh1 * accB1;
             // xhat = (u - shift) * invstd / scale - mean * invstd   on valid positions
             acc[18] = accG0 * (invstd[0] / sc0) - mean[0] * invstd[0] * accB0;
             acc[19] = accG1 * (invstd[1] / sc1) - mean[1] * invstd[1] * accB1;
@@ -336,9 +316,10 @@ conv0_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, Geo gp, 
 }
 
 int conv0_backward(const float* feat, int N, int H, int W, const float* scale, const float* shift, const float* mean,
-                   const float* invstd, const float* w, const float* b, const float* dzp, const Geo& gp, float* dw,
-                   float* db, float* dgamma_in, float* dbeta_in, void* scratch, cudaStream_t s) {
-    conv0_bwd_kernel<<<C0B_BLOCKS, C0_THREADS, 0, s>>>(feat, N, H, W, scale, shift, mean, invstd, w, b, dzp, gp,
+                   const float* invstd, const float* w, const float* b, const float* dzp, const unsigned char* amax,
+                   const Geo& gp, float* dw, float* db, float* dgamma_in, float* dbeta_in, void* scratch, cudaStream_t s) {
+    FSB_REQUIRE(amax != nullptr, "conv0_backward: needs the arg-max map of the forward pass");
+    conv0_bwd_kernel<<<C0B_BLOCKS, C0_THREADS, 0, s>>>(feat, N, H, W, scale, shift, mean, invstd, w, b, dzp, amax, gp,
                                                        (float*)scratch);
     FSB_LAUNCHED();
     FSB_REQUIRE(gp.Cs <= 512, "conv0: at most 512 output channels");

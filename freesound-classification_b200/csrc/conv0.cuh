@@ -14,8 +14,10 @@ int plain_stats(const float* x, long long n, double* partials16, cudaStream_t s)
 
 // feat (N, H, W) float32 ; scale/shift: BN_in coefficients (>= 2 entries) ; w (C0, 2, 3, 3), b (C0)
 // zp: padded-flat pooled output, geometry gp = (N, H/2, W/2, C0)
+// amax (optional, gp.rows * gp.Cs bytes): position 0..3 of the first maximum of every pool window (scan order), kept for
+// the backward pass
 int conv0_forward(const float* feat, int N, int H, int W, const float* scale, const float* shift, const float* w,
-                  const float* b, float* zp, const Geo& gp, cudaStream_t s);
+                  const float* b, float* zp, unsigned char* amax, const Geo& gp, cudaStream_t s);
 
 int conv0_bwd_blocks();
 size_t conv0_bwd_scratch_bytes(const Geo& gp);
@@ -23,7 +25,7 @@ size_t conv0_bwd_scratch_bytes(const Geo& gp);
 // the bias feeds a batch-statistics BN), dgamma_in / dbeta_in (2 entries each).
 int conv0_backward(const float* feat, int N, int H, int W, const float* scale, const float* shift,
                    const float* mean, const float* invstd, const float* w, const float* b, const float* dzp,
-                   const Geo& gp, float* dw, float* db, float* dgamma_in, float* dbeta_in, void* scratch,
-                   cudaStream_t s);
+                   const unsigned char* amax, const Geo& gp, float* dw, float* db, float* dgamma_in, float* dbeta_in,
+                   void* scratch, cudaStream_t s);
 
 }  // namespace fsb

@@ -5,15 +5,26 @@
 // Work decomposition: one CTA of 256 threads owns FPB = 16 consecutive frames of one clip.  A real
 // n_fft-point transform is computed as an M = n_fft/2 point complex transform of the even/odd packed
 // samples followed by the split post-processing; 256 threads execute M/4 radix-4 butterflies per
-// stage, so 1024/M frames are transformed concurrently.  PCM is read from HBM once per CTA window
-// (overlap between neighbouring CTAs is 1/17 and hits L2); outputs are staged in shared memory and
-// flushed with the contiguous dimension fastest.
+// stage, so PAR = 1024/M frames are transformed concurrently.
+//
+// PCM staging: the CTA's window of raw samples is a contiguous run of the clip.  It streams through a three-slot
+// shared-memory ring in chunks of PAR * hop samples (one group of concurrently transformed frames advances the window
+// by exactly one chunk): an elected thread issues 1-D bulk TMA copies (`cp.async.bulk`, completion counted on one
+// mbarrier per slot) two chunks ahead of the group being transformed, so HBM latency hides behind the previous
+// group's FFT and every sample is read from HBM once per CTA and from shared memory by each frame that overlaps it.
+// CTAs whose window needs reflected samples (the first and the last of a clip) or whose global address / hop is not
+// 16-byte aligned read the samples with plain loads and per-sample reflection instead.
+// Outputs are staged in shared memory and flushed with the contiguous dimension fastest.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fsb {
 
 static constexpr int FEAT_THREADS = 256;
-static constexpr int FPB = 16;  // frames per CTA
+static constexpr int FPB = 16;           // frames per CTA
+static constexpr int FEAT_RING = 3;      // PCM ring slots
+static constexpr int FEAT_MAX_CHUNK = 2048;   // floats per ring slot the ring path supports (PAR * hop)
 
 // tw[n] = (cos(2 pi n / n_fft), -sin(2 pi n / n_fft)), evaluated in double
 __global__ void feat_tables_kernel(float2* tw, int n_fft) {
@@ -29,9 +40,22 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+__device__ __forceinline__ uint32_t feat_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void feat_bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
 template <int LOG2N>
 __global__ void __launch_bounds__(FEAT_THREADS)
-feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop, int frames,
+feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop, int frames, int ring_chunk,
             int mode, float eps, int n_mel, const float* __restrict__ fb_vals,
             const int* __restrict__ fb_off, const int* __restrict__ fb_start,
             const int* __restrict__ fb_len, const float2* __restrict__ tw_g, float* __restrict__ out,
@@ -51,14 +75,40 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
     float2* buf0 = tws + M;                                      // PAR * M = 1024
     float2* buf1 = buf0 + 1024;                                  // 1024
     float* mag = reinterpret_cast<float*>(buf1 + 1024);          // PAR * (BINS + 1)
-    float* tile = mag + PAR * (BINS + 1);                        // F_out * (FPB + 1)
+    const int f_out = (mode == 2) ? n_mel : BINS;
+    float* tile = mag + PAR * (BINS + 1);                        // f_out * (FPB + 1)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+        smem_raw + (((size_t)((unsigned char*)(tile + (size_t)f_out * (FPB + 1)) - smem_raw) + 15) & ~(size_t)15));
+    float* ring = reinterpret_cast<float*>(bars + 4);            // FEAT_RING * ring_chunk floats, 16-byte aligned
 
     const int tid = threadIdx.x;
     const int clip = blockIdx.y;
     const int frame0 = blockIdx.x * FPB;
     const int nfr = min(FPB, frames - frame0);
-    const int f_out = (mode == 2) ? n_mel : BINS;
     const float* x = pcm + (long long)clip * pcm_stride;
+
+    // ---- PCM window of this CTA: samples [s0, s0 + wlen) of the clip; ring path only when no reflection is needed
+    const long long s0 = (long long)frame0 * hop - M;            // n_fft/2 == M
+    const int wlen = (nfr - 1) * hop + NFFT;
+    const int CH = ring_chunk;                                   // PAR * hop, or 0: ring path disabled for this launch
+    const bool use_ring = CH > 0 && s0 >= 0 && s0 + wlen <= T && ((reinterpret_cast<size_t>(x + s0) & 15) == 0);
+    const int nchunks = use_ring ? (wlen + CH - 1) / CH : 0;
+    auto issue_chunk = [&](int c) {                              // one thread: bulk copy of chunk c into slot c % 3
+        const uint32_t b = feat_smem_u32(bars + (c % FEAT_RING));
+        const int n = min(CH, wlen - c * CH);                    // multiple of 4 floats (hop % 4 == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((uint32_t)n * 4u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(feat_smem_u32(ring + (size_t)(c % FEAT_RING) * CH)), "l"(x + s0 + (long long)c * CH),
+                       "r"((uint32_t)n * 4u), "r"(b)
+                     : "memory");
+    };
+    if (tid == 0 && use_ring) {
+        for (int i = 0; i < FEAT_RING; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(feat_smem_u32(bars + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue_chunk(0);
+        if (nchunks > 1) issue_chunk(1);
+    }
 
     for (int i = tid; i < NFFT; i += FEAT_THREADS) tw[i] = tw_g[i];
     {
@@ -76,22 +126,44 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
     __syncthreads();
 
     for (int it = 0; it < nfr; it += PAR) {
-        // ---- 1. windowed, reflect-padded frames -> packed complex input (natural order)
-        for (int e = tid; e < PAR * M; e += FEAT_THREADS) {
-            int slot = e / M, j = e - slot * M;
-            int fr = frame0 + it + slot;
-            float2 v = make_float2(0.f, 0.f);
-            if (it + slot < nfr) {
-                int i0 = fr * hop - M + 2 * j;       // n_fft/2 == M
-                int i1 = i0 + 1;
-                i0 = i0 < 0 ? -i0 : (i0 >= T ? 2 * (T - 1) - i0 : i0);
-                i1 = i1 < 0 ? -i1 : (i1 >= T ? 2 * (T - 1) - i1 : i1);
-                float w0 = 0.5f - 0.5f * tw[2 * j].x;
-                float w1 = 0.5f - 0.5f * tw[2 * j + 1].x;
-                v.x = __ldg(x + i0) * w0;
-                v.y = __ldg(x + i1) * w1;
+        // ---- 1. windowed frames -> packed complex input (natural order): z[j] = (x[2j] w[2j], x[2j+1] w[2j+1])
+        if (use_ring) {
+            const int g = it / PAR;                              // group g reads chunks g and g + 1
+            // slot (g + 2) % 3 held chunk g - 1, last read by group g - 1 whose reads completed before the barrier
+            // that ended its step 1: refill it now, two chunks ahead
+            if (tid == 0 && g + 2 < nchunks) issue_chunk(g + 2);
+            feat_bar_wait(feat_smem_u32(bars + (g % FEAT_RING)), (uint32_t)((g / FEAT_RING) & 1));
+            if (g + 1 < nchunks) feat_bar_wait(feat_smem_u32(bars + ((g + 1) % FEAT_RING)), (uint32_t)(((g + 1) / FEAT_RING) & 1));
+            const float* c0 = ring + (size_t)(g % FEAT_RING) * CH;
+            const float* c1 = ring + (size_t)((g + 1) % FEAT_RING) * CH;
+            for (int e = tid; e < PAR * M; e += FEAT_THREADS) {
+                const int slot = e / M, j = e - slot * M;
+                float2 v = make_float2(0.f, 0.f);
+                if (it + slot < nfr) {
+                    const int local = slot * hop + 2 * j;        // sample offset inside chunk g (may run into g + 1)
+                    const float2 xv = *reinterpret_cast<const float2*>(local < CH ? c0 + local : c1 + (local - CH));
+                    v.x = xv.x * (0.5f - 0.5f * tw[2 * j].x);
+                    v.y = xv.y * (0.5f - 0.5f * tw[2 * j + 1].x);
+                }
+                buf0[e] = v;
             }
-            buf0[e] = v;
+        } else {
+            for (int e = tid; e < PAR * M; e += FEAT_THREADS) {
+                int slot = e / M, j = e - slot * M;
+                int fr = frame0 + it + slot;
+                float2 v = make_float2(0.f, 0.f);
+                if (it + slot < nfr) {
+                    int i0 = fr * hop - M + 2 * j;
+                    int i1 = i0 + 1;
+                    i0 = i0 < 0 ? -i0 : (i0 >= T ? 2 * (T - 1) - i0 : i0);
+                    i1 = i1 < 0 ? -i1 : (i1 >= T ? 2 * (T - 1) - i1 : i1);
+                    float w0 = 0.5f - 0.5f * tw[2 * j].x;
+                    float w1 = 0.5f - 0.5f * tw[2 * j + 1].x;
+                    v.x = __ldg(x + i0) * w0;
+                    v.y = __ldg(x + i1) * w1;
+                }
+                buf0[e] = v;
+            }
         }
         __syncthreads();
 
@@ -101,19 +173,19 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
         {
             const int slot = tid / (M / 4);
             const int j = tid - slot * (M / 4);
-            const float2* s0 = nullptr;
+            const float2* s0p = nullptr;
             int Ns = 1, tbase = 0;
 #pragma unroll
             for (int st = 0; st < LOG2M / 2; ++st) {
-                s0 = src + slot * M;
+                s0p = src + slot * M;
                 float2* d0 = dst + slot * M;
                 int k = j & (Ns - 1);
                 const float2* t3 = tws + tbase + 3 * k;      // exp(-2 pi i m k/(4 Ns)), m = 1, 2, 3
                 tbase += 3 * Ns;
-                float2 v0 = s0[j];
-                float2 v1 = cmul(s0[j + M / 4], t3[0]);
-                float2 v2 = cmul(s0[j + M / 2], t3[1]);
-                float2 v3 = cmul(s0[j + 3 * M / 4], t3[2]);
+                float2 v0 = s0p[j];
+                float2 v1 = cmul(s0p[j + M / 4], t3[0]);
+                float2 v2 = cmul(s0p[j + M / 2], t3[1]);
+                float2 v3 = cmul(s0p[j + 3 * M / 4], t3[2]);
                 float2 a = make_float2(v0.x + v2.x, v0.y + v2.y);
                 float2 b = make_float2(v0.x - v2.x, v0.y - v2.y);
                 float2 c = make_float2(v1.x + v3.x, v1.y + v3.y);
@@ -200,11 +272,6 @@ feat_kernel(const float* __restrict__ pcm, long long pcm_stride, int T, int hop,
     }
 }
 
-static size_t feat_smem_bytes(int n_fft, int f_out) {
-    int m = n_fft / 2, par = 1024 / m, bins = m + 1;
-    return (size_t)n_fft * 8 + (size_t)m * 8 + 2 * 1024 * 8 + (size_t)par * (bins + 1) * 4 + (size_t)f_out * (FPB + 1) * 4;
-}
-
 template <int LOG2N>
 static int launch_feat(const float* pcm, int n, long long pcm_stride, int t, int hop, int mode,
                        float eps, int n_mel, const float* fb_vals, const int* fb_off,
@@ -213,12 +280,26 @@ static int launch_feat(const float* pcm, int n, long long pcm_stride, int t, int
     int n_fft = 1 << LOG2N;
     int frames = 1 + t / hop;
     int f_out = mode == 2 ? n_mel : n_fft / 2 + 1;
-    size_t smem = feat_smem_bytes(n_fft, f_out);
+    const int m = n_fft / 2, par = 1024 / m, bins = m + 1;
+    // ring path: one chunk = PAR * hop samples; a group's frames must fit in two consecutive chunks, chunk copies must be
+    // whole 16-byte units and every row of the PCM matrix must keep the 16-byte alignment of the first
+    int chunk = par * hop;
+    const bool ring_ok = hop % 4 == 0 && n_fft - hop <= chunk && chunk <= FEAT_MAX_CHUNK && pcm_stride % 4 == 0 &&
+                         (reinterpret_cast<size_t>(pcm) & 15) == 0;
+    static int ring_env = -1;            // FSB200_FEAT_RING=0: plain-load path everywhere (A/B timing)
+    if (ring_env < 0) { const char* e = getenv("FSB200_FEAT_RING"); ring_env = e ? atoi(e) : 1; }
+    if (!ring_ok || !ring_env) chunk = 0;
+    const size_t smem = (size_t)n_fft * 8 + (size_t)m * 8 + 2 * 1024 * 8 + (size_t)par * (bins + 1) * 4 +
+                        (size_t)f_out * (FPB + 1) * 4 + 16 + 32 + (size_t)FEAT_RING * chunk * 4;
     FSB_REQUIRE(smem <= 227 * 1024, "feat: shared memory %zu too large", smem);
     auto kern = feat_kernel<LOG2N>;
-    FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;        // per instantiation
+    if (!attr_set) {
+        FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
     dim3 grid((frames + FPB - 1) / FPB, n);
-    kern<<<grid, FEAT_THREADS, smem, stream>>>(pcm, pcm_stride, t, hop, frames, mode, eps, n_mel,
+    kern<<<grid, FEAT_THREADS, smem, stream>>>(pcm, pcm_stride, t, hop, frames, chunk, mode, eps, n_mel,
                                                fb_vals, fb_off, fb_start, fb_len,
                                                (const float2*)tables, out, sn, sf, st);
     FSB_LAUNCHED();

@@ -112,6 +112,7 @@ struct fsb_net {
     size_t fork_used = 0;
     cudaEvent_t join_event = nullptr, pack_event = nullptr;
     void* conv0_scratch = nullptr;
+    unsigned char* conv0_amax = nullptr;   // 2D block 0: arg-max position of every pool window (training)
     unsigned* gscale = nullptr;     // [num_blocks][B_PER_BLOCK] GradScale slots (common.cuh), zeroed at the start of backward
 
     // precision of the forward / backward GEMMs (cfg.precision 3 = mixed: three-product forward, single-pass backward)
@@ -257,6 +258,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
                 max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.entry));
             } else {
                 net->conv0_scratch = b.take_bytes(conv0_bwd_scratch_bytes(B.g));
+                net->conv0_amax = b.take<unsigned char>((size_t)B.g.rows * B.g.Cs);
             }
             max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c1));
             max_wgrad = std::max(max_wgrad, wgrad_scratch_bytes(prec, B.c2));
@@ -542,7 +544,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
                                             B.bn_in.shift, B.bn_in.mean, B.bn_in.invstd, s));
             RUN(CAT_CONV0, 2.0 * 2 * B.C * 9 * (double)n * c.n_features * frames,
                 conv0_forward(net->feat, n, c.n_features, frames, B.bn_in.scale, B.bn_in.shift, P[P_CONV_W],
-                              P[P_CONV_B], B.zp, B.g, s));
+                              P[P_CONV_B], B.zp, training ? net->conv0_amax : nullptr, B.g, s));
         } else {
             if (k == 0) {
                 // 1D: features land directly in the padded-flat block input (channels = STFT bins)
@@ -735,7 +737,7 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
         if (c.two_d && k == 0) {
             RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
                 conv0_backward(net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift, B.bn_in.mean,
-                               B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, B.g, G(pb + P_CONV_W),
+                               B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, net->conv0_amax, B.g, G(pb + P_CONV_W),
                                G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->conv0_scratch, s));
         } else {
             RUN(CAT_ELT_BWD, 0, maxpool_backward(B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt_e, GS + B_A, s));

@@ -102,7 +102,7 @@ def stft_magnitude(audio, n_fft, hop):
     padded = F.pad(audio.unsqueeze(1), (half, half), mode="reflect").squeeze(1)
     frames = padded.unfold(-1, n_fft, hop)                       # (N, n_frames, n_fft)
     k = torch.arange(n_fft, dtype=torch.float64)
-    window = (0.5 - 0.5 * torch.cos(2 * math.pi * k / n_fft)).to(torch.float32)
+    window = (0.5 - 0.5 * torch.cos(2 * math.pi * k / n_fft)).to(torch.float32).to(audio.device)
     spec = torch.fft.rfft(frames * window, dim=-1)               # (N, n_frames, F)
     mag = torch.sqrt(spec.real ** 2 + spec.imag ** 2)
     return mag.transpose(1, 2).contiguous()
@@ -120,7 +120,7 @@ def features(signal, descriptor, filterbank=None):
         return torch.log(mag + 1e-4)
     if filterbank is None:
         filterbank = torch.from_numpy(make_mel_filterbanks(descriptor))
-    mel = torch.matmul(torch.as_tensor(filterbank, dtype=torch.float32), mag)
+    mel = torch.matmul(torch.as_tensor(filterbank, dtype=torch.float32).to(mag.device), mag)
     return torch.log(mel + 1e-4)
 
 
@@ -205,7 +205,7 @@ def _head(feats, sd, training, dropout_p, stats_out, dropout_mask=None):
 def add_frequency_encoding(x):
     """networks/classifiers.py:553-561: concat channel `linspace(-1, 1, H)[h]`."""
     n, d, h, w = x.shape
-    vertical = torch.linspace(-1, 1, h, dtype=x.dtype).view(1, 1, -1, 1).repeat(n, 1, 1, w)
+    vertical = torch.linspace(-1, 1, h, dtype=x.dtype).to(x.device).view(1, 1, -1, 1).repeat(n, 1, 1, w)
     return torch.cat([x, vertical], dim=1)
 
 

@@ -9,16 +9,16 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 
-os.environ.setdefault("FSB200_PRECISION", "bf16x3")
+os.environ.setdefault("FSB200_PRECISION", "mixed")
 from networks.classifiers import TwoDimensionalCNNClassificationModel  # noqa: E402
 from networks.losses import lsep_loss  # noqa: E402
 from ops.training import make_step  # noqa: E402
-from oracle.reference_shim import FakeExperiment  # noqa: E402
+from fsb200.experiment import StandaloneExperiment  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 torch.manual_seed(42)
-model = TwoDimensionalCNNClassificationModel(FakeExperiment(bench.canonical_config(0.5)), device="cuda:0")
+model = TwoDimensionalCNNClassificationModel(StandaloneExperiment(bench.model_config("2d", 0.5)), device="cuda:0")
 model.make_optimizer(max_steps=100)
 model.train()
 x = torch.from_numpy(bench.synth_batch(B, 0)).cuda()
