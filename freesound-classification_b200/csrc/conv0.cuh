@@ -19,6 +19,12 @@ int plain_stats(const float* x, long long n, double* partials16, cudaStream_t s)
 int conv0_forward(const float* feat, int N, int H, int W, const float* scale, const float* shift, const float* w,
                   const float* b, float* zp, unsigned char* amax, const Geo& gp, cudaStream_t s);
 
+// the same layer on the tensor cores (conv0_tc.cu): im2col operand built in shared memory, four TMEM accumulators = the
+// four pool-window positions; precision 1 = three products, 2 = single pass.  Supported when Cs <= 128.
+bool conv0_tc_supported(const Geo& gp);
+int conv0_tc_forward(int precision, const float* feat, int N, int H, int W, const float* scale, const float* shift,
+                     const float* w, const float* b, float* zp, unsigned char* amax, const Geo& gp, cudaStream_t s);
+
 int conv0_bwd_blocks();
 size_t conv0_bwd_scratch_bytes(const Geo& gp);
 // dzp: float32 padded-flat gradient wrt the pooled conv output.  Writes dw (C0,2,3,3), db (C0, zeros:

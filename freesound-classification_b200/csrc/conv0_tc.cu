@@ -1,0 +1,286 @@
+// Block-0 entry convolution of the 2D network on the tensor cores (networks/classifiers.py:524-532 for k = 0):
+// BatchNorm2d(2) -> Conv2d(2 -> C0, 3x3, pad 1) -> MaxPool2d(2), fused.  K = 2 * 9 = 18 is far too small for a TMA-fed
+// row-shifted GEMM (the generic conv kernel would spend a 16-wide k-step per tap and write the un-pooled 1.4 GB
+// tensor), so this kernel builds the im2col operand itself:
+//
+//   tile = 128 POOLED pixels.  For each of the four pool-window positions the builder warps write a K-major
+//   [128 x 32] half tile (18 patch values of the BN-applied 2-channel input, zero padded to two k-steps; hi and lo
+//   planes, x = hi + lo) straight into shared memory in the SWIZZLE_64B layout the UMMA descriptors expect -- channel 1
+//   (the frequency encoding, networks/classifiers.py:553-561) is synthesised, never loaded.  One elected thread issues
+//   the tile's 4 positions x 2 k-steps x 3 products as M128 x N(C0 padded) x K16 tcgen05 MMAs into FOUR TMEM
+//   accumulators (one per window position); the epilogue takes the max over the four accumulators, records the
+//   arg-max position for the backward pass, adds the bias and writes the pooled row.
+//   The operand tiles are double buffered: building tile i + 1 overlaps the MMAs of tile i.
+//
+// The weight-gradient / BatchNorm-input gradient pass stays on the CUDA cores (conv0.cu: with the stored arg-max it is
+// 18 FMAs per pooled pixel and channel).
+#include "conv0.cuh"
+#include "tc_ptx.cuh"
+#include "umma_issue.cuh"
+
+namespace fsb {
+namespace {
+
+constexpr int C0T_THREADS = 160;                  // warps 0-3: operand builders + epilogue, warp 4: MMA issuer
+constexpr int C0T_PX = 128;                       // pooled pixels per tile = UMMA M = TMEM lanes
+constexpr uint32_t C0T_PLANE = C0T_PX * 64;       // one [128 x 32] half plane, 64-byte rows
+constexpr uint32_t C0T_POS = 2 * C0T_PLANE;       // hi + lo
+constexpr uint32_t C0T_ABUF = 4 * C0T_POS;        // four window positions
+
+struct Conv0TcParams {
+    const float* feat;
+    int N, H, W;
+    const float* scale;
+    const float* shift;
+    const float* w;
+    const float* b;
+    float* zp;
+    unsigned char* amax;
+    Geo gp;
+    int BN;                 // padded output channels (gp.Cs, multiple of 16, <= 128)
+    int planes;             // 2: three products (hi + lo operands), 1: single pass
+    long long npix;         // pooled pixels
+    int ntiles;
+};
+
+__device__ __forceinline__ float c0t_freq_enc(int h, int H) {
+    const float step = 2.0f / (float)(H - 1);
+    return h < H / 2 ? -1.0f + step * (float)h : 1.0f - step * (float)(H - 1 - h);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// 16-byte chunk `c` (0..3) of 64-byte row `r` of a SWIZZLE_64B tile (Swizzle<2,4,3>: address bits [4,6) ^= bits [7,9))
+__device__ __forceinline__ uint32_t sw64(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
+
+__device__ __forceinline__ void st_shared_v4_u32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// writes K values v[0..17] (zero padded to 32) as row r of the hi (and lo) plane at smem address `base`
+__device__ __forceinline__ void write_k_row(uint32_t base, uint32_t r, const float* v, int planes) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        __half h0, l0, h1, l1;
+        split_h16(v[2 * i], h0, l0);
+        split_h16(v[2 * i + 1], h1, l1);
+        hi[i] = pack_h2(h0, h1);
+        lo[i] = pack_h2(l0, l1);
+    }
+#pragma unroll
+    for (int i = 9; i < 16; ++i) hi[i] = lo[i] = 0u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        st_shared_v4_u32(base + sw64(r, c), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        if (planes == 2)
+            st_shared_v4_u32(base + C0T_PLANE + sw64(r, c), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+    }
+}
+
+__global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_fwd_kernel(const Conv0TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_buf0 = smem_base;                                   // two operand buffers
+    const uint32_t b_tile = a_buf0 + 2u * C0T_ABUF;                      // weights: hi plane, lo plane ([BN x 32] each)
+    const uint32_t w_plane = C0T_PLANE;                                  // plane stride of the weight tile
+    const uint32_t bars = b_tile + 2u * 128u * 64u;                      // a_full[2], acc_full, tmem slot
+    const uint32_t b_afull = bars, b_acc = bars + 16u, tmem_slot = bars + 24u;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bars + 64u - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float sc0 = p.scale[0], sh0 = p.shift[0], sc1 = p.scale[1], sh1 = p.shift[1];
+
+    // ---- one-time set-up: weight tile (K-major, row = output channel, k = ci * 9 + dy * 3 + dx), bias, barriers, TMEM
+    for (int n = threadIdx.x; n < p.BN; n += C0T_THREADS) {
+        float v[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) v[k] = n < p.gp.C ? p.w[n * 18 + k] : 0.f;
+        write_k_row(b_tile, (uint32_t)n, v, 2);          // lo plane C0T_PLANE bytes after the hi plane
+        bias_s[n] = n < p.gp.C ? p.b[n] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(b_afull, 128);
+        mbar_init(b_afull + 8u, 128);
+        mbar_init(b_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    fence_async_smem();                       // the weight tile was written through the generic proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int H2 = p.gp.H, W2 = p.gp.W;
+    if (warp < 4) {
+        const uint32_t r = threadIdx.x;                        // tile row = TMEM lane
+        uint32_t it = 0;
+        long long prev_q = -1;                                 // pooled pixel of the tile whose accumulators are in flight
+        auto epilogue = [&](long long q, uint32_t parity) {
+            mbar_wait(b_acc, parity);
+            tc_fence_after();
+            const bool live = q >= 0 && q < p.npix;            // rows past the last pixel: TMEM loads are warp-wide, stores are not
+            float* zrow = nullptr;
+            unsigned char* arow = nullptr;
+            if (live) {
+                const int px = (int)(q % W2);
+                const long long t = q / W2;
+                const int py = (int)(t % H2), n = (int)(t / H2);
+                const long long row = geo_row(p.gp, n, py, px);
+                zrow = p.zp + row * p.gp.Cs;
+                arow = p.amax ? p.amax + row * p.gp.Cs : nullptr;
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                float v0[16], v1[16], v2[16], v3[16];
+                tmem_ld16_async(taddr + (uint32_t)c0, v0);
+                tmem_ld16_async(taddr + (uint32_t)(p.BN + c0), v1);
+                tmem_ld16_async(taddr + (uint32_t)(2 * p.BN + c0), v2);
+                tmem_ld16_async(taddr + (uint32_t)(3 * p.BN + c0), v3);
+                tmem_ld_wait();
+                float o[16];
+                uint32_t pos4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    // first maximum in window scan order (0,0) (0,1) (1,0) (1,1), like nn.MaxPool2d
+                    float best = v0[i];
+                    uint32_t bp = 0u;
+                    if (v1[i] > best) { best = v1[i]; bp = 1u; }
+                    if (v2[i] > best) { best = v2[i]; bp = 2u; }
+                    if (v3[i] > best) { best = v3[i]; bp = 3u; }
+                    o[i] = best + bias_s[c0 + i];
+                    pos4[i >> 2] |= bp << (8 * (i & 3));
+                }
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(zrow + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                    if (arow) *reinterpret_cast<uint4*>(arow + c0) = make_uint4(pos4[0], pos4[1], pos4[2], pos4[3]);
+                }
+            }
+            tc_fence_before();
+        };
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = a_buf0 + (it & 1u) * C0T_ABUF;
+            const long long q = (long long)tile * C0T_PX + r;
+            // ---- BN-applied 4 x 4 x 2 input patch of this pooled pixel (zero outside the image = conv padding)
+            float u0[4][4], u1[4][4];
+            if (q < p.npix) {
+                const int px = (int)(q % W2);
+                const long long t = q / W2;
+                const int py = (int)(t % H2), n = (int)(t / H2);
+                const float* img = p.feat + (long long)n * p.H * p.W;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int y = 2 * py - 1 + i;
+                    const bool yok = y >= 0 && y < p.H;
+                    const float e1 = yok ? fmaf(c0t_freq_enc(y, p.H), sc1, sh1) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int x = 2 * px - 1 + j;
+                        const bool ok = yok && x >= 0 && x < p.W;
+                        u0[i][j] = ok ? fmaf(__ldg(img + (long long)y * p.W + x), sc0, sh0) : 0.f;
+                        u1[i][j] = ok ? e1 : 0.f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) u0[i][j] = u1[i][j] = 0.f;
+            }
+#pragma unroll
+            for (int pos = 0; pos < 4; ++pos) {
+                const int sy = pos >> 1, sx = pos & 1;
+                float v[18];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        v[dy * 3 + dx] = u0[sy + dy][sx + dx];
+                        v[9 + dy * 3 + dx] = u1[sy + dy][sx + dx];
+                    }
+                write_k_row(buf + (uint32_t)pos * C0T_POS, r, v, p.planes);
+            }
+            fence_async_smem();                                // generic-proxy writes -> visible to the tensor core
+            // the accumulators of the previous tile must be drained before this tile's MMAs overwrite them
+            if (it > 0) epilogue(prev_q, (it - 1u) & 1u);
+            mbar_arrive(b_afull + 8u * (it & 1u));
+            prev_q = q;
+        }
+        if (it > 0) epilogue(prev_q, (it - 1u) & 1u);
+    } else {
+        // ---- MMA issuer: the whole warp walks the tiles, one elected lane issues
+        const uint32_t idesc = make_idesc(C0T_PX, p.BN, 0, 0);
+        const uint32_t d_lo = 1u << 16;
+        const uint32_t d_hi = ((512u >> 4) & 0x3FFFu) | (1u << 14) | (4u << 29);       // SBO = 8 rows x 64 B, SWIZZLE_64B
+        const uint64_t b_desc = ((uint64_t)d_hi << 32) | (d_lo | ((b_tile & 0x3FFFFu) >> 4));
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = a_buf0 + (it & 1u) * C0T_ABUF;
+            mbar_wait(b_afull + 8u * (it & 1u), (it >> 1) & 1u);
+            tc_fence_after();
+            if (umma::elect_one()) {
+                const uint64_t a_desc = ((uint64_t)d_hi << 32) | (d_lo | ((buf & 0x3FFFFu) >> 4));
+                bool ok = true;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {        // window positions {0, 1} then {2, 3}: two "row tiles" per block
+                    const uint64_t a2 = a_desc + (uint64_t)(half * 2) * (C0T_POS >> 4);
+                    const uint32_t d2 = tmem_base + (uint32_t)(half * 2 * p.BN);
+                    ok = ok && (p.planes == 2
+                        ? umma::umma_stage_x3(d2, (uint32_t)p.BN, a2, C0T_POS >> 4, C0T_PLANE >> 4, 0u, b_desc, 0u, w_plane >> 4,
+                                              idesc, 0u, 2, 2, 1)
+                        : umma::umma_stage_x1(d2, (uint32_t)p.BN, a2, C0T_POS >> 4, C0T_PLANE >> 4, 0u, b_desc, 0u, w_plane >> 4,
+                                              idesc, 0u, 2, 2, 1));
+                }
+                if (!ok) __trap();
+                umma_commit(b_acc);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+    (void)lane;
+}
+
+}  // namespace
+
+bool conv0_tc_supported(const Geo& gp) { return gp.Cs <= 128 && gp.Cs % 16 == 0 && gp.C * 18 < (1 << 30); }
+
+int conv0_tc_forward(int precision, const float* feat, int N, int H, int W, const float* scale, const float* shift,
+                     const float* w, const float* b, float* zp, unsigned char* amax, const Geo& gp, cudaStream_t s) {
+    FSB_REQUIRE(gp.H == H / 2 && gp.W == W / 2 && gp.N == N, "conv0_tc: geometry mismatch");
+    FSB_REQUIRE(conv0_tc_supported(gp) && (precision == 1 || precision == 2), "conv0_tc: unsupported shape / precision");
+    Conv0TcParams p;
+    p.feat = feat; p.N = N; p.H = H; p.W = W;
+    p.scale = scale; p.shift = shift; p.w = w; p.b = b;
+    p.zp = zp; p.amax = amax; p.gp = gp;
+    p.BN = gp.Cs;
+    p.planes = precision == 1 ? 2 : 1;
+    p.npix = (long long)N * gp.H * gp.W;
+    p.ntiles = (int)((p.npix + C0T_PX - 1) / C0T_PX);
+    const size_t smem = 1024 + 2 * (size_t)C0T_ABUF + 2 * 128 * 64 + 64 + 128 * sizeof(float) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FSB_CUDA(cudaFuncSetAttribute(conv0_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int sms = 0, dev = 0;
+    FSB_CUDA(cudaGetDevice(&dev));
+    FSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    conv0_tc_fwd_kernel<<<grid, C0T_THREADS, smem, s>>>(p);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace fsb

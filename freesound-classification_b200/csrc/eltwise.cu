@@ -342,6 +342,11 @@ __device__ __forceinline__ float4 prelu4(float4 y, float4 a) {
     return make_float4(prelu1(y.x, a.x), prelu1(y.y, a.y), prelu1(y.z, a.z), prelu1(y.w, a.w));
 }
 
+__device__ __forceinline__ Dropout resolve_seed(Dropout dr) {
+    if (dr.p > 0.f && dr.seed_ptr) dr.seed = *dr.seed_ptr;
+    return dr;
+}
+
 __device__ __forceinline__ float keep_scale(Dropout dr, long long elem) {
     // counter-based hash (splitmix64 finaliser) -> uniform in [0,1)
     unsigned long long h = dr.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(elem + 1);
@@ -395,8 +400,9 @@ __device__ __forceinline__ float4 fwd_compute(const FwdIn& in, const Coef4& cb, 
 
 template <bool STATS>
 __global__ void __launch_bounds__(256)
-bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr, void* a_mma,
+bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr_in, void* a_mma,
                   int fmt, float* a_f32, double* out_stats) {
+    const Dropout dr = resolve_seed(dr_in);
     EW_PROLOGUE
     if (!STATS && !cok) return;
     Acc4 acc[2];
@@ -795,8 +801,9 @@ __device__ __forceinline__ void fma4(float4& a, const float4& b, const float4& c
 template <bool RES, bool DA2>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2,
-                         const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr,
+                         const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr_in,
                          double* partials) {
+    const Dropout dr = resolve_seed(dr_in);
     EW_PROLOGUE
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
     float4 mx = s0, zx = s0;              // max |dy|, max |zhat|: bound of |dz| for the half-precision gradient scale
@@ -885,8 +892,9 @@ int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, in
 template <bool RES, bool DA2>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2, const float* __restrict__ z,
-                        Geo g, BnCoef bn, Residual res, Dropout dr, const float* c1, const float* c2, void* dz,
+                        Geo g, BnCoef bn, Residual res, Dropout dr_in, const float* c1, const float* c2, void* dz,
                         int fmt, float* dres, const unsigned* absmax) {
+    const Dropout dr = resolve_seed(dr_in);
     EW_PROLOGUE
     if (!cok) return;
     const float gscale = gs_scale(absmax);

@@ -26,6 +26,8 @@ struct Residual {          // identity branch r = prelu(zr*scale+shift, slope); 
 struct Dropout {           // keep mask = hash(seed, element) >= p ; scale 1/(1-p); p == 0 = off
     float p;
     unsigned long long seed;
+    const unsigned long long* seed_ptr;   // optional DEVICE location of the seed (overrides `seed`): lets a captured
+                                          // CUDA graph pick up a fresh seed on every replay
 };
 
 // number of pixel-blocks an element-wise reduction over `g` uses (partials are [nblk][K][Cs] doubles)

@@ -19,6 +19,7 @@
 #include "conv0.cuh"
 #include "eltwise.cuh"
 #include "gemm.cuh"
+#include "rnn.cuh"
 
 using namespace fsb;
 
@@ -29,6 +30,8 @@ enum { P_BNIN_W = 0, P_BNIN_B, P_CONV_W, P_CONV_B, P_BNA_W, P_BNA_B, P_PRELUA, P
        P_PER_BLOCK };
 enum { H_BN0_W = 0, H_BN0_B, H_L1_W, H_L1_B, H_BN2_W, H_BN2_B, H_PRELU, H_L5_W, H_L5_B, H_COUNT };
 enum { B_IN = 0, B_A, B_1, B_2, B_3, B_PER_BLOCK };
+enum { R_PER_HEAD = 10 };      // rnn head parameters: ln.w ln.b, then (w_ih w_hh b_ih b_hh) x {forward, reverse}
+enum { RNN_SIZE = 128 };
 
 enum Cat { CAT_FEAT = 0, CAT_GEMM_FWD, CAT_GEMM_DGRAD, CAT_GEMM_WGRAD, CAT_CONV0, CAT_ELT_FWD, CAT_ELT_BWD,
            CAT_HEAD, CAT_PACK, CAT_COUNT };
@@ -68,6 +71,9 @@ struct BlockPlan {
     void* gmax_scratch;
     unsigned char *mask, *mask_in;
     int head_off;        // column offset in the concatenated head input, -1 if no head
+    int rnn_index;       // aggregation_type == "rnn": index of this block's head among the rnn heads, else -1
+    RnnHead rnn;
+    void* pk_rnn[2];     // packed W_ih / b_ih per direction
     // backward
     float *d_out, *da2, *da1, *dr0a, *dr0b, *dzp, *du;
     void *dz3, *dz2, *dz1, *dzf;
@@ -80,6 +86,8 @@ struct fsb_net {
     std::vector<float> fb_vals;
     std::vector<int> fb_off, fb_start, fb_len;
     int D, Ds, CsCls;
+    int n_rnn = 0;              // rnn heads (0 for aggregation_type == "max")
+    int head_param_base = 0;    // index of the first FC-head parameter (after the blocks and the rnn heads)
     std::vector<long long> param_numel, param_offset;
     long long total_params;
 
@@ -89,6 +97,20 @@ struct fsb_net {
     int N = 0, T = 0, training = 0, frames = 0;
     bool tables_ready = false, fwd_done = false;
     bool overlap = true;        // side-stream overlap of weight packing / weight-gradient GEMMs (fsb_net_set_overlap)
+    bool conv0_tc = true;       // block-0 entry conv on the tensor cores (FSB200_CONV0_TC=0: CUDA-core direct conv)
+    // CUDA graphs: the launch sequence of a forward (or backward) call with a given set of pointers / shapes is captured
+    // on its second occurrence and replayed afterwards (~130 launches become one cudaGraphLaunch).
+    bool graphs = true;         // FSB200_GRAPHS=0 / fsb_net_set_graphs(net, 0): always launch eagerly
+    struct GraphEntry { unsigned long long key; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
+    std::vector<GraphEntry> graph_cache;
+    std::vector<unsigned long long> seen_keys;      // keys met once (captured on the next occurrence)
+    unsigned long long graph_clock = 0;
+    unsigned long long* d_seed = nullptr;           // device copy of the dropout seed (kernels read it through a pointer)
+    // Stream capture is not allowed on the legacy default stream (torch's default current stream), so with graphs enabled
+    // the plan executes on its own non-blocking stream, forked from / joined to the caller's stream with events: the
+    // caller still sees plain stream semantics.
+    cudaStream_t exec_stream = nullptr;
+    cudaEvent_t exec_in = nullptr, exec_out = nullptr;
     unsigned long long dropout_seed = 0;
 
     // carved buffers
@@ -99,6 +121,8 @@ struct fsb_net {
     float* feat;          // 2D: (N, F, frames) plain
     double* partials;     // shared reduction scratch
     void* wgrad_scratch;
+    void* rnn_scratch = nullptr;    // split-reduction scratch of the rnn heads' weight gradients (main stream; the conv
+                                    // weight gradients own wgrad_scratch on the side stream)
     float *feats, *h0, *z1h, *h1, *zl, *dzl, *dh1, *dz1h, *dh0, *dfeats;
     BnBuf hbn0, hbn2;
     ConvGeom lin1, lin5;
@@ -142,6 +166,15 @@ void build_param_table(fsb_net* net) {
                                     conv_numel(d, d, 1), d, d, d, d, d, d};
         for (int i = 0; i < P_PER_BLOCK; ++i) net->param_numel.push_back(v[i]);
     }
+    // rnn heads sit between the conv blocks and the FC head (module registration order of the reference: conv_modules,
+    // rnns, output_transform); per head LayerNorm weight / bias, then the GRU tensors in named_parameters() order
+    for (int k = c.start_deep_supervision_on; k < c.num_blocks && c.aggregation == 1; ++k) {
+        long long d = c.depth[k];
+        long long v[R_PER_HEAD] = {d, d, 3 * RNN_SIZE * d, 3 * RNN_SIZE * RNN_SIZE, 3 * RNN_SIZE, 3 * RNN_SIZE,
+                                   3 * RNN_SIZE * d, 3 * RNN_SIZE * RNN_SIZE, 3 * RNN_SIZE, 3 * RNN_SIZE};
+        for (int i = 0; i < R_PER_HEAD; ++i) net->param_numel.push_back(v[i]);
+    }
+    net->head_param_base = (int)net->param_numel.size();
     long long D = net->D;
     long long h[H_COUNT] = {D, D, D * D, D, D, D, D, (long long)c.n_classes * D, c.n_classes};
     for (int i = 0; i < H_COUNT; ++i) net->param_numel.push_back(h[i]);
@@ -183,7 +216,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
 
     net->blocks.assign(c.num_blocks, BlockPlan());
     size_t max_partials = (size_t)plain_stats_blocks() * 2 * 16;
-    size_t max_wgrad = 0;
+    size_t max_wgrad = 0, max_rnn = 0;
     int Hin = c.two_d ? c.n_features : 1, Win = frames;
     int head_off = 0;
     for (int k = 0; k < c.num_blocks; ++k) {
@@ -232,15 +265,27 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
         B.a2 = b.take_bytes(pe * 4);
         B.z3 = b.take<float>(pe);
         B.out = b.take<float>(pe);
-        if (k >= c.start_deep_supervision_on) {
+        B.rnn_index = -1;
+        B.argrow = nullptr;
+        B.gmax_scratch = nullptr;
+        if (k >= c.start_deep_supervision_on && c.aggregation == 1) {
+            B.head_off = head_off;
+            head_off += 2 * RNN_SIZE;
+            B.rnn_index = k - c.start_deep_supervision_on;
+            float* base_f = b.take<float>(rnn_head_floats(N, B.g.W, B.g.Cs, training));
+            rnn_head_carve(B.rnn, base_f, N, B.g.H, B.g.W, B.C, B.g.Cs, training);
+            for (int d = 0; d < 2; ++d) B.pk_rnn[d] = b.take_bytes(rnn_packed_bytes(B.C));
+            if (training) {
+                max_rnn = std::max(max_rnn, simt_wgrad_scratch_bytes(B.rnn.g_ih));
+                max_rnn = std::max(max_rnn, simt_wgrad_scratch_bytes(B.rnn.g_hh));
+            }
+        } else if (k >= c.start_deep_supervision_on) {
             B.head_off = head_off;
             head_off += B.C;
             B.argrow = b.take<int>((size_t)N * B.C);
             B.gmax_scratch = b.take_bytes(gmax_scratch_bytes(B.g));
         } else {
             B.head_off = -1;
-            B.argrow = nullptr;
-            B.gmax_scratch = nullptr;
         }
         if (training) {
             B.d_out = b.take<float>(pe);
@@ -297,7 +342,9 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
         max_partials = std::max(max_partials, (size_t)256 * 2 * net->blocks[k].g.Cs);   // one record per GEMM CTA
     net->partials = b.take<double>(max_partials);
     net->wgrad_scratch = b.take_bytes(max_wgrad + 256);
+    net->rnn_scratch = max_rnn ? b.take_bytes(max_rnn + 256) : nullptr;
     net->gscale = b.take<unsigned>((size_t)c.num_blocks * B_PER_BLOCK);
+    net->d_seed = b.take<unsigned long long>(1);
     return align_up(b.off, 256);
 }
 
@@ -339,7 +386,7 @@ double conv_flops(const ConvGeom& c, const Geo& g) { return 2.0 * c.Cin * c.Cout
     } while (0)
 
 const Residual kNoRes = {nullptr, nullptr, nullptr, nullptr};
-const Dropout kNoDrop = {0.f, 0ull};
+const Dropout kNoDrop = {0.f, 0ull, nullptr};
 
 // finalize a BatchNorm from `nblk` partial records already sitting in net->partials (training) or from the
 // running statistics (eval)
@@ -380,20 +427,40 @@ extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, c
         net->fb_start.assign(fb_start, fb_start + n_mel);
         net->fb_len.assign(fb_len, fb_len + n_mel);
     }
+    FSB_REQUIRE(cfg->aggregation == 0 || (cfg->aggregation == 1 && cfg->two_d),
+                "net_create: aggregation must be 0 (max) or 1 (rnn, 2D model only)");
     net->D = 0;
-    for (int k = cfg->start_deep_supervision_on; k < cfg->num_blocks; ++k) net->D += cfg->depth[k];
+    for (int k = cfg->start_deep_supervision_on; k < cfg->num_blocks; ++k)
+        net->D += cfg->aggregation == 1 ? 2 * RNN_SIZE : cfg->depth[k];
+    net->n_rnn = cfg->aggregation == 1 ? cfg->num_blocks - cfg->start_deep_supervision_on : 0;
     net->Ds = round_up(net->D, 16);
     net->CsCls = round_up(cfg->n_classes, 16);
     build_param_table(net);
     net->overlap = getenv("FSB200_NO_OVERLAP") == nullptr;      // read once; fsb_net_set_overlap changes it later
+    {
+        const char* e = getenv("FSB200_CONV0_TC");
+        net->conv0_tc = !(e && atoi(e) == 0);
+        e = getenv("FSB200_GRAPHS");
+        net->graphs = !(e && atoi(e) == 0);
+    }
     *out = net;
     return 0;
 }
 
+static void drop_graphs(fsb_net* net) {
+    for (auto& g : net->graph_cache) cudaGraphExecDestroy(g.exec);
+    net->graph_cache.clear();
+    net->seen_keys.clear();
+}
+
 extern "C" void fsb_net_destroy(fsb_net* net) {
     if (!net) return;
+    drop_graphs(net);
     for (cudaEvent_t e : net->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : net->fork_events) cudaEventDestroy(e);
+    if (net->exec_in) cudaEventDestroy(net->exec_in);
+    if (net->exec_out) cudaEventDestroy(net->exec_out);
+    if (net->exec_stream) cudaStreamDestroy(net->exec_stream);
     if (net->join_event) cudaEventDestroy(net->join_event);
     if (net->pack_event) cudaEventDestroy(net->pack_event);
     if (net->side) cudaStreamDestroy(net->side);
@@ -439,6 +506,7 @@ static int bind(fsb_net* net, void* ws, size_t ws_bytes, int n, int t, int train
         return FSB_E_WORKSPACE;
     }
     carve(net, (char*)ws, n, t, training);
+    drop_graphs(net);          // captured launch sequences point into the previous carving
     net->ws = ws; net->ws_bytes = ws_bytes; net->N = n; net->T = t; net->training = training;
     net->fwd_done = false;
     // zero once: GEMM inputs rely on zero borders / zero channel tails, which the element-wise
@@ -470,14 +538,155 @@ static int ensure_side_stream(fsb_net* net) {
     return 0;
 }
 
+// ---- CUDA-graph replay of a launch sequence ------------------------------------------------------------------------
+namespace {
+
+__global__ void set_seed_kernel(unsigned long long* dst, unsigned long long v) { *dst = v; }
+
+struct KeyHash {
+    unsigned long long h = 1469598103934665603ull;
+    void add(const void* p, size_t bytes) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    }
+    template <typename T> void add(const T& v) { add(&v, sizeof(T)); }
+};
+
+// Runs `body` (which only enqueues work on `s` and on the plan's side stream) either eagerly or as a captured graph:
+// a key seen for the first time runs eagerly (one-off shapes never pay for a capture, and every lazy initialisation --
+// streams, function attributes, tensor maps -- happens outside capture); its second occurrence is captured and
+// instantiated; later occurrences replay the graph.
+template <typename Body>
+int run_graphed(fsb_net* net, unsigned long long key, cudaStream_t caller, Body body) {
+    if (!net->graphs || net->profiling) return body(caller);
+    if (!net->exec_stream) {
+        FSB_CUDA(cudaStreamCreateWithFlags(&net->exec_stream, cudaStreamNonBlocking));
+        FSB_CUDA(cudaEventCreateWithFlags(&net->exec_in, cudaEventDisableTiming));
+        FSB_CUDA(cudaEventCreateWithFlags(&net->exec_out, cudaEventDisableTiming));
+    }
+    cudaStream_t s = net->exec_stream;
+    FSB_CUDA(cudaEventRecord(net->exec_in, caller));
+    FSB_CUDA(cudaStreamWaitEvent(s, net->exec_in, 0));
+    auto finish = [&](int rc) -> int {
+        if (rc != 0) return rc;
+        FSB_CUDA(cudaEventRecord(net->exec_out, s));
+        FSB_CUDA(cudaStreamWaitEvent(caller, net->exec_out, 0));
+        return 0;
+    };
+    ++net->graph_clock;
+    for (auto& g : net->graph_cache)
+        if (g.key == key) {
+            g.stamp = net->graph_clock;
+            FSB_CUDA(cudaGraphLaunch(g.exec, s));
+            g_launch_count += g.launches;
+            return finish(0);
+        }
+    bool seen = false;
+    for (unsigned long long k : net->seen_keys) seen = seen || k == key;
+    if (!seen) {
+        if (net->seen_keys.size() > 256) net->seen_keys.clear();
+        net->seen_keys.push_back(key);
+        return finish(body(s));
+    }
+    const long long before = g_launch_count;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        net->graphs = false;              // capture is not possible in this context: stay eager from here on
+        return finish(body(s));
+    }
+    const int rc = body(s);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != 0) return rc;
+        net->graphs = false;
+        return finish(body(s));
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !exec) {
+        cudaGetLastError();
+        net->graphs = false;
+        return finish(body(s));
+    }
+    if (net->graph_cache.size() >= 16) {          // evict the least recently used sequence
+        size_t victim = 0;
+        for (size_t i = 1; i < net->graph_cache.size(); ++i)
+            if (net->graph_cache[i].stamp < net->graph_cache[victim].stamp) victim = i;
+        cudaGraphExecDestroy(net->graph_cache[victim].exec);
+        net->graph_cache.erase(net->graph_cache.begin() + victim);
+    }
+    net->graph_cache.push_back({key, exec, g_launch_count - before, net->graph_clock});
+    FSB_CUDA(cudaGraphLaunch(exec, s));
+    return finish(0);
+}
+
+}  // namespace
+
+static int forward_impl(fsb_net* net, const float* signal, const float* features, int n, int t, long long signal_stride,
+                        const float* const* params, float* const* bn_mean, float* const* bn_var,
+                        long long* const* bn_count, int training, unsigned long long dropout_seed, float* logits,
+                        cudaStream_t s);
+
+static int forward_entry(fsb_net* net, const float* signal, const float* features, int n, int t, long long signal_stride,
+                         const float* const* params, float* const* bn_mean, float* const* bn_var,
+                         long long* const* bn_count, int training, unsigned long long dropout_seed, void* workspace,
+                         size_t workspace_bytes, float* logits, void* stream);
+
 extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, long long signal_stride,
                                const float* const* params, float* const* bn_mean, float* const* bn_var,
                                long long* const* bn_count, int training, unsigned long long dropout_seed,
                                void* workspace, size_t workspace_bytes, float* logits, void* stream) {
-    FSB_REQUIRE(net && signal && params && bn_mean && bn_var && workspace && logits, "net_forward: null argument");
+    FSB_REQUIRE(signal, "net_forward: null signal");
+    return forward_entry(net, signal, nullptr, n, t, signal_stride, params, bn_mean, bn_var, bn_count, training, dropout_seed,
+                         workspace, workspace_bytes, logits, stream);
+}
+
+extern "C" int fsb_net_forward_features(fsb_net* net, const float* features, int n, int t, const float* const* params,
+                                        float* const* bn_mean, float* const* bn_var, long long* const* bn_count,
+                                        int training, unsigned long long dropout_seed, void* workspace,
+                                        size_t workspace_bytes, float* logits, void* stream) {
+    FSB_REQUIRE(features, "net_forward_features: null features");
+    return forward_entry(net, nullptr, features, n, t, 0, params, bn_mean, bn_var, bn_count, training, dropout_seed, workspace,
+                         workspace_bytes, logits, stream);
+}
+
+static int forward_entry(fsb_net* net, const float* signal, const float* features, int n, int t, long long signal_stride,
+                         const float* const* params, float* const* bn_mean, float* const* bn_var,
+                         long long* const* bn_count, int training, unsigned long long dropout_seed, void* workspace,
+                         size_t workspace_bytes, float* logits, void* stream) {
+    FSB_REQUIRE(net && params && bn_mean && bn_var && workspace && logits, "net_forward: null argument");
     cudaStream_t s = (cudaStream_t)stream;
     FSB_TRY(fsb_device_ok());
     FSB_TRY(bind(net, workspace, workspace_bytes, n, t, training ? 1 : 0, s));
+    net->fwd_done = false;
+    // the dropout seed changes every call: it travels through device memory, outside the replayed sequence
+    set_seed_kernel<<<1, 1, 0, s>>>(net->d_seed, dropout_seed);
+    FSB_LAUNCHED();
+    KeyHash k;
+    const int np = fsb_net_num_params(net), nb = fsb_net_num_bn(net);
+    k.add(signal); k.add(features); k.add(n); k.add(t); k.add(signal_stride); k.add(training); k.add(logits);
+    k.add(workspace); k.add(net->overlap); k.add(1);
+    k.add(params, sizeof(float*) * np);
+    k.add(bn_mean, sizeof(float*) * nb);
+    k.add(bn_var, sizeof(float*) * nb);
+    if (bn_count) k.add(bn_count, sizeof(long long*) * nb);
+    FSB_TRY(run_graphed(net, k.h, s, [&](cudaStream_t es) {
+        return forward_impl(net, signal, features, n, t, signal_stride, params, bn_mean, bn_var, bn_count, training,
+                            dropout_seed, logits, es);
+    }));
+    net->fwd_done = true;
+    return 0;
+}
+
+// features != nullptr: log features (N, n_features, frames) computed earlier (fsb_feat_forward) replace the feature kernel
+static int forward_impl(fsb_net* net, const float* signal, const float* features, int n, int t, long long signal_stride,
+                        const float* const* params, float* const* bn_mean, float* const* bn_var,
+                        long long* const* bn_count, int training, unsigned long long dropout_seed, float* logits,
+                        cudaStream_t s) {
     const fsb_net_config& c = net->cfg;
     const int prec = net->prec_f, fmt = act_fmt(prec);
     net->recs.clear();
@@ -505,7 +714,7 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
             RUN_S(ps, CAT_PACK, 0, pack_weights(prec, P[P_C3_W], P[P_C3_B], B.c3, B.pk3, ps));
         }
         {
-            const float* const* P = params + (size_t)c.num_blocks * P_PER_BLOCK;
+            const float* const* P = params + net->head_param_base;
             RUN_S(ps, CAT_HEAD, 0, simt_pack_weights(P[H_L1_W], P[H_L1_B], net->lin1, net->pk_l1, ps));
             RUN_S(ps, CAT_HEAD, 0, simt_pack_weights(P[H_L5_W], P[H_L5_B], net->lin5, net->pk_l5, ps));
         }
@@ -530,10 +739,14 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
         auto cnt = [&](int i) { return CT ? CT[i] : nullptr; };
 
         if (c.two_d && k == 0) {
-            RUN(CAT_FEAT, 0, fsb_feat_forward(signal, n, signal_stride, t, c.n_fft, c.hop, c.feat_mode, 1e-4f,
-                                              c.n_features, net->d_fb_vals, net->d_fb_off, net->d_fb_start,
-                                              net->d_fb_len, net->feat_tables, net->feat,
-                                              (long long)c.n_features * frames, frames, 1, s));
+            if (features)
+                FSB_CUDA(cudaMemcpyAsync(net->feat, features, (size_t)n * c.n_features * frames * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, s));
+            else
+                RUN(CAT_FEAT, 0, fsb_feat_forward(signal, n, signal_stride, t, c.n_fft, c.hop, c.feat_mode, 1e-4f,
+                                                  c.n_features, net->d_fb_vals, net->d_fb_off, net->d_fb_start,
+                                                  net->d_fb_len, net->feat_tables, net->feat,
+                                                  (long long)c.n_features * frames, frames, 1, s));
             long long cnt0 = (long long)n * c.n_features * frames;
             if (training) {
                 RUN(CAT_ELT_FWD, 0, plain_stats(net->feat, cnt0, net->partials, s));
@@ -542,17 +755,25 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
             RUN(CAT_ELT_FWD, 0, bn_finalize(net->partials, plain_stats_blocks(), cnt0, P[P_BNIN_W], P[P_BNIN_B],
                                             RM[B_IN], RV[B_IN], cnt(B_IN), training, 2, 16, B.bn_in.scale,
                                             B.bn_in.shift, B.bn_in.mean, B.bn_in.invstd, s));
-            RUN(CAT_CONV0, 2.0 * 2 * B.C * 9 * (double)n * c.n_features * frames,
-                conv0_forward(net->feat, n, c.n_features, frames, B.bn_in.scale, B.bn_in.shift, P[P_CONV_W],
-                              P[P_CONV_B], B.zp, training ? net->conv0_amax : nullptr, B.g, s));
+            if (prec != 0 && net->conv0_tc && conv0_tc_supported(B.g))
+                RUN(CAT_CONV0, 2.0 * 2 * B.C * 9 * (double)n * c.n_features * frames,
+                    conv0_tc_forward(prec, net->feat, n, c.n_features, frames, B.bn_in.scale, B.bn_in.shift, P[P_CONV_W],
+                                     P[P_CONV_B], B.zp, training ? net->conv0_amax : nullptr, B.g, s));
+            else
+                RUN(CAT_CONV0, 2.0 * 2 * B.C * 9 * (double)n * c.n_features * frames,
+                    conv0_forward(net->feat, n, c.n_features, frames, B.bn_in.scale, B.bn_in.shift, P[P_CONV_W],
+                                  P[P_CONV_B], B.zp, training ? net->conv0_amax : nullptr, B.g, s));
         } else {
             if (k == 0) {
                 // 1D: features land directly in the padded-flat block input (channels = STFT bins)
                 float* dst = B.x_in + geo_row(B.g_in, 0, 0, 0) * B.g_in.Cs;
-                RUN(CAT_FEAT, 0, fsb_feat_forward(signal, n, signal_stride, t, c.n_fft, c.hop, c.feat_mode, 1e-4f,
-                                                  c.n_features, net->d_fb_vals, net->d_fb_off, net->d_fb_start,
-                                                  net->d_fb_len, net->feat_tables, dst,
-                                                  (long long)B.g_in.Hp * B.g_in.Wp * B.g_in.Cs, 1, B.g_in.Cs, s));
+                if (features)       // (N, F, frames) = NCHW with H = 1: transpose into the padded-flat block input
+                    RUN(CAT_FEAT, 0, nchw_to_pf(features, B.g_in, B.x_in, FMT_F32, s));
+                else
+                    RUN(CAT_FEAT, 0, fsb_feat_forward(signal, n, signal_stride, t, c.n_fft, c.hop, c.feat_mode, 1e-4f,
+                                                      c.n_features, net->d_fb_vals, net->d_fb_off, net->d_fb_start,
+                                                      net->d_fb_len, net->feat_tables, dst,
+                                                      (long long)B.g_in.Hp * B.g_in.Wp * B.g_in.Cs, 1, B.g_in.Cs, s));
                 FSB_TRY(bn_forward_stats(net, s, B.x_in, B.g_in, B.bn_in, P[P_BNIN_W], P[P_BNIN_B], RM[B_IN], RV[B_IN],
                                          cnt(B_IN), training, CAT_ELT_FWD));
             } else {
@@ -602,13 +823,17 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
         RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z3, B.g, B.bn3.coef(P[P_PRELU3]), res, kNoDrop, nullptr, fmt, B.out,
                                            next_stats ? net->partials : nullptr, s));
         carried_nblk = ew_num_blocks(B.g);
-        if (B.head_off >= 0)
+        if (B.rnn_index >= 0) {
+            const float* const* PR = params + (size_t)c.num_blocks * P_PER_BLOCK + (size_t)B.rnn_index * R_PER_HEAD;
+            RUN(CAT_HEAD, 0, rnn_head_forward(B.rnn, B.out, B.g, PR, B.pk_rnn, net->feats, net->Ds, B.head_off, training, s));
+        } else if (B.head_off >= 0) {
             RUN(CAT_ELT_FWD, 0, gmax_forward(B.out, B.g, net->feats, net->Ds, B.head_off, B.argrow, B.gmax_scratch, s));
+        }
     }
 
     // ---- FC head (float32 CUDA-core GEMMs in every precision mode)
     {
-        const float* const* P = params + (size_t)c.num_blocks * P_PER_BLOCK;
+        const float* const* P = params + net->head_param_base;
         float* const* RM = bn_mean + (size_t)c.num_blocks * B_PER_BLOCK;
         float* const* RV = bn_var + (size_t)c.num_blocks * B_PER_BLOCK;
         long long* const* CT = bn_count ? bn_count + (size_t)c.num_blocks * B_PER_BLOCK : nullptr;
@@ -620,13 +845,12 @@ extern "C" int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, 
         RUN(CAT_HEAD, 0, simt_skinny_fwd(net->h0, net->pk_l1, net->z1h, net->lin1, net->head_scratch, s));
         FSB_TRY(bn_forward_stats(net, s, net->z1h, net->g_head, net->hbn2, P[H_BN2_W], P[H_BN2_B], RM[1], RV[1],
                                  CT ? CT[1] : nullptr, training, CAT_HEAD));
-        Dropout dr = {training ? c.dropout_p : 0.f, dropout_seed};
+        Dropout dr = {training ? c.dropout_p : 0.f, dropout_seed, net->d_seed};
         RUN(CAT_HEAD, 0, bn_act_forward(net->z1h, net->g_head, net->hbn2.coef(P[H_PRELU]), kNoRes, dr, nullptr,
                                         FMT_F32, net->h1, nullptr, s));
         RUN(CAT_HEAD, 0, simt_skinny_fwd(net->h1, net->pk_l5, net->zl, net->lin5, net->head_scratch, s));
         RUN(CAT_HEAD, 0, copy2d(net->zl, n, c.n_classes, net->CsCls, logits, c.n_classes, s));
     }
-    net->fwd_done = true;
     return 0;
 }
 
@@ -644,6 +868,8 @@ static int bn_backward(fsb_net* net, cudaStream_t s, const float* dA1, const flo
     return 0;
 }
 
+static int backward_impl(fsb_net* net, const float* dlogits, const float* const* params, float* grads, cudaStream_t s);
+
 extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float* const* params, float* grads,
                                 void* workspace, size_t workspace_bytes, void* stream) {
     FSB_REQUIRE(net && dlogits && params && grads && workspace, "net_backward: null argument");
@@ -652,6 +878,14 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
         return FSB_E_STATE;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    FSB_TRY(ensure_side_stream(net));
+    KeyHash k;
+    k.add(dlogits); k.add(grads); k.add(workspace); k.add(net->overlap); k.add(2);
+    k.add(params, sizeof(float*) * fsb_net_num_params(net));
+    return run_graphed(net, k.h, s, [&](cudaStream_t es) { return backward_impl(net, dlogits, params, grads, es); });
+}
+
+static int backward_impl(fsb_net* net, const float* dlogits, const float* const* params, float* grads, cudaStream_t s) {
     const fsb_net_config& c = net->cfg;
     // gradient planes carry hi + lo only when the backward GEMMs form three products; the forward activations read by
     // the weight-gradient GEMMs always have their hi plane
@@ -687,13 +921,13 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
 
     // ---- head
     {
-        const int hb = c.num_blocks * P_PER_BLOCK;
+        const int hb = net->head_param_base;
         const float* const* P = params + hb;
         RUN(CAT_HEAD, 0, copy2d(dlogits, n, c.n_classes, c.n_classes, net->dzl, net->CsCls, s));
         RUN(CAT_HEAD, 0, colsum(dlogits, n, c.n_classes, c.n_classes, G(hb + H_L5_B), s));
         RUN(CAT_HEAD, 0, simt_wgrad(net->h1, net->dzl, G(hb + H_L5_W), net->wgrad_scratch, net->lin5, s));
         RUN(CAT_HEAD, 0, simt_skinny_dgrad(net->dzl, net->pk_l5, net->dh1, net->lin5, net->head_scratch, s));
-        Dropout dr = {c.dropout_p, net->dropout_seed};
+        Dropout dr = {c.dropout_p, net->dropout_seed, net->d_seed};
         FSB_TRY(bn_backward(net, s, net->dh1, nullptr, net->z1h, net->g_head, net->hbn2, P[H_PRELU], kNoRes, dr,
                             G(hb + H_BN2_W), G(hb + H_BN2_B), G(hb + H_PRELU), net->dz1h, FMT_F32, nullptr, nullptr, CAT_HEAD));
         RUN(CAT_HEAD, 0, simt_wgrad(net->h0, net->dz1h, G(hb + H_L1_W), net->wgrad_scratch, net->lin1, s));
@@ -709,8 +943,15 @@ extern "C" int fsb_net_backward(fsb_net* net, const float* dlogits, const float*
         const float* const* P = params + pb;
         unsigned* const GS = net->gscale + (size_t)k * B_PER_BLOCK;     // GradScale slots of dz3 / dz2 / dz1 / dzp (-> dzf)
         if (k == c.num_blocks - 1) FSB_CUDA(cudaMemsetAsync(B.d_out, 0, (size_t)B.g.rows * B.g.Cs * 4, s));
-        if (B.head_off >= 0)
+        if (B.rnn_index >= 0) {
+            const int rb = c.num_blocks * P_PER_BLOCK + B.rnn_index * R_PER_HEAD;
+            float* GR[R_PER_HEAD];
+            for (int i = 0; i < R_PER_HEAD; ++i) GR[i] = G(rb + i);
+            RUN(CAT_HEAD, 0, rnn_head_backward(B.rnn, net->dfeats, net->Ds, B.head_off, params + rb, B.pk_rnn, GR, B.d_out,
+                                               B.g, net->rnn_scratch, s));
+        } else if (B.head_off >= 0) {
             RUN(CAT_ELT_BWD, 0, gmax_backward(net->dfeats, net->Ds, B.head_off, B.argrow, B.g, B.d_out, s));
+        }
         // out = prelu3(bn3(z3) + r0)
         Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
         FSB_TRY(bn_backward(net, s, B.d_out, nullptr, B.z3, B.g, B.bn3, P[P_PRELU3], res, kNoDrop, G(pb + P_BN3_W),
@@ -803,6 +1044,13 @@ extern "C" int fsb_net_read_activation(fsb_net* net, int which, float* dst, long
     FSB_REQUIRE(cap >= cnt, "read_activation: destination too small");
     *numel = cnt;
     return pf_to_nchw(B.out, B.g, dst, s);
+}
+
+extern "C" int fsb_net_set_graphs(fsb_net* net, int on) {
+    FSB_REQUIRE(net, "set_graphs: null handle");
+    net->graphs = on != 0;
+    if (!net->graphs) drop_graphs(net);
+    return 0;
 }
 
 extern "C" int fsb_net_set_overlap(fsb_net* net, int on) {

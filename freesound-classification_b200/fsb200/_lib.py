@@ -21,7 +21,7 @@ class NetConfig(ctypes.Structure):
     _fields_ = [("two_d", c_int), ("feat_mode", c_int), ("n_fft", c_int), ("hop", c_int),
                 ("n_features", c_int), ("num_blocks", c_int), ("depth", c_int * MAX_BLOCKS),
                 ("start_deep_supervision_on", c_int), ("n_classes", c_int), ("dropout_p", c_float),
-                ("precision", c_int)]
+                ("precision", c_int), ("aggregation", c_int)]
 
 
 _SIGNATURES = {
@@ -53,10 +53,13 @@ _SIGNATURES = {
     "fsb_net_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "fsb_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_ull, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "fsb_net_forward_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int, c_ull, c_void_p, c_size_t, c_void_p, c_void_p]),
     "fsb_net_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fsb_net_read_activation": (c_int, [c_void_p, c_int, c_void_p, c_ll, ctypes.POINTER(c_ll), c_void_p, c_void_p]),
     "fsb_net_set_profiling": (c_int, [c_void_p, c_int]),
     "fsb_net_set_overlap": (c_int, [c_void_p, c_int]),
+    "fsb_net_set_graphs": (c_int, [c_void_p, c_int]),
     "fsb_net_get_timings": (c_int, [c_void_p, c_int, ctypes.POINTER(c_char_p), ctypes.POINTER(c_float),
                                     ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
     "fsb_launch_count": (c_ll, [c_int]),

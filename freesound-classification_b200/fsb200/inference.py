@@ -118,3 +118,37 @@ def predict_bucketed(model, clips, buckets, max_batch_elems, padding_value=0.0, 
         return out, dict(batches=len(batches), dropped=len(dropped), padded_samples=padded, real_samples=real,
                          padding_overhead=(padded / real - 1.0) if real else 0.0)
     return out
+
+
+def predict_folds(models, clips, buckets, max_batch_elems, padding_value=0.0):
+    """Fold ensemble (predict_2d_cnn.py:111-118 loads one model per fold and averages their probabilities): every padded
+    batch is assembled ONCE, its features are extracted ONCE (they do not depend on the weights) and each fold model runs
+    on the shared features.  Returns the mean sigmoid probability `(n_clips, n_classes)`; clips outside the buckets get
+    NaN rows.  All models must use the same feature descriptor."""
+    descriptors = {m.config.data.features for m in models}
+    if len(descriptors) != 1:
+        raise ValueError("fold models must share one feature descriptor, got %r" % (sorted(descriptors),))
+    lengths = [int(c.numel()) if isinstance(c, torch.Tensor) else len(c) for c in clips]
+    batches, dropped = pack_batches(lengths, buckets, max_batch_elems)
+    rank, world_size = fdist.world()
+    begin, end = fdist.shard_range(len(batches), rank, world_size)
+    first = models[0]
+    device = torch.device(first.device)
+    probs = torch.zeros((len(clips), first.config.data._n_classes), dtype=torch.float32, device=device)
+    for m in models:
+        m.eval()
+    with torch.no_grad():
+        for indices in batches[begin:end]:
+            batch = device_batch(clips, indices, device, padding_value)
+            feats = first.extract_features(batch)
+            acc = None
+            for m in models:
+                p = torch.sigmoid(m.forward_features(feats, batch.shape[1])["class_logits"])
+                acc = p if acc is None else acc + p
+            probs[torch.as_tensor(indices, device=device)] = acc / len(models)
+    if world_size > 1:
+        torch.distributed.all_reduce(probs)
+    out = probs.cpu().numpy()
+    if dropped:
+        out[dropped] = np.nan
+    return out

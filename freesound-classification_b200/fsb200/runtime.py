@@ -192,10 +192,18 @@ BLOCK_BN_PREFIXES = ("0", "3", "5.bn1", "5.bn2", "5.bn3")
 HEAD_BN_PREFIXES = ("0", "2")
 
 
-def canonical_param_names(num_blocks):
+RNN_PARAM_SUFFIXES = ("0.weight", "0.bias",
+                      "1.weight_ih_l0", "1.weight_hh_l0", "1.bias_ih_l0", "1.bias_hh_l0",
+                      "1.weight_ih_l0_reverse", "1.weight_hh_l0_reverse", "1.bias_ih_l0_reverse", "1.bias_hh_l0_reverse")
+
+
+def canonical_param_names(num_blocks, n_rnn=0):
+    """named_parameters() order of the reference's module tree: conv_modules, rnns, output_transform."""
     names = []
     for k in range(num_blocks):
         names += ["conv_modules.%d.%s" % (k, s) for s in BLOCK_PARAM_SUFFIXES]
+    for i in range(n_rnn):
+        names += ["rnns.%d.%s" % (i, s) for s in RNN_PARAM_SUFFIXES]
     names += ["output_transform.%s" % s for s in HEAD_PARAM_NAMES]
     return names
 
@@ -212,7 +220,7 @@ class NetPlan:
     """Owns an `fsb_net` handle plus its workspace tensor."""
 
     def __init__(self, two_d, features, depths, start_deep_supervision_on, n_classes, dropout_p, filterbank=None,
-                 precision=None, device="cuda"):
+                 precision=None, device="cuda", aggregation="max"):
         parts = features.split("_")
         if parts[0] not in ("mel", "stft"):
             raise ValueError("unsupported feature descriptor %r (mel_* / stft_* only)" % features)
@@ -232,6 +240,7 @@ class NetPlan:
         cfg.n_classes = int(n_classes)
         cfg.dropout_p = float(dropout_p)
         cfg.precision = PRECISIONS[self.precision]
+        cfg.aggregation = {"max": 0, "rnn": 1}[aggregation]
         self.cfg = cfg
         handle = ctypes.c_void_p()
         if cfg.feat_mode == 2:
@@ -303,6 +312,26 @@ class NetPlan:
                                         _stream()), "net_forward")
         return logits
 
+    def forward_features(self, features, t, training=False, dropout_seed=0):
+        """Forward pass on log features `(N, n_features, frames)` computed earlier (`FeatureExtractor`, mode 1 / 2) for
+        clips of `t` samples: the feature kernel is skipped (fold ensembles share one extraction per batch)."""
+        require_cuda(features, "features")
+        features = features.float().contiguous()
+        n = features.shape[0]
+        frames = 1 + t // self.cfg.hop
+        if tuple(features.shape) != (n, self.cfg.n_features, frames):
+            raise ValueError("features must be (N, %d, %d) for clips of %d samples, got %r"
+                             % (self.cfg.n_features, frames, t, tuple(features.shape)))
+        ws = self._ensure_workspace(n, t, training)
+        self.forward_id += 1
+        logits = torch.empty((n, self.cfg.n_classes), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().fsb_net_forward_features(self.handle, _ptr(features), n, t, self._param_ptrs, self._mean_ptrs,
+                                                 self._var_ptrs, self._cnt_ptrs, 1 if training else 0,
+                                                 int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(ws), ws.numel(),
+                                                 _ptr(logits), _stream()), "net_forward_features")
+        return logits
+
     def backward(self, dlogits, fresh=False):
         """Runs the backward plan; returns the flat gradient (canonical parameter order).  The plan owns ONE
         persistent flat buffer (stable pointers keep the fused-Adam table and NCCL buffers cached); `fresh`
@@ -333,6 +362,9 @@ class NetPlan:
 
     def set_profiling(self, on):
         lib().fsb_net_set_profiling(self.handle, 1 if on else 0)
+
+    def set_graphs(self, on):
+        check(lib().fsb_net_set_graphs(self.handle, 1 if on else 0), "net_set_graphs")
 
     def set_overlap(self, on):
         check(lib().fsb_net_set_overlap(self.handle, 1 if on else 0), "net_set_overlap")

@@ -97,9 +97,9 @@ class _AcceleratedCNN(nn.Module):
         net, data = self.config.network, self.config.data
         if not (is_mel(data.features) or is_stft(data.features)):
             raise NotImplementedError("features %r: only mel_* / stft_* descriptors are accelerated" % data.features)
-        if net.aggregation_type != "max":
-            raise NotImplementedError("aggregation_type=%r: only 'max' heads are accelerated (SURVEY.md 8f)"
-                                      % net.aggregation_type)
+        if net.aggregation_type not in ("max", "rnn") or (net.aggregation_type == "rnn" and not self.two_d):
+            raise NotImplementedError("aggregation_type=%r is not implemented for %s (max: both models; rnn: the 2D "
+                                      "model, as in the reference)" % (net.aggregation_type, type(self).__name__))
         if self.two_d and not is_mel(data.features) and not is_stft(data.features):
             raise NotImplementedError
 
@@ -125,7 +125,15 @@ class _AcceleratedCNN(nn.Module):
             depth = int(net.growth_rate ** k * net.conv_base_depth)
             self._depths.append(depth)
             if k >= net.start_deep_supervision_on:
-                total_depth += depth
+                if net.aggregation_type == "rnn":
+                    # registered (and default-initialised) BEFORE the block's own modules, like the reference :512-522
+                    rnn_size = 128
+                    total_depth += rnn_size * 2
+                    self.rnns.append(nn.Sequential(
+                        nn.LayerNorm((depth,)),
+                        nn.GRU(depth, rnn_size, batch_first=True, bidirectional=True)))
+                else:
+                    total_depth += depth
             self.conv_modules.append(nn.Sequential(
                 bn(input_size),
                 conv(input_size, depth, kernel_size=3, padding=1),
@@ -164,11 +172,11 @@ class _AcceleratedCNN(nn.Module):
                     raise ValueError("_input_dim=%d does not match features %r (%d)" % (data._input_dim, data.features, n_bins))
             self._plan = runtime.NetPlan(self.two_d, data.features, self._depths, net.start_deep_supervision_on,
                                          data._n_classes, net.output_dropout, filterbank=self._filterbank_np,
-                                         device=dev)
+                                         device=dev, aggregation=net.aggregation_type)
             named = dict(self.named_parameters())
             bufs = dict(self.named_buffers())
             nb = net.num_conv_blocks
-            self._param_list = [named[n] for n in runtime.canonical_param_names(nb)]
+            self._param_list = [named[n] for n in runtime.canonical_param_names(nb, len(self.rnns))]
             if [id(p) for p in self._param_list] != [id(p) for p in self.parameters()]:
                 raise RuntimeError("canonical parameter order differs from named_parameters() order")
             prefixes = runtime.canonical_bn_prefixes(nb)
@@ -195,6 +203,26 @@ class _AcceleratedCNN(nn.Module):
         else:
             class_logits = plan.forward(signal, False, 0)
         return dict(class_logits=class_logits)
+
+    def extract_features(self, signal):
+        """The model's input features `(N, n_features, frames)` (log-mel / log-STFT) for `signal (N, T[, 1])`: the fused
+        feature kernel alone (reference networks/classifiers.py:565-579).  They depend on the feature descriptor only,
+        not on the weights, so fold models with the same descriptor can share them (`forward_features`)."""
+        from fsb200.runtime import FeatureExtractor
+        if signal.dim() == 3:
+            signal = signal.squeeze(-1)
+        data = self.config.data
+        kind, n_fft, hop = data.features.split("_")[0], int(data.features.split("_")[1]), int(data.features.split("_")[2])
+        if getattr(self, "_feature_extractor", None) is None:
+            self._feature_extractor = FeatureExtractor(n_fft, hop, self._filterbank_np, device=self.device)
+        return self._feature_extractor(signal, 2 if kind == "mel" else 1)
+
+    def forward_features(self, features, n_samples):
+        """Eval-mode logits from precomputed features of clips with `n_samples` samples (no autograd)."""
+        plan = self._get_plan()
+        plan.set_pointers([p.data for p in self._param_list], *self._bn_lists)
+        with torch.no_grad():
+            return dict(class_logits=plan.forward_features(features, int(n_samples), training=False))
 
     # ------------------------------------------------------------------------------------------
     def add_scalar_summaries(self, loss, metric, writer, global_step):
@@ -366,6 +394,16 @@ class _AcceleratedCNN(nn.Module):
                     tta_probs.append(torch.sigmoid(class_logits))
             all_class_probs.append(torch.cat(tta_probs).cpu().numpy())
         return np.mean(all_class_probs, 0)
+
+    def predict_clips(self, clips, buckets, max_batch_elems, padding_value=0.0, return_stats=False):
+        """Length-bucketed prediction over a list of 1-D waveforms (numpy arrays, pinned CPU tensors or CUDA tensors):
+        the reference's unused `BucketingSampler` rule (ops/padding.py:36-81) wired into the `predict` loop of
+        predict_2d_cnn.py:89-118 -- clips are binned by length, packed into batches of at most `max_batch_elems`
+        samples, zero-padded per batch like `make_collate_fn`, and the sigmoid probabilities come back in the
+        original clip order.  Under `torchrun` the batches are sharded over the ranks (fsb200.inference)."""
+        from fsb200.inference import predict_bucketed
+        return predict_bucketed(self, clips, buckets, max_batch_elems, padding_value=padding_value,
+                                return_stats=return_stats)
 
     def fit_validate(self, train_loader, valid_loader, epochs, fold, log_interval=25):
         """Reference :799-868."""

@@ -152,6 +152,9 @@ typedef struct fsb_net_config {
                                   2 = tcgen05 single half pass everywhere (fast, logits NOT parity grade),
                                   3 = mixed (default of the Python layer): forward as 1, backward GEMMs (dgrad,
                                       wgrad) as 2 with per-tensor power-of-two gradient scaling              */
+    int aggregation;           /* deep-supervision heads: 0 = global max (AdaptiveMaxPool), 1 = "rnn" (frequency mean ->
+                                  LayerNorm -> bidirectional GRU(128) final states; 2D model only,
+                                  networks/classifiers.py:514-522, 592-597)                                  */
 } fsb_net_config;
 
 typedef struct fsb_net fsb_net;   /* opaque */
@@ -178,6 +181,14 @@ int fsb_net_forward(fsb_net* net, const float* signal, int n, int t, long long s
                     const float* const* params, float* const* bn_mean, float* const* bn_var,
                     long long* const* bn_count, int training, unsigned long long dropout_seed,
                     void* workspace, size_t workspace_bytes, float* logits, void* stream);
+/* Same forward pass on log features computed earlier with fsb_feat_forward (mode 1 / 2, layout (N, n_features, frames),
+ * frames = 1 + t / hop): the feature kernel is skipped.  Lets an ensemble of fold models (predict_2d_cnn.py:111-118
+ * averages 5 folds) share ONE feature extraction per batch -- the features do not depend on the weights.            */
+int fsb_net_forward_features(fsb_net* net, const float* features, int n, int t, const float* const* params,
+                             float* const* bn_running_mean, float* const* bn_running_var,
+                             long long* const* bn_num_batches, int training, unsigned long long dropout_seed,
+                             void* workspace, size_t workspace_bytes, float* logits, void* stream);
+
 /*  dlogits (N, n_classes); grads: one flat float32 device buffer holding every parameter gradient
  *  back to back in canonical order (fully overwritten).                                           */
 int fsb_net_backward(fsb_net* net, const float* dlogits, const float* const* params,
@@ -195,6 +206,10 @@ int fsb_net_set_profiling(fsb_net* net, int on);
 /* side-stream overlap of weight packing / weight-gradient GEMMs (default on unless FSB200_NO_OVERLAP was set when the
  * plan was created); results are bit-identical either way */
 int fsb_net_set_overlap(fsb_net* net, int on);
+/* CUDA-graph replay (default on unless FSB200_GRAPHS=0 was set when the plan was created): the launch sequence of a
+ * forward / backward call is captured the second time the same pointers and shapes are seen and replayed afterwards.
+ * Results are bit-identical to eager launches.                                                                      */
+int fsb_net_set_graphs(fsb_net* net, int on);
 int fsb_net_get_timings(fsb_net* net, int cap, const char** names, float* ms, double* flops, int* count);
 /* number of kernels this library launched since the counter was last reset (bench `gpu_launches`) */
 long long fsb_launch_count(int reset);

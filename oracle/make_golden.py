@@ -123,6 +123,9 @@ def main():
                "net2d_pow2.npz", wave_kind="noise")
     cfg1d = make_config(features="stft_256_128", conv_base_depth=8, growth_rate=1.5)
     model_case(ref, "HierarchicalCNNClassificationModel", cfg1d, 4, 12000, 13, "net1d_small.npz")
+    # aggregation_type="rnn" heads: LayerNorm + bidirectional GRU(128) over time (networks/classifiers.py:514-522)
+    cfg2d_rnn = make_config(conv_base_depth=8, growth_rate=1.5, aggregation_type="rnn", start_deep_supervision_on=3)
+    model_case(ref, "TwoDimensionalCNNClassificationModel", cfg2d_rnn, 4, 40000, 14, "net2d_rnn_small.npz")
 
     # ---- 3. LSEP (networks/losses.py:47-58)
     g = torch.Generator().manual_seed(3)

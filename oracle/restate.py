@@ -202,6 +202,35 @@ def _head(feats, sd, training, dropout_p, stats_out, dropout_mask=None):
     return F.linear(h, sd[p + ".5.weight"], sd[p + ".5.bias"])
 
 
+RNN_SIZE = 128      # networks/classifiers.py:509 (`rnn_size = 128`)
+
+
+def _rnn_head(h, sd, prefix):
+    """aggregation_type == "rnn" (networks/classifiers.py:514-522, 592-597): mean over the frequency axis,
+    LayerNorm over channels, bidirectional GRU(C -> 128, batch_first) over time; the head feature is the pair of final
+    hidden states [forward | backward] = `state.permute(1, 0, 2).view(N, -1)`.  GRU cell restated explicitly (torch
+    gate order r, z, n): r = s(W_ir x + b_ir + W_hr h + b_hr), z likewise, n = tanh(W_in x + b_in + r * (W_hn h + b_hn)),
+    h' = (1 - z) * n + z * h."""
+    x = torch.mean(h, 2).permute(0, 2, 1)                                   # (N, W, C)
+    x = F.layer_norm(x, (x.shape[-1],), sd[prefix + ".0.weight"], sd[prefix + ".0.bias"], 1e-5)
+    finals = []
+    for suffix, reverse in (("", False), ("_reverse", True)):
+        w_ih, w_hh = sd[prefix + ".1.weight_ih_l0" + suffix], sd[prefix + ".1.weight_hh_l0" + suffix]
+        b_ih, b_hh = sd[prefix + ".1.bias_ih_l0" + suffix], sd[prefix + ".1.bias_hh_l0" + suffix]
+        gi = F.linear(x.flip(1) if reverse else x, w_ih, b_ih)              # (N, W, 3 * 128)
+        hcur = torch.zeros(x.shape[0], RNN_SIZE, dtype=x.dtype, device=x.device)
+        for t in range(gi.shape[1]):
+            gh = F.linear(hcur, w_hh, b_hh)
+            i_r, i_z, i_n = gi[:, t].chunk(3, -1)
+            h_r, h_z, h_n = gh.chunk(3, -1)
+            r = torch.sigmoid(i_r + h_r)
+            z = torch.sigmoid(i_z + h_z)
+            cand = torch.tanh(i_n + r * h_n)
+            hcur = (1 - z) * cand + z * hcur
+        finals.append(hcur)
+    return torch.cat(finals, -1)
+
+
 def add_frequency_encoding(x):
     """networks/classifiers.py:553-561: concat channel `linspace(-1, 1, H)[h]`."""
     n, d, h, w = x.shape
@@ -216,7 +245,7 @@ def net2d_forward(sd, config, signal, training=False, stats_out=None, feats_in=N
     requires_grad give gradients through plain autograd).  Returns logits `(N, C)`.
     `stats_out` (dict) receives per-BN batch (mean, unbiased var) in train mode."""
     net = config["network"]
-    assert net["aggregation_type"] == "max"
+    assert net["aggregation_type"] in ("max", "rnn")
     if feats_in is None:
         feats_in = features(signal, config["data"]["features"])
     h = add_frequency_encoding(feats_in.unsqueeze(1))
@@ -234,7 +263,10 @@ def net2d_forward(sd, config, signal, training=False, stats_out=None, feats_in=N
         if taps is not None:
             taps["block%d" % k] = h
         if k >= net["start_deep_supervision_on"]:
-            heads.append(F.adaptive_max_pool2d(h, 1).squeeze(-1).squeeze(-1))
+            if net["aggregation_type"] == "rnn":
+                heads.append(_rnn_head(h, sd, "rnns.%d" % (k - net["start_deep_supervision_on"])))
+            else:
+                heads.append(F.adaptive_max_pool2d(h, 1).squeeze(-1).squeeze(-1))
     feats = torch.cat(heads, -1)
     if taps is not None:
         taps["head_in"] = feats
@@ -301,7 +333,15 @@ def init_state_dict(config, two_d=True, seed=42):
             for k, d in enumerate(depths):
                 cin = (2 if two_d else data["_input_dim"]) if k == 0 else depths[k - 1]
                 if k >= net["start_deep_supervision_on"]:
-                    total += d
+                    if two_d and net["aggregation_type"] == "rnn":        # registered (and initialised) before the block
+                        total += 2 * RNN_SIZE
+                        self.rnns.append(nn.Sequential(
+                            nn.LayerNorm((d,)), nn.GRU(d, RNN_SIZE, batch_first=True, bidirectional=True)))
+                        continue_max = False
+                    else:
+                        continue_max = True
+                    if continue_max:
+                        total += d
                 self.conv_modules.append(nn.Sequential(
                     bn(cin), conv(cin, d, kernel_size=3, padding=1), pool(kernel_size=2, stride=2),
                     bn(d), nn.PReLU(d), Res(d)))

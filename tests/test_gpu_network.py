@@ -40,6 +40,9 @@ CASES = [
      dict(conv_base_depth=8, growth_rate=2.0, start_deep_supervision_on=2)),
     ("net1d_small.npz", "HierarchicalCNNClassificationModel",
      dict(features="stft_256_128", conv_base_depth=8, growth_rate=1.5)),
+    # aggregation_type="rnn": LayerNorm + bidirectional GRU(128) heads (networks/classifiers.py:514-522, 592-597)
+    ("net2d_rnn_small.npz", "TwoDimensionalCNNClassificationModel",
+     dict(conv_base_depth=8, growth_rate=1.5, aggregation_type="rnn", start_deep_supervision_on=3)),
 ]
 
 

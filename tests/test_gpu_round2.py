@@ -343,3 +343,26 @@ def test_two_gpu_allreduce_matches_single_gpu_shards():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "replicas_synced=True allreduce_bit_exact=True" in out.stdout
+
+
+def test_fold_ensemble_shares_one_feature_extraction():
+    """`predict_folds` (one padded batch, one feature extraction, every fold model on the shared features) equals the
+    mean of the fold models' own bucketed predictions, for the 2D (log-mel) and the 1D (log-STFT) model."""
+    from fsb200.inference import predict_bucketed, predict_folds
+    rng = np.random.RandomState(9)
+    lengths = rng.randint(34000, 80000, size=9).tolist()
+    clips = [restate.synth_waveforms(1, n, seed=200 + k)[0] for k, n in enumerate(lengths)]
+    buckets = [33 * 1024, 50000, 70000, 100000]
+    for cls, cfg in (("TwoDimensionalCNNClassificationModel", dict(conv_base_depth=8, growth_rate=1.5)),
+                     ("HierarchicalCNNClassificationModel", dict(features="stft_256_128", conv_base_depth=8, growth_rate=1.5))):
+        models = []
+        for fold in range(3):
+            m = _build(cls, cfg, "mixed")
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.add_(0.01 * fold * torch.randn_like(p))
+            models.append(m)
+        want = np.mean([predict_bucketed(m, clips, buckets, 150000) for m in models], axis=0)
+        got = predict_folds(models, clips, buckets, 150000)
+        assert got.shape == want.shape == (9, 80)
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-7)

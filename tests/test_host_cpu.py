@@ -146,6 +146,8 @@ def test_out_of_scope_transforms_forward_to_a_reference_checkout():
     ("net2d_small.npz", "TwoDimensionalCNNClassificationModel", dict(conv_base_depth=8, growth_rate=1.5)),
     ("net1d_small.npz", "HierarchicalCNNClassificationModel",
      dict(features="stft_256_128", conv_base_depth=8, growth_rate=1.5)),
+    ("net2d_rnn_small.npz", "TwoDimensionalCNNClassificationModel",
+     dict(conv_base_depth=8, growth_rate=1.5, aggregation_type="rnn", start_deep_supervision_on=3)),
 ])
 def test_module_tree_matches_reference(name, cls, cfg):
     import networks.classifiers as nc
@@ -160,7 +162,7 @@ def test_module_tree_matches_reference(name, cls, cfg):
         assert tuple(sd[k].shape) == g["sd/" + k].shape, k
     chk = np.array([float(v.double().sum()) for k, v in sorted(sd.items())])
     assert np.array_equal(chk, g["init_checksum"])           # same default init under seed 42
-    names = canonical_param_names(5)
+    names = canonical_param_names(5, len(model.rnns))
     assert names == [n for n, _ in model.named_parameters()]
     assert len(canonical_bn_prefixes(5)) == 27
     assert "filterbanks" not in sd
@@ -170,11 +172,15 @@ def test_module_tree_matches_reference(name, cls, cfg):
     model.load_state_dict({k: torch.from_numpy(g["sd/" + k]) for k in ref_keys})
 
 
-def test_rnn_aggregation_is_rejected():
+def test_unsupported_aggregation_is_rejected():
+    """rnn heads exist for the 2D model only (as in the reference); anything else must fail loudly."""
     import networks.classifiers as nc
     with pytest.raises(NotImplementedError):
+        nc.HierarchicalCNNClassificationModel(
+            FakeExperiment(make_config(features="stft_256_128", conv_base_depth=8, aggregation_type="rnn")), device="cpu")
+    with pytest.raises(NotImplementedError):
         nc.TwoDimensionalCNNClassificationModel(
-            FakeExperiment(make_config(conv_base_depth=8, aggregation_type="rnn")), device="cpu")
+            FakeExperiment(make_config(conv_base_depth=8, aggregation_type="attention")), device="cpu")
 
 
 def _dp_worker(rank, world_size, port, out_dir):

@@ -59,6 +59,8 @@ CASES = [
     ("net2d_small.npz", True, dict(conv_base_depth=8, growth_rate=1.5)),
     ("net2d_pow2.npz", True, dict(conv_base_depth=8, growth_rate=2.0, start_deep_supervision_on=2)),
     ("net1d_small.npz", False, dict(features="stft_256_128", conv_base_depth=8, growth_rate=1.5)),
+    ("net2d_rnn_small.npz", True, dict(conv_base_depth=8, growth_rate=1.5, aggregation_type="rnn",
+                                       start_deep_supervision_on=3)),
 ]
 
 
