@@ -315,6 +315,14 @@ conv0_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, Geo gp, 
     }
 }
 
+int conv0_bwd_finalize(const float* partials, int nblk, const Geo& gp, float* dw, float* db, float* dgamma_in,
+                       float* dbeta_in, cudaStream_t s) {
+    FSB_REQUIRE(gp.Cs <= 512, "conv0: at most 512 output channels");
+    conv0_bwd_finalize_kernel<<<C0B_REC, 1024, 0, s>>>(partials, nblk, gp, dw, db, dgamma_in, dbeta_in);
+    FSB_LAUNCHED();
+    return 0;
+}
+
 int conv0_backward(const float* feat, int N, int H, int W, const float* scale, const float* shift, const float* mean,
                    const float* invstd, const float* w, const float* b, const float* dzp, const unsigned char* amax,
                    const Geo& gp, float* dw, float* db, float* dgamma_in, float* dbeta_in, void* scratch, cudaStream_t s) {

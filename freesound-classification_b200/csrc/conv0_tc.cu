@@ -252,7 +252,277 @@ __global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_fwd_kernel(const Conv
     (void)lane;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// backward: D[c][k] = sum over pooled pixels q of g[q][c] * [amax[q][c] == pos] * F_pos[q][k], summed over the four
+// window positions, where F_pos[q][0..17] is the BN-applied input patch of position pos, F_pos[q][18..26] flags the taps
+// that fall inside the image and F_pos[q][27..44] is the normalised input patch (xhat).  D[c][0..17] is the weight
+// gradient; d(beta_in)_ci = sum_c sum_t w[c][ci][t] D[c][18 + t] and d(gamma_in)_ci = sum_c sum_t w[c][ci][t] D[c][27 + 9 ci + t].  Per 64-pixel tile: four masked-gradient tiles [64 pixels x 128 channels] (M side, MN-major,
+// two 64-channel SWIZZLE_128B boxes) and four patch tiles [64 pixels x 64 features] (N side), 4 positions x 4 k-steps
+// of M128 x N64 x K16 MMAs into ONE accumulator that lives in TMEM for the whole life of the CTA.
+constexpr int C0B_PX = 64;                         // pooled pixels per tile (reduction dimension of the MMAs)
+constexpr uint32_t C0B_BOX = C0B_PX * 128u;        // one 64-channel box: 64 rows x 128 B
+constexpr int C0B_THREADS = 160;
+
+struct Conv0TcBwdParams {
+    const float* feat;
+    int N, H, W;
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+    const float* w;
+    const float* dzp;
+    const unsigned char* amax;
+    const unsigned* absmax;
+    Geo gp;
+    int planes;
+    long long npix;
+    int ntiles;
+    float* partials;        // [gridDim.x][22][Cs]
+};
+
+// 16-byte chunk c (0..7) of 128-byte row r of a SWIZZLE_128B box
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+
+__global__ void __launch_bounds__(C0B_THREADS, 1) conv0_tc_bwd_kernel(const Conv0TcBwdParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // [G: position][plane][box 0 | box 1]   [F: position][plane][box]
+    const uint32_t g_plane = 2u * C0B_BOX, g_pos = g_plane * (uint32_t)p.planes;
+    const uint32_t f_plane = C0B_BOX, f_pos = f_plane * (uint32_t)p.planes;
+    const uint32_t g_base = smem_base, f_base = g_base + 4u * g_pos;
+    const uint32_t bars = f_base + 4u * f_pos;
+    const uint32_t b_full = bars, b_empty = bars + 8u, tmem_slot = bars + 16u;
+    const int warp = threadIdx.x >> 5;
+    const float sc0 = p.scale[0], sh0 = p.shift[0], sc1 = p.scale[1], sh1 = p.shift[1];
+    const float mean0 = p.mean[0], istd0 = p.invstd[0], mean1 = p.mean[1], istd1 = p.invstd[1];
+
+    // zero the operand region once: channel chunks >= Cs and feature chunks 6..7 are never written afterwards
+    for (uint32_t o = threadIdx.x * 16u; o < 4u * (g_pos + f_pos); o += C0B_THREADS * 16u)
+        st_shared_v4_u32(g_base + o, 0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) {
+        mbar_init(b_full, 128);
+        mbar_init(b_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 64);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int H2 = p.gp.H, W2 = p.gp.W, Cs = p.gp.Cs;
+    uint32_t it = 0;
+    if (warp < 4) {
+        const uint32_t r = threadIdx.x & 63u, half = threadIdx.x >> 6;       // pixel row of the tile, channel half / position pair
+        const float gscale = gs_scale(p.absmax);
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            if (it > 0) mbar_wait(b_empty, (it - 1u) & 1u);                   // the previous tile's MMAs have read the operands
+            const long long q = (long long)tile * C0B_PX + r;
+            const bool live = q < p.npix;
+            int px = 0, py = 0, n = 0;
+            if (live) {
+                px = (int)(q % W2);
+                const long long t = q / W2;
+                py = (int)(t % H2);
+                n = (int)(t / H2);
+            }
+            // ---- masked gradient rows: channels [half * 64, half * 64 + 64) of the four positions
+            const long long grow = live ? geo_row(p.gp, n, py, px) * Cs : 0;
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c) {
+                const int ch0 = (int)(half * 64u + c * 8u);
+                if (ch0 < Cs) {
+                    float g8[8];
+                    uint32_t a8[2] = {0u, 0u};
+                    if (live) {
+                        const float4 lo4 = *reinterpret_cast<const float4*>(p.dzp + grow + ch0);
+                        const float4 hi4 = *reinterpret_cast<const float4*>(p.dzp + grow + ch0 + 4);
+                        g8[0] = lo4.x; g8[1] = lo4.y; g8[2] = lo4.z; g8[3] = lo4.w;
+                        g8[4] = hi4.x; g8[5] = hi4.y; g8[6] = hi4.z; g8[7] = hi4.w;
+                        const uint2 am = *reinterpret_cast<const uint2*>(p.amax + grow + ch0);
+                        a8[0] = am.x; a8[1] = am.y;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) g8[i] = 0.f;
+                    }
+                    __half gh[8], gl[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) split_h16(g8[i] * gscale, gh[i], gl[i]);
+#pragma unroll
+                    for (uint32_t pos = 0; pos < 4; ++pos) {
+                        uint32_t wh[4], wl[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const bool m0 = ((a8[(2 * i) >> 2] >> (8 * ((2 * i) & 3))) & 0xFFu) == pos;
+                            const bool m1 = ((a8[(2 * i + 1) >> 2] >> (8 * ((2 * i + 1) & 3))) & 0xFFu) == pos;
+                            const __half z = __float2half_rn(0.f);
+                            wh[i] = pack_h2(m0 ? gh[2 * i] : z, m1 ? gh[2 * i + 1] : z);
+                            wl[i] = pack_h2(m0 ? gl[2 * i] : z, m1 ? gl[2 * i + 1] : z);
+                        }
+                        const uint32_t dst = g_base + pos * g_pos + half * C0B_BOX + sw128(r, c);
+                        st_shared_v4_u32(dst, wh[0], wh[1], wh[2], wh[3]);
+                        if (p.planes == 2) st_shared_v4_u32(dst + g_plane, wl[0], wl[1], wl[2], wl[3]);
+                    }
+                }
+            }
+            // ---- patch feature rows of positions 2 * half and 2 * half + 1
+            float u0[4][4], u1[4][4], x0[4][4], x1[4][4], ok[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int y = 2 * py - 1 + i;
+                const bool yok = live && y >= 0 && y < p.H;
+                const float e = yok ? c0t_freq_enc(y, p.H) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = 2 * px - 1 + j;
+                    const bool in = yok && x >= 0 && x < p.W;
+                    const float f = in ? __ldg(p.feat + ((long long)n * p.H + y) * p.W + x) : 0.f;
+                    u0[i][j] = in ? fmaf(f, sc0, sh0) : 0.f;
+                    u1[i][j] = in ? fmaf(e, sc1, sh1) : 0.f;
+                    x0[i][j] = in ? (f - mean0) * istd0 : 0.f;
+                    x1[i][j] = in ? (e - mean1) * istd1 : 0.f;
+                    ok[i][j] = in ? 1.f : 0.f;
+                }
+            }
+#pragma unroll
+            for (uint32_t pp = 0; pp < 2; ++pp) {
+                const uint32_t pos = 2u * half + pp;
+                const int sy = (int)(pos >> 1), sx = (int)(pos & 1u);
+                float v[48];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        v[dy * 3 + dx] = u0[sy + dy][sx + dx];
+                        v[9 + dy * 3 + dx] = u1[sy + dy][sx + dx];
+                        v[18 + dy * 3 + dx] = ok[sy + dy][sx + dx];
+                        v[27 + dy * 3 + dx] = x0[sy + dy][sx + dx];
+                        v[36 + dy * 3 + dx] = x1[sy + dy][sx + dx];
+                    }
+#pragma unroll
+                for (int i = 45; i < 48; ++i) v[i] = 0.f;
+#pragma unroll
+                for (uint32_t c = 0; c < 6; ++c) {
+                    uint32_t wh[4], wl[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __half h0, l0, h1, l1;
+                        split_h16(v[8 * c + 2 * i], h0, l0);
+                        split_h16(v[8 * c + 2 * i + 1], h1, l1);
+                        wh[i] = pack_h2(h0, h1);
+                        wl[i] = pack_h2(l0, l1);
+                    }
+                    const uint32_t dst = f_base + pos * f_pos + sw128(r, c);
+                    st_shared_v4_u32(dst, wh[0], wh[1], wh[2], wh[3]);
+                    if (p.planes == 2) st_shared_v4_u32(dst + f_plane, wl[0], wl[1], wl[2], wl[3]);
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(b_full);
+        }
+        // ---- epilogue: this thread's channel row of the accumulator -> the 22-value record of conv0.cu
+        if (it > 0) mbar_wait(b_empty, (it - 1u) & 1u);
+        tc_fence_after();
+        const int c = threadIdx.x;                                             // TMEM lane = output channel
+        float d[48];
+        tmem_ld32_async(tmem_base + ((uint32_t)(warp * 32) << 16), d);
+        tmem_ld16_async(tmem_base + ((uint32_t)(warp * 32) << 16) + 32u, d + 32);
+        tmem_ld_wait();
+        const float unscale = gs_inv_scale(p.absmax);
+        float* o = p.partials + (long long)blockIdx.x * 22 * Cs;
+        if (c < Cs) {
+            float rec[22];
+#pragma unroll
+            for (int i = 0; i < 22; ++i) rec[i] = 0.f;
+            if (c < p.gp.C && it > 0) {
+                float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const float w0 = p.w[c * 18 + t], w1 = p.w[c * 18 + 9 + t];
+                    rec[t] = d[t] * unscale;
+                    rec[9 + t] = d[9 + t] * unscale;
+                    db0 = fmaf(w0, d[18 + t], db0);
+                    db1 = fmaf(w1, d[18 + t], db1);
+                    dg0 = fmaf(w0, d[27 + t], dg0);
+                    dg1 = fmaf(w1, d[36 + t], dg1);
+                }
+                rec[18] = dg0 * unscale;      // d(gamma_in) terms: sum_t w_t * sum_q g xhat_t
+                rec[19] = dg1 * unscale;
+                rec[20] = db0 * unscale;      // d(beta_in) terms: sum_t w_t * sum_q g valid_t
+                rec[21] = db1 * unscale;
+            }
+#pragma unroll
+            for (int i = 0; i < 22; ++i) o[i * Cs + c] = rec[i];
+        }
+        tc_fence_before();
+    } else {
+        const uint32_t idesc = make_idesc(128, 64, 1, 1);
+        // MN-major SWIZZLE_128B descriptors: LBO = stride between 64-channel boxes, SBO = 8 rows x 128 B
+        const uint32_t hi_word = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t lbo = (C0B_BOX >> 4) << 16;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(b_full, it & 1u);
+            tc_fence_after();
+            if (umma::elect_one()) {
+#pragma unroll 1
+                for (uint32_t pos = 0; pos < 4; ++pos) {
+                    const uint32_t gh = g_base + pos * g_pos, fh = f_base + pos * f_pos;
+                    const uint64_t m_hi = ((uint64_t)hi_word << 32) | (lbo | ((gh & 0x3FFFFu) >> 4));
+                    const uint64_t m_lo = ((uint64_t)hi_word << 32) | (lbo | (((gh + g_plane) & 0x3FFFFu) >> 4));
+                    const uint64_t n_hi = ((uint64_t)hi_word << 32) | (lbo | ((fh & 0x3FFFFu) >> 4));
+                    const uint64_t n_lo = ((uint64_t)hi_word << 32) | (lbo | (((fh + f_plane) & 0x3FFFFu) >> 4));
+                    const uint32_t acc = (it > 0 || pos > 0) ? 1u : 0u;
+                    if (p.planes == 2) umma_wgrad_x3(tmem_base, 64u, m_hi, m_lo, n_hi, n_lo, 0u, 0u, idesc, acc, 1);
+                    else umma_wgrad_x1(tmem_base, 64u, m_hi, m_lo, n_hi, n_lo, 0u, 0u, idesc, acc, 1);
+                }
+                umma_commit(b_empty);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
 }  // namespace
+
+int conv0_tc_backward(int precision, const float* feat, int N, int H, int W, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const float* w, const float* dzp, const unsigned char* amax,
+                      const unsigned* dz_absmax, const Geo& gp, float* dw, float* db, float* dgamma_in, float* dbeta_in,
+                      void* scratch, cudaStream_t s) {
+    FSB_REQUIRE(conv0_tc_supported(gp) && (precision == 1 || precision == 2) && amax, "conv0_tc_backward: unsupported");
+    Conv0TcBwdParams p;
+    p.feat = feat; p.N = N; p.H = H; p.W = W;
+    p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd; p.w = w;
+    p.dzp = dzp; p.amax = amax; p.absmax = dz_absmax; p.gp = gp;
+    p.planes = precision == 1 ? 2 : 1;
+    p.npix = (long long)N * gp.H * gp.W;
+    p.ntiles = (int)((p.npix + C0B_PX - 1) / C0B_PX);
+    p.partials = (float*)scratch;
+    const size_t smem = 1024 + (size_t)4 * p.planes * (2 * C0B_BOX + C0B_BOX) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FSB_CUDA(cudaFuncSetAttribute(conv0_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int sms = 0, dev = 0;
+    FSB_CUDA(cudaGetDevice(&dev));
+    FSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int per_sm = p.planes == 1 ? 2 : 1;            // 97 KB (single pass) / 193 KB (three products) of operands per CTA
+    int grid = sms * per_sm;
+    if (grid > p.ntiles) grid = p.ntiles;
+    if (grid > conv0_bwd_blocks()) grid = conv0_bwd_blocks();
+    conv0_tc_bwd_kernel<<<grid, C0B_THREADS, smem, s>>>(p);
+    FSB_LAUNCHED();
+    return conv0_bwd_finalize((const float*)scratch, grid, gp, dw, db, dgamma_in, dbeta_in, s);
+}
 
 bool conv0_tc_supported(const Geo& gp) { return gp.Cs <= 128 && gp.Cs % 16 == 0 && gp.C * 18 < (1 << 30); }
 

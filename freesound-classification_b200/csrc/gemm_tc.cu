@@ -45,203 +45,6 @@ constexpr int TC_THREADS = 192;    // 6 warps
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int WG_R = 64;           // wgrad: pixel rows per pipeline stage
 
-// wgrad: all MMAs of one 64-pixel-row stage -- up to 3 dx taps (one accumulator each, `ncol` TMEM columns apart) x 4
-// k-steps (16 rows = 2048 bytes apart in both MN-major operands) x 3 products -- in one asm block (see umma_stage_x3).
-// The tap shift (one smem row = 128 bytes = 8 descriptor units) applies to whichever operand holds the activations.
-__device__ __forceinline__ void umma_wgrad_x3(uint32_t d0, uint32_t ncol, uint64_t m_hi, uint64_t m_lo, uint64_t n_hi,
-                                              uint64_t n_lo, uint32_t m_shift16, uint32_t n_shift16, uint32_t idesc,
-                                              uint32_t acc, int ntaps) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pacc, pt, ps1, ps2;\n\t"
-        ".reg .b32 d;\n\t"
-        ".reg .b64 mh, ml, nh, nl, ms, ns, xh, xl, yh, yl;\n\t"
-        "setp.ne.b32 pacc, %9, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "setp.gt.s32 ps1, %10, 1;\n\t"
-        "setp.gt.s32 ps2, %10, 2;\n\t"
-        "mov.b32 d, %0;\n\t"
-        "cvt.u64.u32 ms, %6;\n\t"
-        "cvt.u64.u32 ns, %7;\n\t"
-        "mov.b64 mh, %2;\n\t"
-        "mov.b64 ml, %3;\n\t"
-        "mov.b64 nh, %4;\n\t"
-        "mov.b64 nl, %5;\n\t"
-        "add.u64 xh, mh, 0;\n\t"
-        "add.u64 yh, nh, 0;\n\t"
-        "add.u64 xl, ml, 0;\n\t"
-        "add.u64 yl, nl, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pacc;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 128;\n\t"
-        "add.u64 yh, nh, 128;\n\t"
-        "add.u64 xl, ml, 128;\n\t"
-        "add.u64 yl, nl, 128;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 256;\n\t"
-        "add.u64 yh, nh, 256;\n\t"
-        "add.u64 xl, ml, 256;\n\t"
-        "add.u64 yl, nl, 256;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 384;\n\t"
-        "add.u64 yh, nh, 384;\n\t"
-        "add.u64 xl, ml, 384;\n\t"
-        "add.u64 yl, nl, 384;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "@!ps1 bra.uni DONE;\n\t"
-        "add.u32 d, d, %1;\n\t"
-        "add.u64 mh, mh, ms;\n\t"
-        "add.u64 ml, ml, ms;\n\t"
-        "add.u64 nh, nh, ns;\n\t"
-        "add.u64 nl, nl, ns;\n\t"
-        "add.u64 xh, mh, 0;\n\t"
-        "add.u64 yh, nh, 0;\n\t"
-        "add.u64 xl, ml, 0;\n\t"
-        "add.u64 yl, nl, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pacc;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 128;\n\t"
-        "add.u64 yh, nh, 128;\n\t"
-        "add.u64 xl, ml, 128;\n\t"
-        "add.u64 yl, nl, 128;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 256;\n\t"
-        "add.u64 yh, nh, 256;\n\t"
-        "add.u64 xl, ml, 256;\n\t"
-        "add.u64 yl, nl, 256;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 384;\n\t"
-        "add.u64 yh, nh, 384;\n\t"
-        "add.u64 xl, ml, 384;\n\t"
-        "add.u64 yl, nl, 384;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "@!ps2 bra.uni DONE;\n\t"
-        "add.u32 d, d, %1;\n\t"
-        "add.u64 mh, mh, ms;\n\t"
-        "add.u64 ml, ml, ms;\n\t"
-        "add.u64 nh, nh, ns;\n\t"
-        "add.u64 nl, nl, ns;\n\t"
-        "add.u64 xh, mh, 0;\n\t"
-        "add.u64 yh, nh, 0;\n\t"
-        "add.u64 xl, ml, 0;\n\t"
-        "add.u64 yl, nl, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pacc;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 128;\n\t"
-        "add.u64 yh, nh, 128;\n\t"
-        "add.u64 xl, ml, 128;\n\t"
-        "add.u64 yl, nl, 128;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 256;\n\t"
-        "add.u64 yh, nh, 256;\n\t"
-        "add.u64 xl, ml, 256;\n\t"
-        "add.u64 yl, nl, 256;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 384;\n\t"
-        "add.u64 yh, nh, 384;\n\t"
-        "add.u64 xl, ml, 384;\n\t"
-        "add.u64 yl, nl, 384;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xl, yh, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yl, %8, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "DONE:\n\t"
-        "}"
-        ::"r"(d0), "r"(ncol), "l"(m_hi), "l"(m_lo), "l"(n_hi), "l"(n_lo), "r"(m_shift16), "r"(n_shift16), "r"(idesc), "r"(acc),
-          "r"(ntaps)
-        : "memory");
-}
-__device__ __forceinline__ void umma_wgrad_x1(uint32_t d0, uint32_t ncol, uint64_t m_hi, uint64_t m_lo, uint64_t n_hi,
-                                              uint64_t n_lo, uint32_t m_shift16, uint32_t n_shift16, uint32_t idesc,
-                                              uint32_t acc, int ntaps) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pacc, pt, ps1, ps2;\n\t"
-        ".reg .b32 d;\n\t"
-        ".reg .b64 mh, ml, nh, nl, ms, ns, xh, xl, yh, yl;\n\t"
-        "setp.ne.b32 pacc, %9, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "setp.gt.s32 ps1, %10, 1;\n\t"
-        "setp.gt.s32 ps2, %10, 2;\n\t"
-        "mov.b32 d, %0;\n\t"
-        "cvt.u64.u32 ms, %6;\n\t"
-        "cvt.u64.u32 ns, %7;\n\t"
-        "mov.b64 mh, %2;\n\t"
-        "mov.b64 ml, %3;\n\t"
-        "mov.b64 nh, %4;\n\t"
-        "mov.b64 nl, %5;\n\t"
-        "add.u64 xh, mh, 0;\n\t"
-        "add.u64 yh, nh, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pacc;\n\t"
-        "add.u64 xh, mh, 128;\n\t"
-        "add.u64 yh, nh, 128;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 256;\n\t"
-        "add.u64 yh, nh, 256;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 384;\n\t"
-        "add.u64 yh, nh, 384;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "@!ps1 bra.uni DONE;\n\t"
-        "add.u32 d, d, %1;\n\t"
-        "add.u64 mh, mh, ms;\n\t"
-        "add.u64 ml, ml, ms;\n\t"
-        "add.u64 nh, nh, ns;\n\t"
-        "add.u64 nl, nl, ns;\n\t"
-        "add.u64 xh, mh, 0;\n\t"
-        "add.u64 yh, nh, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pacc;\n\t"
-        "add.u64 xh, mh, 128;\n\t"
-        "add.u64 yh, nh, 128;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 256;\n\t"
-        "add.u64 yh, nh, 256;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 384;\n\t"
-        "add.u64 yh, nh, 384;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "@!ps2 bra.uni DONE;\n\t"
-        "add.u32 d, d, %1;\n\t"
-        "add.u64 mh, mh, ms;\n\t"
-        "add.u64 ml, ml, ms;\n\t"
-        "add.u64 nh, nh, ns;\n\t"
-        "add.u64 nl, nl, ns;\n\t"
-        "add.u64 xh, mh, 0;\n\t"
-        "add.u64 yh, nh, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pacc;\n\t"
-        "add.u64 xh, mh, 128;\n\t"
-        "add.u64 yh, nh, 128;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 256;\n\t"
-        "add.u64 yh, nh, 256;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "add.u64 xh, mh, 384;\n\t"
-        "add.u64 yh, nh, 384;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], xh, yh, %8, pt;\n\t"
-        "DONE:\n\t"
-        "}"
-        ::"r"(d0), "r"(ncol), "l"(m_hi), "l"(m_lo), "l"(n_hi), "l"(n_lo), "r"(m_shift16), "r"(n_shift16), "r"(idesc), "r"(acc),
-          "r"(ntaps)
-        : "memory");
-}
 // ---------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ---------------------------------------------------------------------------------------------

@@ -976,10 +976,17 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
         FSB_TRY(bn_backward(net, s, B.dr0a, B.dr0b, B.zp, B.g, B.bn_a, P[P_PRELUA], kNoRes, kNoDrop, G(pb + P_BNA_W),
                             G(pb + P_BNA_B), G(pb + P_PRELUA), B.dzp, FMT_F32, nullptr, GS + B_A, CAT_ELT_BWD));
         if (c.two_d && k == 0) {
-            RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
-                conv0_backward(net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift, B.bn_in.mean,
-                               B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, net->conv0_amax, B.g, G(pb + P_CONV_W),
-                               G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->conv0_scratch, s));
+            if (prec != 0 && net->conv0_tc && conv0_tc_supported(B.g))
+                RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
+                    conv0_tc_backward(prec, net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift,
+                                      B.bn_in.mean, B.bn_in.invstd, P[P_CONV_W], B.dzp, net->conv0_amax, GS + B_A, B.g,
+                                      G(pb + P_CONV_W), G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B),
+                                      net->conv0_scratch, s));
+            else
+                RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
+                    conv0_backward(net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift, B.bn_in.mean,
+                                   B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, net->conv0_amax, B.g, G(pb + P_CONV_W),
+                                   G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->conv0_scratch, s));
         } else {
             RUN(CAT_ELT_BWD, 0, maxpool_backward(B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt_e, GS + B_A, s));
             FSB_TRY(fork());
