@@ -126,6 +126,28 @@ __device__ __forceinline__ float gs_inv_scale(const unsigned* absmax_bits) {
     return absmax_bits ? __uint_as_float((unsigned)(127 - gs_exponent(*absmax_bits)) << 23) : 1.f;
 }
 
+// GradScale of a tensor whose bound is the PRODUCT of a stored bound and a float multiplier (dgrad outputs of the compact
+// backward: |dA| <= max|dZ| * max_ci sum_{co,t} |W|, both already on the device): writer and readers derive the same
+// exponent from the same two device words, so no extra slot or launch is needed.
+__device__ __forceinline__ int gs_exponent2(const unsigned* absmax_bits, const float* mul) {
+    if (!absmax_bits) return 0;
+    unsigned b = *absmax_bits;
+    if (mul) b = __float_as_uint(__uint_as_float(b) * (*mul));
+    return gs_exponent(b);
+}
+__device__ __forceinline__ float gs_pow2(int k) { return __uint_as_float((unsigned)(127 + k) << 23); }
+
+// A gradient tensor as the element-wise backward kernels read it: a float32 plane, or (compact backward of the mixed
+// mode) ONE half plane holding 2^k * gradient with k = gs_exponent2(bits, mul).
+struct GradRef {
+    const void* p;
+    int half;                // 1 = half plane
+    const unsigned* bits;    // half: bound slot (GradScale)
+    const float* mul;        // half, optional: multiplier of the bound
+};
+inline GradRef grad_f32(const float* p) { return GradRef{p, 0, nullptr, nullptr}; }
+inline GradRef grad_h16(const void* p, const unsigned* bits, const float* mul = nullptr) { return GradRef{p, 1, bits, mul}; }
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace fsb

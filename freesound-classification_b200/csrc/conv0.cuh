@@ -30,9 +30,9 @@ int conv0_tc_forward(int precision, const float* feat, int N, int H, int W, cons
 // dz_absmax: GradScale slot of dzp (common.cuh), may be null.  Needs scale[0], scale[1] != 0 (checked on the device: the
 // result is then NaN-free but the BatchNorm-input terms are computed by the CUDA-core kernel instead -- see net.cu).
 int conv0_tc_backward(int precision, const float* feat, int N, int H, int W, const float* scale, const float* shift,
-                      const float* mean, const float* invstd, const float* w, const float* dzp, const unsigned char* amax,
-                      const unsigned* dz_absmax, const Geo& gp, float* dw, float* db, float* dgamma_in, float* dbeta_in,
-                      void* scratch, cudaStream_t s);
+                      const float* mean, const float* invstd, const float* w, const void* dzp, int dzp_half,
+                      const unsigned char* amax, const unsigned* dz_absmax, const Geo& gp, float* dw, float* db,
+                      float* dgamma_in, float* dbeta_in, void* scratch, cudaStream_t s);
 // fixed-order sum of `nblk` per-CTA records [22][Cs] (18 dW taps, 2 d(gamma_in) terms, 2 d(beta_in) terms per channel)
 int conv0_bwd_finalize(const float* partials, int nblk, const Geo& gp, float* dw, float* db, float* dgamma_in,
                        float* dbeta_in, cudaStream_t s);

@@ -48,16 +48,8 @@ __device__ __forceinline__ float c0t_freq_enc(int h, int H) {
     return h < H / 2 ? -1.0f + step * (float)h : 1.0f - step * (float)(H - 1 - h);
 }
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-
 // 16-byte chunk `c` (0..3) of 64-byte row `r` of a SWIZZLE_64B tile (Swizzle<2,4,3>: address bits [4,6) ^= bits [7,9))
 __device__ __forceinline__ uint32_t sw64(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
-
-__device__ __forceinline__ void st_shared_v4_u32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
 // writes K values v[0..17] (zero padded to 32) as row r of the hi (and lo) plane at smem address `base`
 __device__ __forceinline__ void write_k_row(uint32_t base, uint32_t r, const float* v, int planes) {
@@ -272,6 +264,7 @@ struct Conv0TcBwdParams {
     const float* invstd;
     const float* w;
     const float* dzp;
+    int dzp_half;           // 1: dzp is ONE half plane that already carries the GradScale of `absmax` (compact backward)
     const unsigned char* amax;
     const unsigned* absmax;
     Geo gp;
@@ -335,22 +328,36 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_tc_bwd_kernel(const Conv
             for (uint32_t c = 0; c < 8; ++c) {
                 const int ch0 = (int)(half * 64u + c * 8u);
                 if (ch0 < Cs) {
-                    float g8[8];
                     uint32_t a8[2] = {0u, 0u};
-                    if (live) {
-                        const float4 lo4 = *reinterpret_cast<const float4*>(p.dzp + grow + ch0);
-                        const float4 hi4 = *reinterpret_cast<const float4*>(p.dzp + grow + ch0 + 4);
-                        g8[0] = lo4.x; g8[1] = lo4.y; g8[2] = lo4.z; g8[3] = lo4.w;
-                        g8[4] = hi4.x; g8[5] = hi4.y; g8[6] = hi4.z; g8[7] = hi4.w;
-                        const uint2 am = *reinterpret_cast<const uint2*>(p.amax + grow + ch0);
-                        a8[0] = am.x; a8[1] = am.y;
+                    __align__(16) __half gh[8];
+                    __half gl[8];
+                    if (p.dzp_half) {
+                        // the half plane is the hi operand as it stands (same GradScale slot); single pass: no lo plane
+                        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                        if (live) {
+                            raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.dzp) + grow + ch0);
+                            const uint2 am = *reinterpret_cast<const uint2*>(p.amax + grow + ch0);
+                            a8[0] = am.x; a8[1] = am.y;
+                        }
+                        *reinterpret_cast<uint4*>(gh) = raw;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) gl[i] = __float2half_rn(0.f);
                     } else {
+                        float g8[8];
+                        if (live) {
+                            const float4 lo4 = *reinterpret_cast<const float4*>(p.dzp + grow + ch0);
+                            const float4 hi4 = *reinterpret_cast<const float4*>(p.dzp + grow + ch0 + 4);
+                            g8[0] = lo4.x; g8[1] = lo4.y; g8[2] = lo4.z; g8[3] = lo4.w;
+                            g8[4] = hi4.x; g8[5] = hi4.y; g8[6] = hi4.z; g8[7] = hi4.w;
+                            const uint2 am = *reinterpret_cast<const uint2*>(p.amax + grow + ch0);
+                            a8[0] = am.x; a8[1] = am.y;
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) g8[i] = 0.f;
+                            for (int i = 0; i < 8; ++i) g8[i] = 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split_h16(g8[i] * gscale, gh[i], gl[i]);
                     }
-                    __half gh[8], gl[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) split_h16(g8[i] * gscale, gh[i], gl[i]);
 #pragma unroll
                     for (uint32_t pos = 0; pos < 4; ++pos) {
                         uint32_t wh[4], wl[4];
@@ -494,14 +501,15 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_tc_bwd_kernel(const Conv
 }  // namespace
 
 int conv0_tc_backward(int precision, const float* feat, int N, int H, int W, const float* scale, const float* shift,
-                      const float* mean, const float* invstd, const float* w, const float* dzp, const unsigned char* amax,
-                      const unsigned* dz_absmax, const Geo& gp, float* dw, float* db, float* dgamma_in, float* dbeta_in,
-                      void* scratch, cudaStream_t s) {
+                      const float* mean, const float* invstd, const float* w, const void* dzp, int dzp_half,
+                      const unsigned char* amax, const unsigned* dz_absmax, const Geo& gp, float* dw, float* db,
+                      float* dgamma_in, float* dbeta_in, void* scratch, cudaStream_t s) {
     FSB_REQUIRE(conv0_tc_supported(gp) && (precision == 1 || precision == 2) && amax, "conv0_tc_backward: unsupported");
+    FSB_REQUIRE(!dzp_half || (precision == 2 && dz_absmax), "conv0_tc_backward: a half dzp needs the single-pass mode and its GradScale");
     Conv0TcBwdParams p;
     p.feat = feat; p.N = N; p.H = H; p.W = W;
     p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd; p.w = w;
-    p.dzp = dzp; p.amax = amax; p.absmax = dz_absmax; p.gp = gp;
+    p.dzp = (const float*)dzp; p.dzp_half = dzp_half; p.amax = amax; p.absmax = dz_absmax; p.gp = gp;
     p.planes = precision == 1 ? 2 : 1;
     p.npix = (long long)N * gp.H * gp.W;
     p.ntiles = (int)((p.npix + C0B_PX - 1) / C0B_PX);

@@ -76,6 +76,15 @@ int pf_build_mask(const Geo& g, unsigned char* mask, cudaStream_t s) {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldh4(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 ld_grad(const GradRef& r, long long idx) {
+    return r.half ? ldh4(reinterpret_cast<const __half*>(r.p) + idx) : ld4(reinterpret_cast<const float*>(r.p) + idx);
+}
 
 // writes four channels in the destination format; half formats multiply by `scale` first (1 for activations, the
 // tensor's power-of-two GradScale for gradients, common.cuh)
@@ -496,9 +505,12 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
+// amax (optional, training): position 0..3 of the first maximum of every window in scan order, one byte per pooled
+// element -- the backward pass routes by it instead of re-reading the four full-resolution planes
 template <bool STATS>
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int pool_h, double* out_stats) {
+maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int pool_h, double* out_stats,
+                   unsigned char* amax) {
     EW_PROLOGUE
     if (!STATS && !cok) return;
     Acc4 acc[2];
@@ -510,12 +522,33 @@ maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int p
             const unsigned rr = (unsigned)(row - (long long)n * img);
             const int y = (int)(rr / (unsigned)g.Wp) - g.padH, x = (int)(rr % (unsigned)g.Wp) - g.padW;
             long long r00 = geo_row(gf, n, y * pool_h, 2 * x);
-            float4 m = max4(ld4(zf + r00 * gf.Cs + c0), ld4(zf + (r00 + 1) * gf.Cs + c0));
+            const float4 v0 = ld4(zf + r00 * gf.Cs + c0), v1 = ld4(zf + (r00 + 1) * gf.Cs + c0);
+            float4 v2 = v0, v3 = v0;
+            float4 m = max4(v0, v1);
             if (pool_h == 2) {
                 long long r10 = r00 + gf.Wp;
-                m = max4(m, max4(ld4(zf + r10 * gf.Cs + c0), ld4(zf + (r10 + 1) * gf.Cs + c0)));
+                v2 = ld4(zf + r10 * gf.Cs + c0);
+                v3 = ld4(zf + (r10 + 1) * gf.Cs + c0);
+                m = max4(m, max4(v2, v3));
             }
             st4(zp + row * g.Cs + c0, m);
+            if (amax) {
+                const float a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w};
+                const float a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w};
+                unsigned packed = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    unsigned best = 0u;
+                    float bv = a0[i];
+                    if (a1[i] > bv) { bv = a1[i]; best = 1u; }
+                    if (pool_h == 2) {
+                        if (a2[i] > bv) { bv = a2[i]; best = 2u; }
+                        if (a3[i] > bv) { bv = a3[i]; best = 3u; }
+                    }
+                    packed |= best << (8 * i);
+                }
+                *reinterpret_cast<unsigned*>(amax + row * g.Cs + c0) = packed;
+            }
             if (STATS) {
                 acc[0].add(m);
                 acc[1].add(make_float4(m.x * m.x, m.y * m.y, m.z * m.z, m.w * m.w));
@@ -526,13 +559,13 @@ maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int p
 }
 
 int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, double* out_stats,
-                    cudaStream_t s) {
+                    unsigned char* amax, cudaStream_t s) {
     EW_CHECK(gp);
     EwShape sh = ew_shape(gp);
     if (out_stats)
-        maxpool_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, out_stats);
+        maxpool_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, out_stats, amax);
     else
-        maxpool_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr);
+        maxpool_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr, amax);
     FSB_LAUNCHED();
     return 0;
 }
@@ -610,6 +643,68 @@ int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo
                 "maxpool_backward: geometries are not a floor-mode 2x pooling pair");
     EwShape sh = ew_shape(gp);
     maxpool_bwd_kernel<<<sh.grid, sh.block, 0, s>>>(dzp, gp, zf, gf, pool_h, dzf, fmt, absmax);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// Same routing from the stored arg-max bytes: reads dzp (float32, or a half plane that already carries the GradScale
+// of `absmax`) and one byte per pooled element instead of the four full-resolution planes of zf.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_amax_kernel(const GradRef dzp, Geo gp, const unsigned char* __restrict__ amax, Geo g, int pool_h,
+                        void* dzf, int fmt, const unsigned* absmax) {
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= g.Cs / 4) return;
+    // half source: stored 2^k1 g, destination wants 2^k2 g (k1 == k2 when both use the same slot: exact copy)
+    const float gscale = gs_scale(absmax) * (dzp.half ? gs_pow2(-gs_exponent2(dzp.bits, dzp.mul)) : 1.f);
+    const int c0 = cv * 4;
+    const long long plane = g.rows * g.Cs;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool odd_w = g.W > 2 * gp.W, odd_h = pool_h == 2 && g.H > 2 * gp.H;
+    for (long long prow = (long long)blockIdx.x * blockDim.y + threadIdx.y; prow < gp.rows;
+         prow += (long long)gridDim.x * blockDim.y) {
+        if (gp.mask != nullptr && !gp.mask[prow]) continue;
+        const unsigned img = (unsigned)(gp.Hp * gp.Wp);
+        const int n = (int)((unsigned long long)prow / img);
+        const unsigned rr = (unsigned)(prow - (long long)n * img);
+        const int py = (int)(rr / (unsigned)gp.Wp) - gp.padH, px = (int)(rr % (unsigned)gp.Wp) - gp.padW;
+        const long long r00 = geo_row(g, n, py * pool_h, 2 * px);
+        const float4 gsrc = ld_grad(dzp, prow * gp.Cs + c0);
+        const unsigned am = *reinterpret_cast<const unsigned*>(amax + prow * gp.Cs + c0);
+        const float gs[4] = {gsrc.x, gsrc.y, gsrc.z, gsrc.w};
+        float o[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int best = (int)((am >> (8 * i)) & 0xFFu);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k][i] = best == k ? gs[i] : 0.f;
+        }
+        store_fmt(dzf, fmt, plane, r00 * g.Cs + c0, make_float4(o[0][0], o[0][1], o[0][2], o[0][3]), gscale);
+        store_fmt(dzf, fmt, plane, (r00 + 1) * g.Cs + c0, make_float4(o[1][0], o[1][1], o[1][2], o[1][3]), gscale);
+        if (pool_h == 2) {
+            store_fmt(dzf, fmt, plane, (r00 + g.Wp) * g.Cs + c0, make_float4(o[2][0], o[2][1], o[2][2], o[2][3]), gscale);
+            store_fmt(dzf, fmt, plane, (r00 + g.Wp + 1) * g.Cs + c0, make_float4(o[3][0], o[3][1], o[3][2], o[3][3]), gscale);
+        }
+        const bool last_x = odd_w && px == gp.W - 1, last_y = odd_h && py == gp.H - 1;
+        if (last_x) {
+            store_fmt(dzf, fmt, plane, (r00 + 2) * g.Cs + c0, zero);
+            if (pool_h == 2) store_fmt(dzf, fmt, plane, (r00 + g.Wp + 2) * g.Cs + c0, zero);
+        }
+        if (last_y) {
+            store_fmt(dzf, fmt, plane, (r00 + 2 * g.Wp) * g.Cs + c0, zero);
+            store_fmt(dzf, fmt, plane, (r00 + 2 * g.Wp + 1) * g.Cs + c0, zero);
+            if (last_x) store_fmt(dzf, fmt, plane, (r00 + 2 * g.Wp + 2) * g.Cs + c0, zero);
+        }
+    }
+}
+
+int maxpool_backward_amax(GradRef dzp, const Geo& gp, const unsigned char* amax, const Geo& gf, int pool_h, void* dzf,
+                          int fmt, const unsigned* absmax, cudaStream_t s) {
+    EW_CHECK(gf);
+    EW_CHECK(gp);
+    FSB_REQUIRE(gf.W - 2 * gp.W <= 1 && gf.W >= 2 * gp.W && (pool_h == 1 ? gf.H == gp.H : (gf.H - 2 * gp.H <= 1 && gf.H >= 2 * gp.H)),
+                "maxpool_backward: geometries are not a floor-mode 2x pooling pair");
+    EwShape sh = ew_shape(gp);
+    maxpool_bwd_amax_kernel<<<sh.grid, sh.block, 0, s>>>(dzp, gp, amax, gf, pool_h, dzf, fmt, absmax);
     FSB_LAUNCHED();
     return 0;
 }
@@ -729,25 +824,34 @@ int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* 
 
 // ---------------------------------------------------------------------------------------------
 // backward of a = act(BN(z) [+ r]) : shared recomputation of dy (and the PReLU slope term)
+//
+// Compact backward (mixed mode): the incoming gradient may be ONE half plane with a GradScale (written by the dgrad
+// epilogue), and zhat / the PReLU branch may be taken from the hi plane of the stored activation `a` instead of the
+// float32 pre-activation z -- half the bytes per element on both inputs.  The inverse map a -> y -> zhat is used per
+// thread (four channels) only where it is well conditioned: 1/64 <= slope <= 16, gamma != 0 and |beta| <= 8 |gamma|
+// (zhat error <= 2^-12 (|zhat| + 8)); every other channel group reads z as before.
 struct BwdCoef {
     Coef4 cb, cr;
-    float4 mean, invstd;
-    bool has_res;
+    float4 mean, invstd;      // from_a: beta, 1 / gamma
+    float4 rsl;               // from_a: 1 / slope
+    float inv1, inv2;         // inverse GradScale of the two incoming gradient planes (1 for float32 planes)
+    bool has_res, from_a;
 };
 
 struct BwdIn {
     float4 z, r, g, g2;
 };
 
+
 // RES: the activation has a residual branch (res.zr); DA2: the incoming gradient is dA1 + dA2
 template <bool RES, bool DA2>
-__device__ __forceinline__ BwdIn bwd_load(const float* dA1, const float* dA2, const float* z, const float* zr,
-                                          long long idx) {
+__device__ __forceinline__ BwdIn bwd_load(const GradRef& dA1, const GradRef& dA2, const float* z, const __half* a,
+                                          bool from_a, const float* zr, long long idx) {
     BwdIn in;
-    in.z = ld4(z + idx);
-    in.g = ld4(dA1 + idx);
+    in.z = from_a ? ldh4(a + idx) : ld4(z + idx);
+    in.g = ld_grad(dA1, idx);
     if (RES) in.r = ld4(zr + idx);
-    if (DA2) in.g2 = ld4(dA2 + idx);
+    if (DA2) in.g2 = ld_grad(dA2, idx);
     return in;
 }
 
@@ -755,14 +859,22 @@ template <bool RES, bool DA2>
 __device__ __forceinline__ void bwd_compute(const BwdIn& in, const BwdCoef& k, const Dropout& dr, long long idx,
                                             float4& dy, float4& zhat, float4& dsl) {
     const float4 zz = in.z;
-    float4 y = affine4(zz, k.cb.sc, k.cb.sh);
+    float4 y;
+    if (!RES && k.from_a) {
+        // zz holds a = prelu(y): invert the activation (slope > 0, so the sign of a is the sign of y)
+        y = k.cb.has_sl ? make_float4(zz.x > 0.f ? zz.x : zz.x * k.rsl.x, zz.y > 0.f ? zz.y : zz.y * k.rsl.y,
+                                      zz.z > 0.f ? zz.z : zz.z * k.rsl.z, zz.w > 0.f ? zz.w : zz.w * k.rsl.w)
+                        : zz;
+    } else {
+        y = affine4(zz, k.cb.sc, k.cb.sh);
+    }
     if (RES) {
         float4 r = affine4(in.r, k.cr.sc, k.cr.sh);
         if (k.cr.has_sl) r = prelu4(r, k.cr.sl);
         y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
     }
-    float4 g = in.g;
-    if (DA2) { g.x += in.g2.x; g.y += in.g2.y; g.z += in.g2.z; g.w += in.g2.w; }
+    float4 g = make_float4(in.g.x * k.inv1, in.g.y * k.inv1, in.g.z * k.inv1, in.g.w * k.inv1);
+    if (DA2) { g.x = fmaf(in.g2.x, k.inv2, g.x); g.y = fmaf(in.g2.y, k.inv2, g.y); g.z = fmaf(in.g2.z, k.inv2, g.z); g.w = fmaf(in.g2.w, k.inv2, g.w); }
     if (dr.p > 0.f) {
         g.x *= keep_scale(dr, idx); g.y *= keep_scale(dr, idx + 1);
         g.z *= keep_scale(dr, idx + 2); g.w *= keep_scale(dr, idx + 3);
@@ -776,18 +888,51 @@ __device__ __forceinline__ void bwd_compute(const BwdIn& in, const BwdCoef& k, c
         dsl = make_float4(0.f, 0.f, 0.f, 0.f);
         dy = g;
     }
-    zhat = make_float4((zz.x - k.mean.x) * k.invstd.x, (zz.y - k.mean.y) * k.invstd.y,
-                       (zz.z - k.mean.z) * k.invstd.z, (zz.w - k.mean.w) * k.invstd.w);
+    // (z - mean) * invstd, or (y - beta) * (1 / gamma) when working from the stored activation
+    const float4 base = (!RES && k.from_a) ? y : zz;
+    zhat = make_float4((base.x - k.mean.x) * k.invstd.x, (base.y - k.mean.y) * k.invstd.y,
+                       (base.z - k.mean.z) * k.invstd.z, (base.w - k.mean.w) * k.invstd.w);
 }
 
 template <bool RES>
-__device__ __forceinline__ BwdCoef load_bwd(const BnCoef& bn, const Residual& res, int c0) {
+__device__ __forceinline__ BwdCoef load_bwd(const BnCoef& bn, const Residual& res, const GradRef& dA1, const GradRef& dA2,
+                                            const void* a_hi, int c0) {
     BwdCoef k;
     k.cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
     k.has_res = RES;
     if (RES) k.cr = load_coef(res.scale, res.shift, res.slope, c0);
     k.mean = ld4(bn.mean + c0);
     k.invstd = ld4(bn.invstd + c0);
+    k.rsl = make_float4(1.f, 1.f, 1.f, 1.f);
+    k.inv1 = dA1.half ? gs_pow2(-gs_exponent2(dA1.bits, dA1.mul)) : 1.f;
+    k.inv2 = (dA2.p && dA2.half) ? gs_pow2(-gs_exponent2(dA2.bits, dA2.mul)) : 1.f;
+    k.from_a = false;
+    if (!RES && a_hi) {
+        const float sc[4] = {k.cb.sc.x, k.cb.sc.y, k.cb.sc.z, k.cb.sc.w}, sh[4] = {k.cb.sh.x, k.cb.sh.y, k.cb.sh.z, k.cb.sh.w};
+        const float sl[4] = {k.cb.sl.x, k.cb.sl.y, k.cb.sl.z, k.cb.sl.w};
+        const float mu[4] = {k.mean.x, k.mean.y, k.mean.z, k.mean.w}, is[4] = {k.invstd.x, k.invstd.y, k.invstd.z, k.invstd.w};
+        float beta[4], rg[4], rs[4];
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (sc[i] == 0.f && is[i] == 0.f) {          // padded channel: a = 0, zhat = 0
+                beta[i] = 0.f; rg[i] = 0.f; rs[i] = 1.f;
+                continue;
+            }
+            const float gamma = sc[i] / is[i];
+            beta[i] = fmaf(mu[i], sc[i], sh[i]);
+            rg[i] = 1.f / gamma;
+            rs[i] = 1.f / sl[i];
+            ok = ok && fabsf(gamma) > 0.f && fabsf(beta[i]) <= 8.f * fabsf(gamma) && fabsf(rg[i]) < 3.0e38f &&
+                 (!k.cb.has_sl || (sl[i] >= 0.015625f && sl[i] <= 16.f));
+        }
+        if (ok) {
+            k.from_a = true;
+            k.mean = make_float4(beta[0], beta[1], beta[2], beta[3]);
+            k.invstd = make_float4(rg[0], rg[1], rg[2], rg[3]);
+            k.rsl = make_float4(rs[0], rs[1], rs[2], rs[3]);
+        }
+    }
     return k;
 }
 
@@ -796,19 +941,25 @@ __device__ __forceinline__ void fma4(float4& a, const float4& b, const float4& c
     a.x = fmaf(b.x, c.x, a.x); a.y = fmaf(b.y, c.y, a.y); a.z = fmaf(b.z, c.z, a.z); a.w = fmaf(b.w, c.w, a.w);
 }
 
+bool bn_bwd_compact_ok(const GradRef& dA1, const GradRef& dA2, const Geo& g, const Residual& res, const Dropout& dr);
+static int bn_bwd_c8_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
+                            double* partials, cudaStream_t s);
+static int bn_bwd_c8_apply(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
+                           const float* c1, const float* c2, void* dz, int fmt, const unsigned* absmax, cudaStream_t s);
+
 // Per-thread float32 partial sums (a thread visits rows / (gridDim.x * blockDim.y) ~ 10^2 pixels); the cross-thread
 // and cross-block reductions run in double.
 template <bool RES, bool DA2>
 __global__ void __launch_bounds__(256, 2)
-bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2,
-                         const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr_in,
-                         double* partials) {
+bn_act_bwd_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
+                         BnCoef bn, Residual res, Dropout dr_in, double* partials) {
     const Dropout dr = resolve_seed(dr_in);
     EW_PROLOGUE
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
     float4 mx = s0, zx = s0;              // max |dy|, max |zhat|: bound of |dz| for the half-precision gradient scale
     if (cok) {
-        BwdCoef k = load_bwd<RES>(bn, res, c0);
+        const BwdCoef k = load_bwd<RES>(bn, res, dA1, dA2, a_hi, c0);
+        const __half* ah = reinterpret_cast<const __half*>(a_hi);
         // ROWS rows in flight per thread (two loads each in the plain variant): see bn_act_fwd_simple_kernel
         constexpr int ROWS = (RES || DA2) ? 2 : 4;
         const long long stride = (long long)gridDim.x * blockDim.y;
@@ -824,7 +975,7 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict_
             }
 #pragma unroll
             for (int j = 0; j < ROWS; ++j)
-                if (ok[j]) in[j] = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idx[j]);
+                if (ok[j]) in[j] = bwd_load<RES, DA2>(dA1, dA2, z, ah, k.from_a, res.zr, idx[j]);
 #pragma unroll
             for (int j = 0; j < ROWS; ++j)
                 if (ok[j]) {
@@ -843,24 +994,26 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dA1, const float* __restrict_
     block_reduce_store<5, 2>(acc, partials, g.Cs, c0, cok);
 }
 
-int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
-                      Dropout dr, double* partials, cudaStream_t s) {
+int bn_act_bwd_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
+                      Residual res, Dropout dr, double* partials, cudaStream_t s) {
     EW_CHECK(g);
-    FSB_REQUIRE(!(res.zr && dA2), "bn_act_bwd: residual and second gradient are mutually exclusive");
+    FSB_REQUIRE(!(res.zr && dA2.p), "bn_act_bwd: residual and second gradient are mutually exclusive");
+    if (bn_bwd_compact_ok(dA1, dA2, g, res, dr)) return bn_bwd_c8_reduce(dA1, dA2, z, a_hi, g, bn, partials, s);
     EwShape sh = ew_shape(g);
     if (res.zr)
-        bn_act_bwd_reduce_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
-    else if (dA2)
-        bn_act_bwd_reduce_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
+        bn_act_bwd_reduce_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, partials);
+    else if (dA2.p)
+        bn_act_bwd_reduce_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, partials);
     else
-        bn_act_bwd_reduce_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
+        bn_act_bwd_reduce_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, partials);
     FSB_LAUNCHED();
     return 0;
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
 bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
-                       float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax) {
+                       float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
+                       unsigned* absmax_dy) {
     const int c = blockIdx.x * FIN_CH + (threadIdx.x % FIN_CH);
     double tot[5];
     reduce_partials<5, 2>(partials, nblk, Cs, c, tot);
@@ -878,65 +1031,505 @@ bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C,
         const float bound = 1.001f * fabsf(bn_scale[c]) * ((float)tot[3] + fabsf(m1) + (float)tot[4] * fabsf(m2));
         if (bound > 0.f) atomicMax(absmax, __float_as_uint(bound));
     }
+    if (absmax_dy) {                      // bound of the residual-branch gradient dres = dy (written as a half plane)
+        const float bound = 1.001f * (float)tot[3];
+        if (bound > 0.f) atomicMax(absmax_dy, __float_as_uint(bound));
+    }
 }
 
 int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
                     float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
-                    cudaStream_t s) {
+                    unsigned* absmax_dy, cudaStream_t s) {
     bn_bwd_finalize_kernel<<<(Cs + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, s>>>(partials, nblk, count, C, Cs, bn_scale, dgamma,
-                                                                              dbeta, dslope, c1, c2, absmax);
+                                                                              dbeta, dslope, c1, c2, absmax, absmax_dy);
     FSB_LAUNCHED();
     return 0;
 }
 
+// dres: float32 plane, or (dres_bits != nullptr) one half plane with the GradScale of *dres_bits
+__device__ __forceinline__ void store_dres(void* dres, const unsigned* dres_bits, float dscale, long long idx, float4 dy) {
+    if (dres_bits) {
+        __half2 a = __floats2half2_rn(dy.x * dscale, dy.y * dscale), b = __floats2half2_rn(dy.z * dscale, dy.w * dscale);
+        uint2 u;
+        u.x = *reinterpret_cast<unsigned*>(&a);
+        u.y = *reinterpret_cast<unsigned*>(&b);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dres) + idx) = u;
+    } else {
+        st4(reinterpret_cast<float*>(dres) + idx, dy);
+    }
+}
+
 template <bool RES, bool DA2>
 __global__ void __launch_bounds__(256, 2)
-bn_act_bwd_apply_kernel(const float* __restrict__ dA1, const float* __restrict__ dA2, const float* __restrict__ z,
-                        Geo g, BnCoef bn, Residual res, Dropout dr_in, const float* c1, const float* c2, void* dz,
-                        int fmt, float* dres, const unsigned* absmax) {
+bn_act_bwd_apply_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
+                        BnCoef bn, Residual res, Dropout dr_in, const float* c1, const float* c2, void* dz, int fmt,
+                        void* dres, const unsigned* dres_bits, const unsigned* absmax) {
     const Dropout dr = resolve_seed(dr_in);
     EW_PROLOGUE
     if (!cok) return;
     const float gscale = gs_scale(absmax);
-    BwdCoef k = load_bwd<RES>(bn, res, c0);
+    const float dscale = gs_scale(dres_bits);
+    const BwdCoef k = load_bwd<RES>(bn, res, dA1, dA2, a_hi, c0);
+    const __half* ah = reinterpret_cast<const __half*>(a_hi);
     float4 m1 = ld4(c1 + c0), m2 = ld4(c2 + c0);
     const long long plane = g.rows * g.Cs;
     EW_PIXEL_LOOP2 {
         const long long idxA = rowA * g.Cs + c0, idxB = rowB * g.Cs + c0;
         BwdIn inA, inB;
-        if (okA) inA = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxA);
-        if (okB) inB = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxB);
+        if (okA) inA = bwd_load<RES, DA2>(dA1, dA2, z, ah, k.from_a, res.zr, idxA);
+        if (okB) inB = bwd_load<RES, DA2>(dA1, dA2, z, ah, k.from_a, res.zr, idxB);
         float4 dy, zh, dsl;
         if (okA) {
             bwd_compute<RES, DA2>(inA, k, dr, idxA, dy, zh, dsl);
             float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
                                    k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
             store_fmt(dz, fmt, plane, idxA, o, gscale);
-            if (RES && dres) st4(dres + idxA, dy);
+            if (RES && dres) store_dres(dres, dres_bits, dscale, idxA, dy);
         }
         if (okB) {
             bwd_compute<RES, DA2>(inB, k, dr, idxB, dy, zh, dsl);
             float4 o = make_float4(k.cb.sc.x * (dy.x - m1.x - zh.x * m2.x), k.cb.sc.y * (dy.y - m1.y - zh.y * m2.y),
                                    k.cb.sc.z * (dy.z - m1.z - zh.z * m2.z), k.cb.sc.w * (dy.w - m1.w - zh.w * m2.w));
             store_fmt(dz, fmt, plane, idxB, o, gscale);
-            if (RES && dres) st4(dres + idxB, dy);
+            if (RES && dres) store_dres(dres, dres_bits, dscale, idxB, dy);
         }
     }
 }
 
-int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn, Residual res,
-                     Dropout dr, const float* c1, const float* c2, void* dz, int fmt, float* dres,
-                     const unsigned* absmax, cudaStream_t s) {
+int bn_act_bwd_apply(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn, Residual res,
+                     Dropout dr, const float* c1, const float* c2, void* dz, int fmt, void* dres,
+                     const unsigned* dres_bits, const unsigned* absmax, cudaStream_t s) {
     EW_CHECK(g);
-    FSB_REQUIRE(!(res.zr && dA2), "bn_act_bwd: residual and second gradient are mutually exclusive");
+    FSB_REQUIRE(!(res.zr && dA2.p), "bn_act_bwd: residual and second gradient are mutually exclusive");
     FSB_REQUIRE(res.zr || !dres, "bn_act_bwd: dres needs a residual branch");
+    if (bn_bwd_compact_ok(dA1, dA2, g, res, dr) && (fmt == FMT_F32 || fmt == FMT_H16))
+        return bn_bwd_c8_apply(dA1, dA2, z, a_hi, g, bn, c1, c2, dz, fmt, absmax, s);
     EwShape sh = ew_shape(g);
     if (res.zr)
-        bn_act_bwd_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, absmax);
-    else if (dA2)
-        bn_act_bwd_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, absmax);
+        bn_act_bwd_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
+    else if (dA2.p)
+        bn_act_bwd_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
     else
-        bn_act_bwd_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, absmax);
+        bn_act_bwd_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compact BatchNorm backward (mixed mode, no residual branch): every operand is a half plane, so a thread owns EIGHT
+// channels and every access is 16 bytes (the 4-channel kernels above would move 8 bytes per load and, being latency
+// bound, lose what the smaller planes save).  Gradients arrive as scaled half planes (GradRef), zhat and the PReLU branch
+// come from the hi plane of the stored activation where the inverse map is well conditioned (see BwdCoef above) and from
+// the float32 z otherwise -- decided per thread.  Partials / finalize are those of the 4-channel kernels.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8_scaled(const float (&f)[8], float scale) {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        // clamp to the half range; NaN stays NaN (fminf / fmaxf would drop it)
+        const float x0 = f[2 * i] * scale, x1 = f[2 * i + 1] * scale;
+        const float lo = x0 == x0 ? fminf(fmaxf(x0, -65504.f), 65504.f) : x0, hi = x1 == x1 ? fminf(fmaxf(x1, -65504.f), 65504.f) : x1;
+        const __half2 h = __floats2half2_rn(lo, hi);
+        w[i] = *reinterpret_cast<const unsigned*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// may this thread's eight channels work from the stored activation?
+__device__ __forceinline__ bool c8_from_a(const BnCoef& bn, const void* a_hi, int c0, int C) {
+    bool ok = a_hi != nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (c0 + i >= C) continue;                        // padded channel (the slope vector has C entries only)
+        const float sc = bn.scale[c0 + i], is = bn.invstd[c0 + i];
+        const float gamma = sc / is, beta = fmaf(bn.mean[c0 + i], sc, bn.shift[c0 + i]);
+        const float sl = bn.slope ? bn.slope[c0 + i] : 1.f;
+        ok = ok && fabsf(gamma) > 0.f && fabsf(beta) <= 8.f * fabsf(gamma) && fabsf(1.f / gamma) < 3.0e38f &&
+             sl >= 0.015625f && sl <= 16.f;
+    }
+    return ok;
+}
+
+// Per-channel coefficients of one path.  FROM_A: y = a > 0 ? a : a * e (e = 1 / slope), zhat = y * b + a_ (b = 1 / gamma,
+// a_ = -beta / gamma).  From z: y = z * e + f (e = scale, f = shift), zhat = z * b + a_ (b = invstd, a_ = -mean * invstd).
+template <bool FROM_A>
+struct C8Coef {
+    float e[8], f[FROM_A ? 1 : 8], sl[8], a[8], b[8];
+    bool has_sl;
+    __device__ __forceinline__ void load(const BnCoef& bn, int c0, int C) {
+        has_sl = bn.slope != nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float sc = bn.scale[c0 + i], sh = bn.shift[c0 + i], mu = bn.mean[c0 + i], is = bn.invstd[c0 + i];
+            sl[i] = (has_sl && c0 + i < C) ? bn.slope[c0 + i] : 1.f;     // padded channels: scale = shift = 0, everything stays 0
+            if (FROM_A) {
+                const bool pad = sc == 0.f && is == 0.f;
+                const float rg = pad ? 0.f : is / sc;                 // 1 / gamma
+                e[i] = 1.f / sl[i];
+                b[i] = rg;
+                a[i] = pad ? 0.f : -fmaf(mu, sc, sh) * rg;
+            } else {
+                e[i] = sc; f[i] = sh;
+                b[i] = is;
+                a[i] = -mu * is;
+            }
+        }
+    }
+};
+
+template <bool DA2, bool FROM_A>
+struct C8In {
+    uint4 s0, s1;      // source: a (s0 only) or z (two float4)
+    uint4 g1, g2;
+    __device__ __forceinline__ void load(const GradRef& dA1, const GradRef& dA2, const float* z, const __half* a, long long idx) {
+        if (FROM_A) {
+            s0 = *reinterpret_cast<const uint4*>(a + idx);
+        } else {
+            s0 = *reinterpret_cast<const uint4*>(z + idx);
+            s1 = *reinterpret_cast<const uint4*>(z + idx + 4);
+        }
+        g1 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(dA1.p) + idx);
+        if (DA2) g2 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(dA2.p) + idx);
+    }
+};
+
+// dy, zhat and the PReLU-slope gradient term of the eight channels
+template <bool DA2, bool FROM_A>
+__device__ __forceinline__ void c8_compute(const C8In<DA2, FROM_A>& in, const C8Coef<FROM_A>& k, float inv1, float inv2,
+                                           float (&dy)[8], float (&zh)[8], float (&dsl)[8]) {
+    float src[8], g[8];
+    if (FROM_A) {
+        unpack8(in.s0, src);
+    } else {
+        const unsigned w[8] = {in.s0.x, in.s0.y, in.s0.z, in.s0.w, in.s1.x, in.s1.y, in.s1.z, in.s1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) src[i] = __uint_as_float(w[i]);
+    }
+    unpack8(in.g1, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] *= inv1;
+    if (DA2) {
+        float g2[8];
+        unpack8(in.g2, g2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(g2[i], inv2, g[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float v = src[i];
+        const float y = FROM_A ? ((v > 0.f || !k.has_sl) ? v : v * k.e[i]) : fmaf(v, k.e[i], k.f[i]);
+        const bool pos = y > 0.f || !k.has_sl;
+        dy[i] = pos ? g[i] : k.sl[i] * g[i];
+        dsl[i] = pos ? 0.f : y * g[i];
+        zh[i] = fmaf(FROM_A ? y : v, k.b[i], k.a[i]);
+    }
+}
+
+struct C8Sums {
+    float s0[8], s1[8], s2[8];
+    float mx, zx;          // max |dy|, max |zhat| over the thread's eight channels (a common bound for all eight)
+};
+
+template <int ROWS, typename In>
+__device__ __forceinline__ void c8_load_rows(In (&in)[ROWS], bool (&ok)[ROWS], const GradRef& dA1, const GradRef& dA2,
+                                             const float* z, const __half* ah, const Geo& g, long long row0,
+                                             long long stride, int c0) {
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        const long long row = row0 + j * stride;
+        ok[j] = row < g.rows && (g.mask == nullptr || g.mask[row]);
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j)
+        if (ok[j]) in[j].load(dA1, dA2, z, ah, (row0 + j * stride) * g.Cs + c0);
+}
+
+// ---- fast path (from the stored activation): everything folded into per-channel select-and-FMA coefficients.
+//   pos = a > 0;  dy = g (pos ? inv1 : sl inv1);  zhat = a (pos ? 1/gamma : 1/(slope gamma)) - beta/gamma;
+//   slope term = (1/slope) sum_{!pos} a g inv1   (no activation: sl = 1 and the slope term is dropped)
+template <bool DA2>
+__device__ __forceinline__ void c8_reduce_fast(const GradRef& dA1, const GradRef& dA2, const __half* ah, const Geo& g,
+                                               const BnCoef& bn, int c0, C8Sums& S) {
+    const float inv1 = gs_pow2(-gs_exponent2(dA1.bits, dA1.mul));
+    const float ratio = DA2 ? gs_pow2(gs_exponent2(dA1.bits, dA1.mul) - gs_exponent2(dA2.bits, dA2.mul)) : 0.f;   // inv2 / inv1
+    const bool has_sl = bn.slope != nullptr;
+    float slI[8], bp[8], bn_[8], a0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float sc = bn.scale[c0 + i], sh = bn.shift[c0 + i], mu = bn.mean[c0 + i], is = bn.invstd[c0 + i];
+        const bool pad = c0 + i >= g.C;                  // padded channel: a = g = 0, every coefficient 0
+        const float sl = (has_sl && !pad) ? bn.slope[c0 + i] : 1.f;
+        const float rg = pad ? 0.f : is / sc;
+        slI[i] = pad ? 0.f : sl * inv1;
+        bp[i] = rg;
+        bn_[i] = rg / sl;
+        a0[i] = pad ? 0.f : -fmaf(mu, sc, sh) * rg;
+    }
+    constexpr int ROWS = DA2 ? 2 : 4;
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long row0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; row0 < g.rows; row0 += ROWS * stride) {
+        bool ok[ROWS];
+        C8In<DA2, true> in[ROWS];
+        c8_load_rows<ROWS>(in, ok, dA1, dA2, nullptr, ah, g, row0, stride, c0);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) {
+                float av[8], gv[8];
+                unpack8(in[j].s0, av);
+                unpack8(in[j].g1, gv);
+                if (DA2) {
+                    float g2[8];
+                    unpack8(in[j].g2, g2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gv[i] = fmaf(g2[i], ratio, gv[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool pos = av[i] > 0.f;
+                    const float dy = gv[i] * (pos ? inv1 : slI[i]);
+                    const float zh = fmaf(av[i], pos ? bp[i] : bn_[i], a0[i]);
+                    S.s2[i] = fmaf(av[i], pos ? 0.f : gv[i], S.s2[i]);
+                    S.s0[i] += dy;
+                    S.s1[i] = fmaf(dy, zh, S.s1[i]);
+                    S.mx = fmaxf(S.mx, fabsf(dy));
+                    S.zx = fmaxf(S.zx, fabsf(zh));
+                }
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S.s2[i] = (has_sl && c0 + i < g.C) ? S.s2[i] * inv1 / bn.slope[c0 + i] : 0.f;
+}
+
+template <bool DA2, bool OUT_F32>
+__device__ __forceinline__ void c8_apply_fast(const GradRef& dA1, const GradRef& dA2, const __half* ah, const Geo& g,
+                                              const BnCoef& bn, const float* c1, const float* c2, void* dz, float gscale,
+                                              int c0) {
+    const float inv1 = gs_pow2(-gs_exponent2(dA1.bits, dA1.mul));
+    const float ratio = DA2 ? gs_pow2(gs_exponent2(dA1.bits, dA1.mul) - gs_exponent2(dA2.bits, dA2.mul)) : 0.f;
+    const bool has_sl = bn.slope != nullptr;
+    // dz = scale (dy - c1 - zhat c2) gscale = g (pos ? P1 : P2) + a (pos ? Q1 : Q2) + R
+    float P1[8], P2[8], Q1[8], Q2[8], R[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float sc = bn.scale[c0 + i], sh = bn.shift[c0 + i], mu = bn.mean[c0 + i], is = bn.invstd[c0 + i];
+        const bool pad = c0 + i >= g.C;                  // padded channel: every coefficient 0, so dz = 0 exactly
+        const float sl = (has_sl && !pad) ? bn.slope[c0 + i] : 1.f;
+        const float rg = pad ? 0.f : is / sc;
+        const float p = pad ? 0.f : sc * gscale, q = pad ? 0.f : -p * c2[c0 + i];
+        P1[i] = p * inv1;
+        P2[i] = P1[i] * sl;
+        Q1[i] = q * rg;
+        Q2[i] = Q1[i] / sl;
+        R[i] = pad ? 0.f : -p * c1[c0 + i] - q * fmaf(mu, sc, sh) * rg;
+    }
+    constexpr int ROWS = DA2 ? 2 : 4;
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long row0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; row0 < g.rows; row0 += ROWS * stride) {
+        bool ok[ROWS];
+        C8In<DA2, true> in[ROWS];
+        c8_load_rows<ROWS>(in, ok, dA1, dA2, nullptr, ah, g, row0, stride, c0);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) {
+                const long long idx = (row0 + j * stride) * g.Cs + c0;
+                float av[8], gv[8], o[8];
+                unpack8(in[j].s0, av);
+                unpack8(in[j].g1, gv);
+                if (DA2) {
+                    float g2[8];
+                    unpack8(in[j].g2, g2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gv[i] = fmaf(g2[i], ratio, gv[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool pos = av[i] > 0.f;
+                    o[i] = fmaf(gv[i], pos ? P1[i] : P2[i], fmaf(av[i], pos ? Q1[i] : Q2[i], R[i]));
+                }
+                if (OUT_F32) {
+                    float* d = reinterpret_cast<float*>(dz) + idx;
+                    st4(d, make_float4(o[0], o[1], o[2], o[3]));
+                    st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
+                } else {
+                    // |o| <= the GradScale bound (2^14): no clamp needed
+                    unsigned w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+                        w[i] = *reinterpret_cast<const unsigned*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(dz) + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+    }
+}
+
+// ---- general path (from the float32 pre-activation): channel groups whose inverse map is badly conditioned
+template <bool DA2>
+__device__ __forceinline__ void c8_reduce_general(const GradRef& dA1, const GradRef& dA2, const float* __restrict__ z,
+                                                  const Geo& g, const BnCoef& bn, int c0, C8Sums& S) {
+    C8Coef<false> k;
+    k.load(bn, c0, g.C);
+    const float inv1 = gs_pow2(-gs_exponent2(dA1.bits, dA1.mul));
+    const float inv2 = DA2 ? gs_pow2(-gs_exponent2(dA2.bits, dA2.mul)) : 1.f;
+    constexpr int ROWS = 2;
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long row0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; row0 < g.rows; row0 += ROWS * stride) {
+        bool ok[ROWS];
+        C8In<DA2, false> in[ROWS];
+        c8_load_rows<ROWS>(in, ok, dA1, dA2, z, nullptr, g, row0, stride, c0);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) {
+                float dy[8], zh[8], dsl[8];
+                c8_compute<DA2, false>(in[j], k, inv1, inv2, dy, zh, dsl);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    S.s0[i] += dy[i];
+                    S.s1[i] = fmaf(dy[i], zh[i], S.s1[i]);
+                    S.s2[i] += dsl[i];
+                    S.mx = fmaxf(S.mx, fabsf(dy[i]));
+                    S.zx = fmaxf(S.zx, fabsf(zh[i]));
+                }
+            }
+    }
+}
+
+template <bool DA2>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_c8_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
+                        BnCoef bn, double* partials) {
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool cok = cv < g.Cs / 8;
+    const int c0 = cv * 8;
+    C8Sums S;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { S.s0[i] = 0.f; S.s1[i] = 0.f; S.s2[i] = 0.f; }
+    S.mx = 0.f; S.zx = 0.f;
+    if (cok) {
+        if (c8_from_a(bn, a_hi, c0, g.C)) c8_reduce_fast<DA2>(dA1, dA2, reinterpret_cast<const __half*>(a_hi), g, bn, c0, S);
+        else c8_reduce_general<DA2>(dA1, dA2, z, g, bn, c0, S);
+    }
+    // publish through the 4-channel block reduction: lower and upper half of the thread's eight channels.  The
+    // record layout [blockIdx.x][5][Cs] is the one bn_bwd_finalize reads.
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        Acc4 acc[5];
+        acc[0].f = make_float4(S.s0[4 * h], S.s0[4 * h + 1], S.s0[4 * h + 2], S.s0[4 * h + 3]);
+        acc[1].f = make_float4(S.s1[4 * h], S.s1[4 * h + 1], S.s1[4 * h + 2], S.s1[4 * h + 3]);
+        acc[2].f = make_float4(S.s2[4 * h], S.s2[4 * h + 1], S.s2[4 * h + 2], S.s2[4 * h + 3]);
+        acc[3].f = make_float4(S.mx, S.mx, S.mx, S.mx);
+        acc[4].f = make_float4(S.zx, S.zx, S.zx, S.zx);
+        block_reduce_store<5, 2>(acc, partials, g.Cs, c0 + 4 * h, cok);
+    }
+}
+
+template <bool DA2, bool OUT_F32>
+__device__ __forceinline__ void c8_apply_general(const GradRef& dA1, const GradRef& dA2, const float* __restrict__ z,
+                                                 const Geo& g, const BnCoef& bn, const float* c1, const float* c2, void* dz,
+                                                 float gscale, int c0) {
+    C8Coef<false> k;
+    k.load(bn, c0, g.C);
+    const float inv1 = gs_pow2(-gs_exponent2(dA1.bits, dA1.mul));
+    const float inv2 = DA2 ? gs_pow2(-gs_exponent2(dA2.bits, dA2.mul)) : 1.f;
+    // dz = scale (dy - c1 - zhat c2) = p dy + q zhat + r   (output GradScale folded in)
+    float pq[8], qq[8], rr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float sc = bn.scale[c0 + i] * gscale;
+        pq[i] = sc;
+        qq[i] = -sc * c2[c0 + i];
+        rr[i] = -sc * c1[c0 + i];
+    }
+    constexpr int ROWS = 2;
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long row0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; row0 < g.rows; row0 += ROWS * stride) {
+        bool ok[ROWS];
+        C8In<DA2, false> in[ROWS];
+        c8_load_rows<ROWS>(in, ok, dA1, dA2, z, nullptr, g, row0, stride, c0);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) {
+                const long long idx = (row0 + j * stride) * g.Cs + c0;
+                float dy[8], zh[8], dsl[8], o[8];
+                c8_compute<DA2, false>(in[j], k, inv1, inv2, dy, zh, dsl);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = fmaf(pq[i], dy[i], fmaf(qq[i], zh[i], rr[i]));
+                if (OUT_F32) {
+                    float* d = reinterpret_cast<float*>(dz) + idx;
+                    st4(d, make_float4(o[0], o[1], o[2], o[3]));
+                    st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
+                } else {
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(dz) + idx) = pack8_scaled(o, 1.f);
+                }
+            }
+    }
+}
+
+template <bool DA2, bool OUT_F32>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_c8_apply_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
+                       BnCoef bn, const float* c1, const float* c2, void* dz, const unsigned* absmax) {
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= g.Cs / 8) return;
+    const int c0 = cv * 8;
+    const float gscale = OUT_F32 ? 1.f : gs_scale(absmax);
+    if (c8_from_a(bn, a_hi, c0, g.C))
+        c8_apply_fast<DA2, OUT_F32>(dA1, dA2, reinterpret_cast<const __half*>(a_hi), g, bn, c1, c2, dz, gscale, c0);
+    else
+        c8_apply_general<DA2, OUT_F32>(dA1, dA2, z, g, bn, c1, c2, dz, gscale, c0);
+}
+
+static const int C8_MAX_BLOCKS = 592;   // 4 x 148 SMs
+
+static EwShape c8_shape(const Geo& g) {
+    const int cv = g.Cs / 8;
+    const int bx = cv < 32 ? cv : 32;
+    const int by = 256 / bx;
+    EwShape s;
+    s.block = dim3(bx, by);
+    // fewer, longer-lived CTAs than the 4-channel kernels: the block-level reduction tail and the finalize pass scale
+    // with the CTA count
+    const int gx = ew_shape(g).grid.x;
+    s.grid = dim3(gx < C8_MAX_BLOCKS ? gx : C8_MAX_BLOCKS, (cv + bx - 1) / bx);
+    return s;
+}
+
+bool bn_bwd_compact_ok(const GradRef& dA1, const GradRef& dA2, const Geo& g, const Residual& res, const Dropout& dr) {
+    return dA1.half && (!dA2.p || dA2.half) && !res.zr && dr.p == 0.f && g.Cs % 8 == 0;
+}
+
+int bn_bwd_num_blocks(GradRef dA1, GradRef dA2, const Geo& g, Residual res, Dropout dr) {
+    return bn_bwd_compact_ok(dA1, dA2, g, res, dr) ? (int)c8_shape(g).grid.x : ew_num_blocks(g);
+}
+
+static int bn_bwd_c8_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
+                            double* partials, cudaStream_t s) {
+    EwShape sh = c8_shape(g);
+    if (dA2.p) bn_bwd_c8_reduce_kernel<true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, partials);
+    else bn_bwd_c8_reduce_kernel<false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, partials);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+static int bn_bwd_c8_apply(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
+                           const float* c1, const float* c2, void* dz, int fmt, const unsigned* absmax, cudaStream_t s) {
+    FSB_REQUIRE(fmt == FMT_F32 || fmt == FMT_H16, "compact BatchNorm backward writes float32 or one half plane");
+    EwShape sh = c8_shape(g);
+    if (fmt == FMT_F32) {
+        if (dA2.p) bn_bwd_c8_apply_kernel<true, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, c1, c2, dz, absmax);
+        else bn_bwd_c8_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, c1, c2, dz, absmax);
+    } else {
+        if (dA2.p) bn_bwd_c8_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, c1, c2, dz, absmax);
+        else bn_bwd_c8_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, c1, c2, dz, absmax);
+    }
     FSB_LAUNCHED();
     return 0;
 }

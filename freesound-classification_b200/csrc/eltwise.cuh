@@ -60,12 +60,16 @@ int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropou
 
 // 2x2 (pool_h = 2) or 1x2 (pool_h = 1) max pool, floor mode: zf (gf) -> zp (gp)
 // out_stats (optional): partial sum / sum of squares of zp, [ew_num_blocks(gp)][2][Cs] doubles
+// amax (optional): position 0..3 of the first maximum of every window, one byte per pooled element (gp.rows * Cs bytes)
 int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, double* out_stats,
-                    cudaStream_t s);
+                    unsigned char* amax, cudaStream_t s);
 // dzf (fmt planes, full-res geometry) <- dzp routed to the first maximum of every window
 // absmax (optional): GradScale of the half-precision destination (common.cuh)
 int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h,
                      void* dzf, int fmt, const unsigned* absmax, cudaStream_t s);
+// the same routing from the arg-max bytes of maxpool_forward (dzp: float32 or half + GradScale)
+int maxpool_backward_amax(GradRef dzp, const Geo& gp, const unsigned char* amax, const Geo& gf, int pool_h, void* dzf,
+                          int fmt, const unsigned* absmax, cudaStream_t s);
 
 // global max over (H, W) per (n, c): feat[n*feat_stride + feat_off + c], argrow[n*C + c] (padded row)
 // scratch: gmax_scratch_bytes(g) bytes (packed per-(n, c) atomic-max slots)
@@ -76,20 +80,26 @@ int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int
 int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* argrow, const Geo& g,
                   float* dx, cudaStream_t s);
 
-// backward of a = act(BN(z) [+ residual]) given dA = dA1 (+ dA2):
+// backward of a = act(BN(z) [+ residual]) given dA = dA1 (+ dA2; dA2.p == nullptr: none):
 //   reduce  : partials [nblk][5][Cs] doubles = sum dy, sum dy*zhat, sum dslope, max |dy|, max |zhat|
 //   finalize: dgamma, dbeta, dslope (C entries, written) and c1 = mean dy, c2 = mean dy*zhat (Cs);
-//             absmax (optional, zeroed by the caller): atomicMax of the float32 bits of a bound on |dz| (GradScale)
+//             absmax (optional, zeroed by the caller): atomicMax of the float32 bits of a bound on |dz| (GradScale);
+//             absmax_dy (optional): the same for |dy| (scale of a half-precision dres)
 //   apply   : dz = scale * (dy - c1 - zhat*c2) -> fmt planes (half formats: times the GradScale of `absmax`);
-//             dres (float32, optional) = dy
-int bn_act_bwd_reduce(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn,
+//             dres (optional) = dy, float32 or (dres_bits != nullptr) one half plane with that GradScale
+// Gradients come as float32 planes or scaled half planes (GradRef, common.cuh).  a_hi (optional, no residual): hi half
+// plane of the stored activation a = act(BN(z)); channel groups whose inverse map a -> zhat is well conditioned read
+// it instead of the float32 z (half the bytes), see eltwise.cu.
+int bn_act_bwd_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
                       Residual res, Dropout dr, double* partials, cudaStream_t s);
+// number of partial records bn_act_bwd_reduce writes for these operands (the `nblk` of bn_bwd_finalize)
+int bn_bwd_num_blocks(GradRef dA1, GradRef dA2, const Geo& g, Residual res, Dropout dr);
 int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
                     float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
-                    cudaStream_t s);
-int bn_act_bwd_apply(const float* dA1, const float* dA2, const float* z, const Geo& g, BnCoef bn,
-                     Residual res, Dropout dr, const float* c1, const float* c2, void* dz, int fmt,
-                     float* dres, const unsigned* absmax, cudaStream_t s);
+                    unsigned* absmax_dy, cudaStream_t s);
+int bn_act_bwd_apply(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
+                     Residual res, Dropout dr, const float* c1, const float* c2, void* dz, int fmt, void* dres,
+                     const unsigned* dres_bits, const unsigned* absmax, cudaStream_t s);
 
 // column sums of a dense (rows, C) matrix with row stride ld (final Linear bias gradient)
 int colsum(const float* x, long long rows, int C, int ld, float* out, cudaStream_t s);

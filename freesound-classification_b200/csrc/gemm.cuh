@@ -51,9 +51,16 @@ struct FwdStats {
 int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
                   cudaStream_t s);
 // dz_absmax (optional, tensor-core back ends): GradScale of dZ (common.cuh) -- dZ holds 2^k * gradient, the result is
-// multiplied by 2^-k
-int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c,
-                    const unsigned* dz_absmax, cudaStream_t s);
+// multiplied by 2^-k.
+// out_half_mul (optional, tensor-core back ends; needs dz_absmax): dA is written as ONE half plane holding 2^j * dA,
+// j = gs_exponent2(dz_absmax, out_half_mul); *out_half_mul = max column L1 norm of the weights (weight_l1_bounds), so
+// that max|dZ| * (*out_half_mul) bounds |dA| (compact backward of the mixed mode).  nullptr: float32 dA.
+int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, void* dA, const ConvGeom& c,
+                    const unsigned* dz_absmax, const float* out_half_mul, cudaStream_t s);
+
+// out[l] = max over input channels ci of sum_{co, tap} |w_l[co][ci][tap]| for up to 32 layers in one launch
+struct WeightL1Job { const float* w; int Cin, Cout, ntaps; };
+int weight_l1_bounds(const WeightL1Job* jobs, int njobs, float* out, cudaStream_t s);
 
 size_t wgrad_scratch_bytes(int precision, const ConvGeom& c);
 // dw: torch layout (Cout, Cin, taps), fully overwritten
@@ -77,8 +84,8 @@ int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* 
 int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
            cudaStream_t s);
 int tc_max_ctas();
-int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, const unsigned* dz_absmax,
-             cudaStream_t s);
+int tc_dgrad(int precision, const void* dZ, const void* packed, void* dA, const ConvGeom& c, const unsigned* dz_absmax,
+             const float* out_half_mul, cudaStream_t s);
 size_t tc_wgrad_scratch_bytes(const ConvGeom& c);
 int tc_wgrad(int precision, const void* A, const void* dZ, float* dw, void* scratch, const ConvGeom& c,
              const unsigned* dz_absmax, cudaStream_t s);

@@ -322,10 +322,11 @@ int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, co
     }
     return 0;
 }
-int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c,
-                    const unsigned* dz_absmax, cudaStream_t s) {
-    return precision == 0 ? simt_dgrad((const float*)dZ, packed, dA, c, s)
-                          : tc_dgrad(precision, dZ, packed, dA, c, dz_absmax, s);
+int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, void* dA, const ConvGeom& c,
+                    const unsigned* dz_absmax, const float* out_half_mul, cudaStream_t s) {
+    FSB_REQUIRE(precision != 0 || !out_half_mul, "conv_gemm_dgrad: the float32 back end writes float32 only");
+    return precision == 0 ? simt_dgrad((const float*)dZ, packed, (float*)dA, c, s)
+                          : tc_dgrad(precision, dZ, packed, dA, c, dz_absmax, out_half_mul, s);
 }
 size_t wgrad_scratch_bytes(int precision, const ConvGeom& c) {
     return precision == 0 ? simt_wgrad_scratch_bytes(c) : tc_wgrad_scratch_bytes(c);
@@ -334,6 +335,54 @@ int conv_gemm_wgrad(int precision, const void* A, const void* dZ, float* dw, voi
                     const unsigned* dz_absmax, cudaStream_t s) {
     return precision == 0 ? simt_wgrad((const float*)A, (const float*)dZ, dw, scratch, c, s)
                           : tc_wgrad(precision, A, dZ, dw, scratch, c, dz_absmax, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// max column L1 norm of conv weights: the Hoelder bound |dA[r, ci]| <= max|dZ| * sum_{co,t} |w[co][ci][t]| that fixes
+// the GradScale of a half-precision dgrad output before the GEMM runs.  One CTA per layer, one thread per input
+// channel (strided), block-wide max.
+struct WeightL1Jobs {
+    WeightL1Job j[32];
+};
+
+// grid (input-channel chunks of 32, layers); block (32 input channels, 8 output-channel slices)
+__global__ void __launch_bounds__(256) weight_l1_kernel(const WeightL1Jobs jobs, unsigned* out_bits) {
+    const WeightL1Job job = jobs.j[blockIdx.y];
+    const int ci = blockIdx.x * 32 + threadIdx.x;
+    float sum = 0.f;
+    if (ci < job.Cin) {
+        for (int co = threadIdx.y; co < job.Cout; co += 8) {
+            const float* w = job.w + ((long long)co * job.Cin + ci) * job.ntaps;
+            for (int t = 0; t < job.ntaps; ++t) sum += fabsf(w[t]);
+        }
+    }
+    __shared__ float red[8][32];
+    red[threadIdx.y][threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) tot += red[y][threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot = fmaxf(tot, __shfl_xor_sync(0xffffffffu, tot, o));
+        // 1.001: the GEMM multiplies by the half-rounded weights.  Non-negative floats order like their bit patterns.
+        if (threadIdx.x == 0 && blockIdx.x * 32 < job.Cin) atomicMax(out_bits + blockIdx.y, __float_as_uint(tot * 1.001f));
+    }
+}
+
+int weight_l1_bounds(const WeightL1Job* jobs, int njobs, float* out, cudaStream_t s) {
+    FSB_REQUIRE(njobs >= 1 && njobs <= 32, "weight_l1_bounds: 1..32 layers per launch");
+    WeightL1Jobs J;
+    memset(&J, 0, sizeof(J));
+    int max_cin = 1;
+    for (int i = 0; i < njobs; ++i) {
+        J.j[i] = jobs[i];
+        if (jobs[i].Cin > max_cin) max_cin = jobs[i].Cin;
+    }
+    FSB_CUDA(cudaMemsetAsync(out, 0, (size_t)njobs * sizeof(float), s));
+    weight_l1_kernel<<<dim3((max_cin + 31) / 32, njobs), dim3(32, 8), 0, s>>>(J, reinterpret_cast<unsigned*>(out));
+    FSB_LAUNCHED();
+    return 0;
 }
 
 }  // namespace fsb

@@ -75,6 +75,10 @@ struct ConvTcParams {
     double* stats;
     const unsigned char* mask;   // interior mask of the output geometry (nullptr = every row is interior)
     const unsigned* out_scale;   // GradScale of the A operand (dgrad): the output is multiplied by its inverse; nullptr = 1
+    // compact backward: the output is ONE half plane holding 2^k * D, k = gs_exponent2(out_scale, out_mul) (out_mul =
+    // device float, the max column L1 norm of the weights: |D| <= max|dZ| * out_mul); tmZ32 / tmZ16 are half maps then
+    int out_half;
+    const float* out_mul;
 };
 
 constexpr int EPI_BOX_BYTES = 4096;             // one staged box: 32 rows x 128 bytes; 4 epilogue warps x nstg boxes
@@ -219,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t stg0 = epi_stage + (uint32_t)(q * p.nstg) * EPI_BOX_BYTES;
         const unsigned char* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
         double* my_acc = stat_acc + (size_t)q * 2 * p.BN;
-        const float oscale = gs_inv_scale(p.out_scale);
+        const float oscale = gs_inv_scale(p.out_scale) * (p.out_half ? gs_pow2(gs_exponent2(p.out_scale, p.out_mul)) : 1.f);
         // per-lane column statistics of this CTA's column tile: compensated float32 sums in registers (a DADD per panel
         // through shared memory was the top stall of the 1x1 layers); [128-column chunk][32-column panel][sum, sum of squares]
         float accS[2][4][2], accC[2][4][2];
@@ -295,6 +299,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 __syncwarp();
                                 const uint32_t stg = stg0 + sb * EPI_BOX_BYTES;
                                 const float* stg_g = reinterpret_cast<const float*>(stg0_g + sb * EPI_BOX_BYTES);
+                                if (p.out_half) {
+                                    // half output: 64-byte staged rows in the SWIZZLE_64B pattern (16-byte chunk index xor
+                                    // address bits 7..8), or plain 32-byte rows for a 16-column panel
+                                    const uint32_t rbh = wide ? 64u : 32u;
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        if (wide || j < 2) {
+                                            const uint32_t ch = wide ? (uint32_t)((j ^ ((lane >> 1) & 3)) << 4) : (uint32_t)(j << 4);
+                                            const float* vv = v + pn * 32 + 8 * j;
+                                            const float* bb = bias_s + cl0 + 8 * j;
+                                            uint32_t w4[4];
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                const __half2 h2 = __floats2half2_rn(fmaf(vv[2 * e], oscale, bb[2 * e]),
+                                                                                     fmaf(vv[2 * e + 1], oscale, bb[2 * e + 1]));
+                                                w4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                                            }
+                                            st_shared_v4_u32(stg + (uint32_t)lane * rbh + ch, w4[0], w4[1], w4[2], w4[3]);
+                                        }
+                                    }
+                                } else {
                                 const uint32_t rb = wide ? 128u : 64u;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
@@ -305,6 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         st_shared_v4(stg + (uint32_t)lane * rb + ch, fmaf(vv[0], oscale, b4.x), fmaf(vv[1], oscale, b4.y),
                                                      fmaf(vv[2], oscale, b4.z), fmaf(vv[3], oscale, b4.w));
                                     }
+                                }
                                 }
                                 fence_async_smem();
                                 __syncwarp();
@@ -681,6 +707,27 @@ int make_out_map(CUtensorMap* m, const float* base, long long rows, int ldz, int
     return 0;
 }
 
+// half output matrix (ldz, rows), box (box_cols, 32): the epilogue's TMA-store target of the compact backward
+int make_out_map_h(CUtensorMap* m, const void* base, long long rows, int ldz, int box_cols, bool swizzle) {
+    auto fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return FSB_E_NODEVICE;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)ldz, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldz * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(half output rows=%lld ldz=%d box=%d) failed: %d", rows, ldz, box_cols, (int)r);
+        return FSB_E_INVALID;
+    }
+    return 0;
+}
+
 // FSB200_* tuning switches, read once per process
 struct TcEnv {
     int mode;      // FSB200_TC_MODE: bit 0 = one TMA box per tap (no dx sharing), bit 1 = descriptor base_offset = row
@@ -765,7 +812,7 @@ LaunchCache<ConvLaunch> g_conv_cache;
 
 int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
                  const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
-                 const FwdStats* st, const unsigned* out_scale) {
+                 const FwdStats* st, const unsigned* out_scale, const float* out_half_mul) {
     ConvTcParams& p = L.p;
     memset(&p, 0, sizeof(p));
     p.rows = rows;
@@ -780,6 +827,9 @@ int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacke
     p.ldz = ldz;
     p.bias = bias;
     p.out_scale = out_scale;
+    p.out_half = out_half_mul ? 1 : 0;
+    p.out_mul = out_half_mul;
+    FSB_REQUIRE(!(st && out_half_mul), "conv_tc: fused statistics need the float32 output");
     if (st) {
         const Geo& g = *st->g;
         FSB_REQUIRE(g.rows == rows && g.Cs == ldz, "conv_tc: statistics geometry does not match the output");
@@ -826,8 +876,13 @@ int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacke
     L.smem = fixed + stage * p.nstages;
     FSB_TRY(make_act_map(&L.tmA, A, rows, K, p.a_box_rows, p.bk));
     FSB_TRY(make_w_map(&L.tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn, p.bk));
-    FSB_TRY(make_out_map(&L.tmZ32, Z, rows, ldz, 32, true));
-    FSB_TRY(make_out_map(&L.tmZ16, Z, rows, ldz, 16, false));
+    if (p.out_half) {
+        FSB_TRY(make_out_map_h(&L.tmZ32, Z, rows, ldz, 32, true));
+        FSB_TRY(make_out_map_h(&L.tmZ16, Z, rows, ldz, 16, false));
+    } else {
+        FSB_TRY(make_out_map(&L.tmZ32, Z, rows, ldz, 32, true));
+        FSB_TRY(make_out_map(&L.tmZ16, Z, rows, ldz, 16, false));
+    }
     // every CTA owns one column tile: the grid is a multiple of n_tiles
     const int n_groups = (p.m_tiles + T - 1) / T;
     L.grid = (n_groups < ctas_per_col ? n_groups : ctas_per_col) * p.n_tiles;
@@ -836,18 +891,19 @@ int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacke
 
 int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
                    const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
-                   const FwdStats* st, const unsigned* out_scale, cudaStream_t s) {
+                   const FwdStats* st, const unsigned* out_scale, const float* out_half_mul, cudaStream_t s) {
     const LaunchKey key = {(uint64_t)(uintptr_t)A, (uint64_t)(uintptr_t)wpacked, (uint64_t)(uintptr_t)Z, (uint64_t)rows,
                            (uint64_t)(uintptr_t)bias, (uint64_t)(uintptr_t)(st ? st->partials : nullptr),
                            (uint64_t)(uintptr_t)(st ? st->g->mask : nullptr), (uint64_t)(uintptr_t)out_scale,
                            ((uint64_t)(uint32_t)K << 32) | (uint32_t)ldz, ((uint64_t)(uint32_t)bn << 32) | (uint32_t)nt,
                            ((uint64_t)(uint32_t)w_kpad << 32) | (uint32_t)w_npad,
                            ((uint64_t)(uint32_t)precision << 32) | (uint32_t)(sign + 1),
-                           ((uint64_t)(uint32_t)c.ntaps << 32) | (uint32_t)c.offs[0], (uint64_t)(uint32_t)c.offs[1], 0, 0};
+                           ((uint64_t)(uint32_t)c.ntaps << 32) | (uint32_t)c.offs[0], (uint64_t)(uint32_t)c.offs[1],
+                           (uint64_t)(uintptr_t)out_half_mul, 0};
     ConvLaunch* L = g_conv_cache.find(key);
     if (!L) {
         ConvLaunch fresh;
-        FSB_TRY(plan_conv_tc(fresh, precision, A, wpacked, w_kpad, w_npad, bn, nt, bias, Z, rows, K, ldz, c, sign, st, out_scale));
+        FSB_TRY(plan_conv_tc(fresh, precision, A, wpacked, w_kpad, w_npad, bn, nt, bias, Z, rows, K, ldz, c, sign, st, out_scale, out_half_mul));
         L = g_conv_cache.insert(key, fresh);
     }
     static bool attr_set = false;
@@ -888,15 +944,16 @@ int tc_fwd(int precision, const void* A, const void* packed, float* Z, const Con
     TcPackLayout L = pack_layout(c);
     const char* base = tc_pack_base(packed);
     return launch_conv_tc(precision, A, base + L.off_fwd, L.kpad_f, L.npad_f, L.bn_f, L.nt_f,
-                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, st, nullptr, s);
+                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, st, nullptr, nullptr, s);
 }
 
-int tc_dgrad(int precision, const void* dZ, const void* packed, float* dA, const ConvGeom& c, const unsigned* dz_absmax,
-             cudaStream_t s) {
+int tc_dgrad(int precision, const void* dZ, const void* packed, void* dA, const ConvGeom& c, const unsigned* dz_absmax,
+             const float* out_half_mul, cudaStream_t s) {
     TcPackLayout L = pack_layout(c);
     const char* base = tc_pack_base(packed);
-    return launch_conv_tc(precision, dZ, base + L.off_dgr, L.kpad_d, L.npad_d, L.bn_d, L.nt_d, nullptr, dA, c.rows,
-                          c.CsOut, c.CsIn, c, -1, nullptr, dz_absmax, s);
+    FSB_REQUIRE(!out_half_mul || dz_absmax, "tc_dgrad: the half output needs the GradScale of dZ");
+    return launch_conv_tc(precision, dZ, base + L.off_dgr, L.kpad_d, L.npad_d, L.bn_d, L.nt_d, nullptr, (float*)dA, c.rows,
+                          c.CsOut, c.CsIn, c, -1, nullptr, dz_absmax, out_half_mul, s);
 }
 
 struct WgradShape {

@@ -74,8 +74,10 @@ struct BlockPlan {
     int rnn_index;       // aggregation_type == "rnn": index of this block's head among the rnn heads, else -1
     RnnHead rnn;
     void* pk_rnn[2];     // packed W_ih / b_ih per direction
-    // backward
-    float *d_out, *da2, *da1, *dr0a, *dr0b, *dzp, *du;
+    unsigned char* pool_amax;   // training, blocks with an entry GEMM: arg-max position of every pool window
+    // backward (compact mode: da2 / da1 / dr0a / dr0b / dzp / du are scaled half planes, common.cuh GradRef)
+    float* d_out;
+    void *da2, *da1, *dr0a, *dr0b, *dzp, *du;
     void *dz3, *dz2, *dz1, *dzf;
 };
 
@@ -98,6 +100,11 @@ struct fsb_net {
     bool tables_ready = false, fwd_done = false;
     bool overlap = true;        // side-stream overlap of weight packing / weight-gradient GEMMs (fsb_net_set_overlap)
     bool conv0_tc = true;       // block-0 entry conv on the tensor cores (FSB200_CONV0_TC=0: CUDA-core direct conv)
+    // Compact backward (mixed mode; FSB200_COMPACT_BWD=0 turns it off): dgrad outputs, the residual-branch gradient and
+    // dzp are single scaled half planes, BatchNorm-backward reads the hi plane of the stored activation instead of the
+    // float32 pre-activation, max-pool backward routes by stored arg-max bytes.
+    bool compact = false;
+    float* wl1 = nullptr;       // [num_blocks][4] max column L1 norm of the entry / conv1 / conv2 / conv3 weights
     // CUDA graphs: the launch sequence of a forward (or backward) call with a given set of pointers / shapes is captured
     // on its second occurrence and replayed afterwards (~130 launches become one cudaGraphLaunch).
     bool graphs = true;         // FSB200_GRAPHS=0 / fsb_net_set_graphs(net, 0): always launch eagerly
@@ -257,6 +264,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
             B.zf = b.take<float>((size_t)B.g_full.rows * B.g_full.Cs);
         }
         size_t pe = (size_t)B.g.rows * B.g.Cs;
+        B.pool_amax = (!direct0 && training) ? b.take<unsigned char>(pe) : nullptr;
         B.zp = b.take<float>(pe);
         B.r0 = b.take_bytes(pe * 4);
         B.z1 = b.take<float>(pe);
@@ -293,7 +301,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
             B.da1 = b.take<float>(pe);
             B.dr0a = b.take<float>(pe);
             B.dr0b = b.take<float>(pe);
-            B.dzp = b.take<float>(pe);
+            B.dzp = b.take<float>(pe);      // (sized for float32; the compact backward uses half of each)
             B.dz3 = b.take_bytes(pe * 4);
             B.dz2 = b.take_bytes(pe * 4);
             B.dz1 = b.take_bytes(pe * 4);
@@ -344,6 +352,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
     net->wgrad_scratch = b.take_bytes(max_wgrad + 256);
     net->rnn_scratch = max_rnn ? b.take_bytes(max_rnn + 256) : nullptr;
     net->gscale = b.take<unsigned>((size_t)c.num_blocks * B_PER_BLOCK);
+    net->wl1 = b.take<float>((size_t)c.num_blocks * 4);
     net->d_seed = b.take<unsigned long long>(1);
     return align_up(b.off, 256);
 }
@@ -442,6 +451,8 @@ extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, c
         net->conv0_tc = !(e && atoi(e) == 0);
         e = getenv("FSB200_GRAPHS");
         net->graphs = !(e && atoi(e) == 0);
+        e = getenv("FSB200_COMPACT_BWD");
+        net->compact = net->prec_b == 2 && !(e && atoi(e) == 0);
     }
     *out = net;
     return 0;
@@ -718,6 +729,20 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
             RUN_S(ps, CAT_HEAD, 0, simt_pack_weights(P[H_L1_W], P[H_L1_B], net->lin1, net->pk_l1, ps));
             RUN_S(ps, CAT_HEAD, 0, simt_pack_weights(P[H_L5_W], P[H_L5_B], net->lin5, net->pk_l5, ps));
         }
+        if (training && net->compact) {
+            // Hoelder bounds of the dgrad outputs (GradScale of the half planes the compact backward writes)
+            WeightL1Job jobs[32];
+            int nj = 0;
+            for (int k = 0; k < c.num_blocks && nj + 4 <= 32; ++k) {
+                const BlockPlan& B = net->blocks[k];
+                const float* const* P = params + (size_t)k * P_PER_BLOCK;
+                jobs[nj++] = WeightL1Job{P[P_CONV_W], B.entry.Cin, B.entry.Cout, B.entry.ntaps};
+                jobs[nj++] = WeightL1Job{P[P_C1_W], B.c1.Cin, B.c1.Cout, B.c1.ntaps};
+                jobs[nj++] = WeightL1Job{P[P_C2_W], B.c2.Cin, B.c2.Cout, B.c2.ntaps};
+                jobs[nj++] = WeightL1Job{P[P_C3_W], B.c3.Cin, B.c3.Cout, B.c3.ntaps};
+            }
+            RUN_S(ps, CAT_PACK, 0, weight_l1_bounds(jobs, nj, net->wl1, ps));
+        }
         if (overlap) FSB_CUDA(cudaEventRecord(net->pack_event, net->side));
     }
     bool packs_joined = !net->overlap;
@@ -787,7 +812,7 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
             RUN(CAT_GEMM_FWD, conv_flops(B.entry, B.g_in),
                 conv_gemm_fwd(prec, B.u, B.pk_entry, B.zf, B.entry, nullptr, s));
             RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1,
-                                                training ? net->partials : nullptr, s));
+                                                training ? net->partials : nullptr, B.pool_amax, s));
             zp_stats_ready = true;
         }
         // BN_a + PReLU_a -> r0
@@ -857,14 +882,15 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
 // =================================================================================================
 // absmax (optional): GradScale slot of the gradient tensor this BatchNorm emits (half-precision planes are written
 // with its power-of-two scale; float32 outputs ignore it but the slot is still filled for a later converter)
-static int bn_backward(fsb_net* net, cudaStream_t s, const float* dA1, const float* dA2, const float* z, const Geo& g,
-                       BnBuf& bn, const float* slope, Residual res, Dropout dr, float* dgamma, float* dbeta,
-                       float* dslope, void* dz, int fmt, float* dres, unsigned* absmax, int cat) {
+static int bn_backward(fsb_net* net, cudaStream_t s, GradRef dA1, GradRef dA2, const float* z, const void* a_hi,
+                       const Geo& g, BnBuf& bn, const float* slope, Residual res, Dropout dr, float* dgamma, float* dbeta,
+                       float* dslope, void* dz, int fmt, void* dres, unsigned* dres_bits, unsigned* absmax, int cat) {
     BnCoef coef = bn.coef(slope);
-    RUN(cat, 0, bn_act_bwd_reduce(dA1, dA2, z, g, coef, res, dr, net->partials, s));
-    RUN(cat, 0, bn_bwd_finalize(net->partials, ew_num_blocks(g), g.pixels, bn.C, bn.Cs, bn.scale, dgamma, dbeta, dslope,
-                                bn.c1, bn.c2, absmax, s));
-    if (dz) RUN(cat, 0, bn_act_bwd_apply(dA1, dA2, z, g, coef, res, dr, bn.c1, bn.c2, dz, fmt, dres, absmax, s));
+    RUN(cat, 0, bn_act_bwd_reduce(dA1, dA2, z, a_hi, g, coef, res, dr, net->partials, s));
+    RUN(cat, 0, bn_bwd_finalize(net->partials, bn_bwd_num_blocks(dA1, dA2, g, res, dr), g.pixels, bn.C, bn.Cs, bn.scale,
+                                dgamma, dbeta, dslope, bn.c1, bn.c2, absmax, dres_bits, s));
+    if (dz) RUN(cat, 0, bn_act_bwd_apply(dA1, dA2, z, a_hi, g, coef, res, dr, bn.c1, bn.c2, dz, fmt, dres, dres_bits,
+                                         absmax, s));
     return 0;
 }
 
@@ -920,6 +946,7 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
     };
 
     // ---- head
+    const GradRef kNoGrad = grad_f32(nullptr);
     {
         const int hb = net->head_param_base;
         const float* const* P = params + hb;
@@ -928,20 +955,31 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
         RUN(CAT_HEAD, 0, simt_wgrad(net->h1, net->dzl, G(hb + H_L5_W), net->wgrad_scratch, net->lin5, s));
         RUN(CAT_HEAD, 0, simt_skinny_dgrad(net->dzl, net->pk_l5, net->dh1, net->lin5, net->head_scratch, s));
         Dropout dr = {c.dropout_p, net->dropout_seed, net->d_seed};
-        FSB_TRY(bn_backward(net, s, net->dh1, nullptr, net->z1h, net->g_head, net->hbn2, P[H_PRELU], kNoRes, dr,
-                            G(hb + H_BN2_W), G(hb + H_BN2_B), G(hb + H_PRELU), net->dz1h, FMT_F32, nullptr, nullptr, CAT_HEAD));
+        FSB_TRY(bn_backward(net, s, grad_f32(net->dh1), kNoGrad, net->z1h, nullptr, net->g_head, net->hbn2, P[H_PRELU],
+                            kNoRes, dr, G(hb + H_BN2_W), G(hb + H_BN2_B), G(hb + H_PRELU), net->dz1h, FMT_F32, nullptr,
+                            nullptr, nullptr, CAT_HEAD));
         RUN(CAT_HEAD, 0, simt_wgrad(net->h0, net->dz1h, G(hb + H_L1_W), net->wgrad_scratch, net->lin1, s));
         RUN(CAT_HEAD, 0, simt_skinny_dgrad(net->dz1h, net->pk_l1, net->dh0, net->lin1, net->head_scratch, s));
-        FSB_TRY(bn_backward(net, s, net->dh0, nullptr, net->feats, net->g_head, net->hbn0, nullptr, kNoRes, kNoDrop,
-                            G(hb + H_BN0_W), G(hb + H_BN0_B), nullptr, net->dfeats, FMT_F32, nullptr, nullptr, CAT_HEAD));
+        FSB_TRY(bn_backward(net, s, grad_f32(net->dh0), kNoGrad, net->feats, nullptr, net->g_head, net->hbn0, nullptr,
+                            kNoRes, kNoDrop, G(hb + H_BN0_W), G(hb + H_BN0_B), nullptr, net->dfeats, FMT_F32, nullptr,
+                            nullptr, nullptr, CAT_HEAD));
     }
 
     // ---- conv blocks, last to first
+    // Compact mode (mixed precision): every dgrad writes ONE half plane scaled by the Hoelder bound max|dZ| * L1(W);
+    // dr0b and dzp are half planes scaled by the bounds their producers reduce; BatchNorm-backward recovers zhat and
+    // the PReLU branch from the hi plane of the stored activation wherever that is well conditioned.
+    const bool cmp = net->compact && prec == 2;
     for (int k = c.num_blocks - 1; k >= 0; --k) {
         BlockPlan& B = net->blocks[k];
         const int pb = k * P_PER_BLOCK;
         const float* const* P = params + pb;
-        unsigned* const GS = net->gscale + (size_t)k * B_PER_BLOCK;     // GradScale slots of dz3 / dz2 / dz1 / dzp (-> dzf)
+        unsigned* const GS = net->gscale + (size_t)k * B_PER_BLOCK;     // GradScale slots of dz3 / dz2 / dz1 / dzp (-> dzf); B_IN: dr0b
+        const float* const L1 = net->wl1 + (size_t)k * 4;               // entry, conv1, conv2, conv3
+        // gradient w.r.t. the input of a dgrad GEMM whose operand carries the GradScale of `slot`
+        auto dgrad_out = [&](const void* p, const unsigned* slot, const float* l1) {
+            return cmp ? grad_h16(p, slot, l1) : grad_f32((const float*)p);
+        };
         if (k == c.num_blocks - 1) FSB_CUDA(cudaMemsetAsync(B.d_out, 0, (size_t)B.g.rows * B.g.Cs * 4, s));
         if (B.rnn_index >= 0) {
             const int rb = c.num_blocks * P_PER_BLOCK + B.rnn_index * R_PER_HEAD;
@@ -954,48 +992,72 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
         }
         // out = prelu3(bn3(z3) + r0)
         Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
-        FSB_TRY(bn_backward(net, s, B.d_out, nullptr, B.z3, B.g, B.bn3, P[P_PRELU3], res, kNoDrop, G(pb + P_BN3_W),
-                            G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, GS + B_3, CAT_ELT_BWD));
+        FSB_TRY(bn_backward(net, s, grad_f32(B.d_out), kNoGrad, B.z3, nullptr, B.g, B.bn3, P[P_PRELU3], res, kNoDrop,
+                            G(pb + P_BN3_W), G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, cmp ? GS + B_IN : nullptr,
+                            GS + B_3, CAT_ELT_BWD));
         FSB_TRY(fork());
         RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c3, B.g),
               conv_gemm_wgrad(prec, B.a2, B.dz3, G(pb + P_C3_W), net->wgrad_scratch, B.c3, GS + B_3, ws));
-        RUN(CAT_GEMM_DGRAD, conv_flops(B.c3, B.g), conv_gemm_dgrad(prec, B.dz3, B.pk3, B.da2, B.c3, GS + B_3, s));
-        FSB_TRY(bn_backward(net, s, B.da2, nullptr, B.z2, B.g, B.bn2, P[P_PRELU2], kNoRes, kNoDrop, G(pb + P_BN2_W),
-                            G(pb + P_BN2_B), G(pb + P_PRELU2), B.dz2, fmt, nullptr, GS + B_2, CAT_ELT_BWD));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c3, B.g),
+            conv_gemm_dgrad(prec, B.dz3, B.pk3, B.da2, B.c3, GS + B_3, cmp ? L1 + 3 : nullptr, s));
+        FSB_TRY(bn_backward(net, s, dgrad_out(B.da2, GS + B_3, L1 + 3), kNoGrad, B.z2, cmp ? B.a2 : nullptr, B.g, B.bn2,
+                            P[P_PRELU2], kNoRes, kNoDrop, G(pb + P_BN2_W), G(pb + P_BN2_B), G(pb + P_PRELU2), B.dz2, fmt,
+                            nullptr, nullptr, GS + B_2, CAT_ELT_BWD));
         FSB_TRY(fork());
         RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c2, B.g),
               conv_gemm_wgrad(prec, B.a1, B.dz2, G(pb + P_C2_W), net->wgrad_scratch, B.c2, GS + B_2, ws));
-        RUN(CAT_GEMM_DGRAD, conv_flops(B.c2, B.g), conv_gemm_dgrad(prec, B.dz2, B.pk2, B.da1, B.c2, GS + B_2, s));
-        FSB_TRY(bn_backward(net, s, B.da1, nullptr, B.z1, B.g, B.bn1, P[P_PRELU1], kNoRes, kNoDrop, G(pb + P_BN1_W),
-                            G(pb + P_BN1_B), G(pb + P_PRELU1), B.dz1, fmt, nullptr, GS + B_1, CAT_ELT_BWD));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c2, B.g),
+            conv_gemm_dgrad(prec, B.dz2, B.pk2, B.da1, B.c2, GS + B_2, cmp ? L1 + 2 : nullptr, s));
+        FSB_TRY(bn_backward(net, s, dgrad_out(B.da1, GS + B_2, L1 + 2), kNoGrad, B.z1, cmp ? B.a1 : nullptr, B.g, B.bn1,
+                            P[P_PRELU1], kNoRes, kNoDrop, G(pb + P_BN1_W), G(pb + P_BN1_B), G(pb + P_PRELU1), B.dz1, fmt,
+                            nullptr, nullptr, GS + B_1, CAT_ELT_BWD));
         FSB_TRY(fork());
         RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c1, B.g),
               conv_gemm_wgrad(prec, B.r0, B.dz1, G(pb + P_C1_W), net->wgrad_scratch, B.c1, GS + B_1, ws));
-        RUN(CAT_GEMM_DGRAD, conv_flops(B.c1, B.g), conv_gemm_dgrad(prec, B.dz1, B.pk1, B.dr0a, B.c1, GS + B_1, s));
-        // r0 = prelu_a(bn_a(zp)) ; gradient = conv1 dgrad + residual branch
-        FSB_TRY(bn_backward(net, s, B.dr0a, B.dr0b, B.zp, B.g, B.bn_a, P[P_PRELUA], kNoRes, kNoDrop, G(pb + P_BNA_W),
-                            G(pb + P_BNA_B), G(pb + P_PRELUA), B.dzp, FMT_F32, nullptr, GS + B_A, CAT_ELT_BWD));
+        RUN(CAT_GEMM_DGRAD, conv_flops(B.c1, B.g),
+            conv_gemm_dgrad(prec, B.dz1, B.pk1, B.dr0a, B.c1, GS + B_1, cmp ? L1 + 1 : nullptr, s));
+        // r0 = prelu_a(bn_a(zp)) ; gradient = conv1 dgrad + residual branch.  dzp: float32, or (compact, 2D) a half
+        // plane with the GradScale of slot B_A -- the same scale the routed dzf carries
+        const bool dzp_half = cmp && c.two_d;
+        const GradRef dr0b = cmp ? grad_h16(B.dr0b, GS + B_IN) : grad_f32((const float*)B.dr0b);
+        FSB_TRY(bn_backward(net, s, dgrad_out(B.dr0a, GS + B_1, L1 + 1), dr0b, B.zp, cmp ? B.r0 : nullptr, B.g, B.bn_a,
+                            P[P_PRELUA], kNoRes, kNoDrop, G(pb + P_BNA_W), G(pb + P_BNA_B), G(pb + P_PRELUA), B.dzp,
+                            dzp_half ? FMT_H16 : FMT_F32, nullptr, nullptr, GS + B_A, CAT_ELT_BWD));
+        const GradRef dzp = dzp_half ? grad_h16(B.dzp, GS + B_A) : grad_f32((const float*)B.dzp);
         if (c.two_d && k == 0) {
             if (prec != 0 && net->conv0_tc && conv0_tc_supported(B.g))
                 RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
                     conv0_tc_backward(prec, net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift,
-                                      B.bn_in.mean, B.bn_in.invstd, P[P_CONV_W], B.dzp, net->conv0_amax, GS + B_A, B.g,
-                                      G(pb + P_CONV_W), G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B),
+                                      B.bn_in.mean, B.bn_in.invstd, P[P_CONV_W], B.dzp, dzp_half ? 1 : 0, net->conv0_amax,
+                                      GS + B_A, B.g, G(pb + P_CONV_W), G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B),
                                       net->conv0_scratch, s));
-            else
+            else {
+                FSB_REQUIRE(!dzp_half, "net_backward: the CUDA-core block-0 conv needs FSB200_COMPACT_BWD=0");
                 RUN(CAT_CONV0, 2.0 * 2.0 * 2 * B.C * 9 * (double)n * c.n_features * net->frames,
                     conv0_backward(net->feat, n, c.n_features, net->frames, B.bn_in.scale, B.bn_in.shift, B.bn_in.mean,
-                                   B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], B.dzp, net->conv0_amax, B.g, G(pb + P_CONV_W),
-                                   G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B), net->conv0_scratch, s));
+                                   B.bn_in.invstd, P[P_CONV_W], P[P_CONV_B], (const float*)B.dzp, net->conv0_amax, B.g,
+                                   G(pb + P_CONV_W), G(pb + P_CONV_B), G(pb + P_BNIN_W), G(pb + P_BNIN_B),
+                                   net->conv0_scratch, s));
+            }
         } else {
-            RUN(CAT_ELT_BWD, 0, maxpool_backward(B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt_e, GS + B_A, s));
+            if (cmp)
+                RUN(CAT_ELT_BWD, 0, maxpool_backward_amax(dzp, B.g, B.pool_amax, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt_e,
+                                                          GS + B_A, s));
+            else
+                RUN(CAT_ELT_BWD, 0, maxpool_backward((const float*)B.dzp, B.g, B.zf, B.g_full, c.two_d ? 2 : 1, B.dzf, fmt_e,
+                                                     GS + B_A, s));
             FSB_TRY(fork());
             RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.entry, B.g_in),
                   conv_gemm_wgrad(prec, B.u, B.dzf, G(pb + P_CONV_W), net->wgrad_scratch, B.entry, GS + B_A, ws));
-            RUN(CAT_GEMM_DGRAD, conv_flops(B.entry, B.g_in), conv_gemm_dgrad(prec_e, B.dzf, B.pk_entry, B.du, B.entry, GS + B_A, s));
+            // 1D: the entry dgrad keeps three products and a float32 output (d(beta_in) telescopes, see above)
+            const bool du_half = cmp && c.two_d;
+            RUN(CAT_GEMM_DGRAD, conv_flops(B.entry, B.g_in),
+                conv_gemm_dgrad(prec_e, B.dzf, B.pk_entry, B.du, B.entry, GS + B_A, du_half ? L1 + 0 : nullptr, s));
             float* dprev = k > 0 ? net->blocks[k - 1].d_out : nullptr;
-            FSB_TRY(bn_backward(net, s, B.du, nullptr, B.x_in, B.g_in, B.bn_in, nullptr, kNoRes, kNoDrop,
-                                G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, FMT_F32, nullptr, nullptr, CAT_ELT_BWD));
+            const GradRef du = du_half ? grad_h16(B.du, GS + B_A, L1 + 0) : grad_f32((const float*)B.du);
+            FSB_TRY(bn_backward(net, s, du, kNoGrad, B.x_in, du_half ? B.u : nullptr, B.g_in, B.bn_in, nullptr, kNoRes,
+                                kNoDrop, G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, FMT_F32, nullptr, nullptr,
+                                nullptr, CAT_ELT_BWD));
         }
     }
     if (overlap) {      // join: the caller's stream continues only after the last weight gradient has landed
@@ -1037,7 +1099,8 @@ extern "C" int fsb_net_read_activation(fsb_net* net, int which, float* dst, long
         int kb = (which - 300) / 10, j = (which - 300) % 10;
         FSB_REQUIRE(kb >= 0 && kb < c.num_blocks && j <= 7, "read_activation: unknown tap %d", which);
         const BlockPlan& Bk = net->blocks[kb];
-        const float* src[8] = {Bk.zp, (const float*)Bk.r0, Bk.z1, (const float*)Bk.dz1, Bk.dr0a, Bk.dr0b, Bk.da1, Bk.dzp};
+        const float* src[8] = {Bk.zp, (const float*)Bk.r0, Bk.z1, (const float*)Bk.dz1, (const float*)Bk.dr0a,
+                               (const float*)Bk.dr0b, (const float*)Bk.da1, (const float*)Bk.dzp};
         FSB_REQUIRE(src[j] != nullptr, "read_activation: tap %d not available (training only)", which);
         long long cnt = Bk.g.pixels * Bk.g.C;
         FSB_REQUIRE(cap >= cnt, "read_activation: destination too small");
@@ -1150,7 +1213,7 @@ extern "C" int fsb_conv_backward(const float* x, const float* w, const float* dy
     FSB_TRY(nchw_to_pf(x, gi, A, fmt, s));
     FSB_TRY(nchw_to_pf(dy, go, dZ, fmt, s));
     FSB_TRY(pack_weights(precision, w, nullptr, c, pk, s));
-    FSB_TRY(conv_gemm_dgrad(precision, dZ, pk, dA, c, nullptr, s));
+    FSB_TRY(conv_gemm_dgrad(precision, dZ, pk, dA, c, nullptr, nullptr, s));
     FSB_TRY(pf_to_nchw(dA, gi, dx, s));
     FSB_TRY(conv_gemm_wgrad(precision, A, dZ, dw, scratch, c, nullptr, s));
     // bias gradient: sum of dy over (n, h, w) -- dy is NCHW here
