@@ -277,7 +277,7 @@ struct Conv0TcBwdParams {
 // 16-byte chunk c (0..7) of 128-byte row r of a SWIZZLE_128B box
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
-__global__ void __launch_bounds__(C0B_THREADS, 1) conv0_tc_bwd_kernel(const Conv0TcBwdParams p) {
+__global__ void __launch_bounds__(C0B_THREADS, 2) conv0_tc_bwd_kernel(const Conv0TcBwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     // [G: position][plane][box 0 | box 1]   [F: position][plane][box]
@@ -312,7 +312,6 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_tc_bwd_kernel(const Conv
         const uint32_t r = threadIdx.x & 63u, half = threadIdx.x >> 6;       // pixel row of the tile, channel half / position pair
         const float gscale = gs_scale(p.absmax);
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            if (it > 0) mbar_wait(b_empty, (it - 1u) & 1u);                   // the previous tile's MMAs have read the operands
             const long long q = (long long)tile * C0B_PX + r;
             const bool live = q < p.npix;
             int px = 0, py = 0, n = 0;
@@ -322,27 +321,60 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_tc_bwd_kernel(const Conv
                 py = (int)(t % H2);
                 n = (int)(t / H2);
             }
-            // ---- masked gradient rows: channels [half * 64, half * 64 + 64) of the four positions
             const long long grow = live ? geo_row(p.gp, n, py, px) * Cs : 0;
+            // ---- every global load of the tile is issued BEFORE the wait for the operand buffers (one round trip per
+            //      tile, overlapping the previous tile's MMAs; the loop below used to pay one per 8-channel chunk)
+            float fr[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int y = 2 * py - 1 + i;
+                const bool yok = live && y >= 0 && y < p.H;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = 2 * px - 1 + j;
+                    fr[i][j] = (yok && x >= 0 && x < p.W) ? __ldg(p.feat + ((long long)n * p.H + y) * p.W + x) : 0.f;
+                }
+            }
+            uint4 graw[8];
+            uint2 araw[8];
+            if (p.dzp_half) {
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) {
+                    const int ch0 = (int)(half * 64u + c * 8u);
+                    graw[c] = make_uint4(0u, 0u, 0u, 0u);
+                    araw[c] = make_uint2(0u, 0u);
+                    if (live && ch0 < Cs) {
+                        graw[c] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.dzp) + grow + ch0);
+                        araw[c] = *reinterpret_cast<const uint2*>(p.amax + grow + ch0);
+                    }
+                }
+            }
+            if (it > 0) mbar_wait(b_empty, (it - 1u) & 1u);                   // the previous tile's MMAs have read the operands
+            // ---- masked gradient rows: channels [half * 64, half * 64 + 64) of the four positions
+            if (p.dzp_half) {
+                // the half plane is the hi operand as it stands (same GradScale slot, single pass: no lo plane); the
+                // arg-max bytes become 16-bit lane masks (byte compare, byte permute)
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) {
+                    const int ch0 = (int)(half * 64u + c * 8u);
+                    if (ch0 < Cs) {
+#pragma unroll
+                        for (uint32_t pos = 0; pos < 4; ++pos) {
+                            const uint32_t m_lo = __vcmpeq4(araw[c].x, pos * 0x01010101u), m_hi = __vcmpeq4(araw[c].y, pos * 0x01010101u);
+                            const uint32_t dst = g_base + pos * g_pos + half * C0B_BOX + sw128(r, c);
+                            st_shared_v4_u32(dst, graw[c].x & __byte_perm(m_lo, 0u, 0x1100u), graw[c].y & __byte_perm(m_lo, 0u, 0x3322u),
+                                             graw[c].z & __byte_perm(m_hi, 0u, 0x1100u), graw[c].w & __byte_perm(m_hi, 0u, 0x3322u));
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (uint32_t c = 0; c < 8; ++c) {
                 const int ch0 = (int)(half * 64u + c * 8u);
                 if (ch0 < Cs) {
                     uint32_t a8[2] = {0u, 0u};
-                    __align__(16) __half gh[8];
-                    __half gl[8];
-                    if (p.dzp_half) {
-                        // the half plane is the hi operand as it stands (same GradScale slot); single pass: no lo plane
-                        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                        if (live) {
-                            raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.dzp) + grow + ch0);
-                            const uint2 am = *reinterpret_cast<const uint2*>(p.amax + grow + ch0);
-                            a8[0] = am.x; a8[1] = am.y;
-                        }
-                        *reinterpret_cast<uint4*>(gh) = raw;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) gl[i] = __float2half_rn(0.f);
-                    } else {
+                    __half gh[8], gl[8];
+                    {
                         float g8[8];
                         if (live) {
                             const float4 lo4 = *reinterpret_cast<const float4*>(p.dzp + grow + ch0);
@@ -375,39 +407,39 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_tc_bwd_kernel(const Conv
                     }
                 }
             }
-            // ---- patch feature rows of positions 2 * half and 2 * half + 1
-            float u0[4][4], u1[4][4], x0[4][4], x1[4][4], ok[4][4];
+            }
+            // ---- patch feature rows of positions 2 * half and 2 * half + 1 (window rows half .. half + 2, window columns
+            //      pp .. pp + 2); every index into the register arrays is a compile-time constant
+            float fw[3][4], ew[3];
+            uint32_t inw[3];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int y = 2 * py - 1 + i;
+            for (int dy = 0; dy < 3; ++dy) {
+                const int y = 2 * py - 1 + (int)half + dy;
                 const bool yok = live && y >= 0 && y < p.H;
-                const float e = yok ? c0t_freq_enc(y, p.H) : 0.f;
+                ew[dy] = yok ? c0t_freq_enc(y, p.H) : 0.f;
+                inw[dy] = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int x = 2 * px - 1 + j;
-                    const bool in = yok && x >= 0 && x < p.W;
-                    const float f = in ? __ldg(p.feat + ((long long)n * p.H + y) * p.W + x) : 0.f;
-                    u0[i][j] = in ? fmaf(f, sc0, sh0) : 0.f;
-                    u1[i][j] = in ? fmaf(e, sc1, sh1) : 0.f;
-                    x0[i][j] = in ? (f - mean0) * istd0 : 0.f;
-                    x1[i][j] = in ? (e - mean1) * istd1 : 0.f;
-                    ok[i][j] = in ? 1.f : 0.f;
+                    fw[dy][j] = half ? fr[dy + 1][j] : fr[dy][j];
+                    if (yok && x >= 0 && x < p.W) inw[dy] |= 1u << j;
                 }
             }
 #pragma unroll
             for (uint32_t pp = 0; pp < 2; ++pp) {
                 const uint32_t pos = 2u * half + pp;
-                const int sy = (int)(pos >> 1), sx = (int)(pos & 1u);
                 float v[48];
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
-                        v[dy * 3 + dx] = u0[sy + dy][sx + dx];
-                        v[9 + dy * 3 + dx] = u1[sy + dy][sx + dx];
-                        v[18 + dy * 3 + dx] = ok[sy + dy][sx + dx];
-                        v[27 + dy * 3 + dx] = x0[sy + dy][sx + dx];
-                        v[36 + dy * 3 + dx] = x1[sy + dy][sx + dx];
+                        const bool in = (inw[dy] >> (pp + dx)) & 1u;
+                        const float f = fw[dy][pp + dx], e = ew[dy];
+                        v[dy * 3 + dx] = in ? fmaf(f, sc0, sh0) : 0.f;
+                        v[9 + dy * 3 + dx] = in ? fmaf(e, sc1, sh1) : 0.f;
+                        v[18 + dy * 3 + dx] = in ? 1.f : 0.f;
+                        v[27 + dy * 3 + dx] = in ? (f - mean0) * istd0 : 0.f;
+                        v[36 + dy * 3 + dx] = in ? (e - mean1) * istd1 : 0.f;
                     }
 #pragma unroll
                 for (int i = 45; i < 48; ++i) v[i] = 0.f;

@@ -1290,6 +1290,7 @@ __device__ __forceinline__ void c8_reduce_fast(const GradRef& dA1, const GradRef
 #pragma unroll
                     for (int i = 0; i < 8; ++i) gv[i] = fmaf(g2[i], ratio, gv[i]);
                 }
+                float ady[8], azh[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const bool pos = av[i] > 0.f;
@@ -1298,9 +1299,14 @@ __device__ __forceinline__ void c8_reduce_fast(const GradRef& dA1, const GradRef
                     S.s2[i] = fmaf(av[i], pos ? 0.f : gv[i], S.s2[i]);
                     S.s0[i] += dy;
                     S.s1[i] = fmaf(dy, zh, S.s1[i]);
-                    S.mx = fmaxf(S.mx, fabsf(dy));
-                    S.zx = fmaxf(S.zx, fabsf(zh));
+                    ady[i] = fabsf(dy);
+                    azh[i] = fabsf(zh);
                 }
+                // tree maxima: one dependent step per row on the running bounds instead of eight
+                const float m0 = fmaxf(fmaxf(ady[0], ady[1]), fmaxf(ady[2], ady[3])), m1 = fmaxf(fmaxf(ady[4], ady[5]), fmaxf(ady[6], ady[7]));
+                const float z0 = fmaxf(fmaxf(azh[0], azh[1]), fmaxf(azh[2], azh[3])), z1 = fmaxf(fmaxf(azh[4], azh[5]), fmaxf(azh[6], azh[7]));
+                S.mx = fmaxf(S.mx, fmaxf(m0, m1));
+                S.zx = fmaxf(S.zx, fmaxf(z0, z1));
             }
     }
 #pragma unroll
@@ -1417,17 +1423,29 @@ bn_bwd_c8_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __res
         if (c8_from_a(bn, a_hi, c0, g.C)) c8_reduce_fast<DA2>(dA1, dA2, reinterpret_cast<const __half*>(a_hi), g, bn, c0, S);
         else c8_reduce_general<DA2>(dA1, dA2, z, g, bn, c0, S);
     }
-    // publish through the 4-channel block reduction: lower and upper half of the thread's eight channels.  The
-    // record layout [blockIdx.x][5][Cs] is the one bn_bwd_finalize reads.
+    // one-pass block reduction: every thread parks its 26 partials in shared memory (float32), then thread (k, x, i)
+    // sums one (record, channel) column over threadIdx.y in double.  Record layout [blockIdx.x][5][Cs] as read by
+    // bn_bwd_finalize; the two bounds are common to a thread's eight channels.
+    __shared__ float red[26][256];
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        Acc4 acc[5];
-        acc[0].f = make_float4(S.s0[4 * h], S.s0[4 * h + 1], S.s0[4 * h + 2], S.s0[4 * h + 3]);
-        acc[1].f = make_float4(S.s1[4 * h], S.s1[4 * h + 1], S.s1[4 * h + 2], S.s1[4 * h + 3]);
-        acc[2].f = make_float4(S.s2[4 * h], S.s2[4 * h + 1], S.s2[4 * h + 2], S.s2[4 * h + 3]);
-        acc[3].f = make_float4(S.mx, S.mx, S.mx, S.mx);
-        acc[4].f = make_float4(S.zx, S.zx, S.zx, S.zx);
-        block_reduce_store<5, 2>(acc, partials, g.Cs, c0 + 4 * h, cok);
+    for (int i = 0; i < 8; ++i) { red[i][t] = S.s0[i]; red[8 + i][t] = S.s1[i]; red[16 + i][t] = S.s2[i]; }
+    red[24][t] = S.mx;
+    red[25][t] = S.zx;
+    __syncthreads();
+    const int nthr = blockDim.x * blockDim.y, nout = 5 * 8 * (int)blockDim.x;
+    for (int o = t; o < nout; o += nthr) {
+        const int k = o / (8 * (int)blockDim.x), rem = o - k * 8 * (int)blockDim.x;
+        const int x = rem >> 3, i = rem & 7;
+        const int c = (blockIdx.y * blockDim.x + x) * 8 + i;
+        if (c >= g.Cs) continue;
+        const int slot = k < 3 ? k * 8 + i : 21 + k;
+        double acc = 0.0;
+        for (int y = 0; y < (int)blockDim.y; ++y) {
+            const double v = (double)red[slot][y * blockDim.x + x];
+            acc = k < 3 ? acc + v : fmax(acc, v);
+        }
+        partials[((long long)blockIdx.x * 5 + k) * g.Cs + c] = acc;
     }
 }
 
