@@ -822,6 +822,46 @@ int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* 
     return 0;
 }
 
+// the same scatter-add into a scaled half plane (compact backward: dx holds 2^k * gradient, k from `bits`)
+__global__ void gmax_bwd_h16_kernel(const float* dfeat, int feat_stride, int feat_off, const int* argrow, Geo g,
+                                    __half* dx, const unsigned* bits) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)g.N * g.C) return;
+    int n = (int)(i / g.C), c = (int)(i % g.C);
+    long long row = argrow[i];
+    const float scale = gs_scale(bits);
+    __half* d = dx + row * g.Cs + c;
+    *d = __float2half_rn(fmaf(dfeat[(long long)n * feat_stride + feat_off + c], scale, __half2float(*d)));
+}
+
+int gmax_backward_h16(const float* dfeat, int feat_stride, int feat_off, const int* argrow, const Geo& g, void* dx,
+                      const unsigned* bits, cudaStream_t s) {
+    long long total = (long long)g.N * g.C;
+    gmax_bwd_h16_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(dfeat, feat_stride, feat_off, argrow, g, (__half*)dx, bits);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+// bits[0] = float32 bit pattern of max |x| over n values (single CTA; a few thousand head gradients)
+__global__ void __launch_bounds__(256) absmax_bits_kernel(const float* x, long long n, unsigned* bits) {
+    float m = 0.f;
+    for (long long i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(x[i]));
+    __shared__ float red[256];
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bits[0] = __float_as_uint(red[0]);
+}
+
+int absmax_bits(const float* x, long long n, unsigned* bits, cudaStream_t s) {
+    absmax_bits_kernel<<<1, 256, 0, s>>>(x, n, bits);
+    FSB_LAUNCHED();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward of a = act(BN(z) [+ r]) : shared recomputation of dy (and the PReLU slope term)
 //
@@ -1013,7 +1053,7 @@ int bn_act_bwd_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi
 __global__ void __launch_bounds__(FIN_THREADS)
 bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
                        float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
-                       unsigned* absmax_dy) {
+                       unsigned* absmax_dy, const unsigned* extra_bits) {
     const int c = blockIdx.x * FIN_CH + (threadIdx.x % FIN_CH);
     double tot[5];
     reduce_partials<5, 2>(partials, nblk, Cs, c, tot);
@@ -1028,7 +1068,9 @@ bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C,
     if (absmax) {
         // |dz| = |scale (dy - c1 - zhat c2)| <= |scale| (max|dy| + |c1| + max|zhat| |c2|); 1.001: float32 rounding of
         // the apply pass.  Non-negative floats order like their bit patterns, and max is order independent.
-        const float bound = 1.001f * fabsf(bn_scale[c]) * ((float)tot[3] + fabsf(m1) + (float)tot[4] * fabsf(m2));
+        // extra_bits (optional): bound of a term added to dz afterwards (global-max scatter into the same plane)
+        const float bound = 1.001f * fabsf(bn_scale[c]) * ((float)tot[3] + fabsf(m1) + (float)tot[4] * fabsf(m2)) +
+                            (extra_bits ? 1.001f * __uint_as_float(*extra_bits) : 0.f);
         if (bound > 0.f) atomicMax(absmax, __float_as_uint(bound));
     }
     if (absmax_dy) {                      // bound of the residual-branch gradient dres = dy (written as a half plane)
@@ -1039,9 +1081,10 @@ bn_bwd_finalize_kernel(const double* partials, int nblk, long long count, int C,
 
 int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
                     float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
-                    unsigned* absmax_dy, cudaStream_t s) {
+                    unsigned* absmax_dy, const unsigned* extra_bits, cudaStream_t s) {
     bn_bwd_finalize_kernel<<<(Cs + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, s>>>(partials, nblk, count, C, Cs, bn_scale, dgamma,
-                                                                              dbeta, dslope, c1, c2, absmax, absmax_dy);
+                                                                              dbeta, dslope, c1, c2, absmax, absmax_dy,
+                                                                              extra_bits);
     FSB_LAUNCHED();
     return 0;
 }
@@ -1408,21 +1451,7 @@ __device__ __forceinline__ void c8_reduce_general(const GradRef& dA1, const Grad
     }
 }
 
-template <bool DA2>
-__global__ void __launch_bounds__(256, 2)
-bn_bwd_c8_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
-                        BnCoef bn, double* partials) {
-    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-    const bool cok = cv < g.Cs / 8;
-    const int c0 = cv * 8;
-    C8Sums S;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { S.s0[i] = 0.f; S.s1[i] = 0.f; S.s2[i] = 0.f; }
-    S.mx = 0.f; S.zx = 0.f;
-    if (cok) {
-        if (c8_from_a(bn, a_hi, c0, g.C)) c8_reduce_fast<DA2>(dA1, dA2, reinterpret_cast<const __half*>(a_hi), g, bn, c0, S);
-        else c8_reduce_general<DA2>(dA1, dA2, z, g, bn, c0, S);
-    }
+__device__ __forceinline__ void c8_publish(const C8Sums& S, const Geo& g, double* partials) {
     // one-pass block reduction: every thread parks its 26 partials in shared memory (float32), then thread (k, x, i)
     // sums one (record, channel) column over threadIdx.y in double.  Record layout [blockIdx.x][5][Cs] as read by
     // bn_bwd_finalize; the two bounds are common to a thread's eight channels.
@@ -1447,6 +1476,24 @@ bn_bwd_c8_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __res
         }
         partials[((long long)blockIdx.x * 5 + k) * g.Cs + c] = acc;
     }
+}
+
+template <bool DA2>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_c8_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
+                        BnCoef bn, double* partials) {
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool cok = cv < g.Cs / 8;
+    const int c0 = cv * 8;
+    C8Sums S;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { S.s0[i] = 0.f; S.s1[i] = 0.f; S.s2[i] = 0.f; }
+    S.mx = 0.f; S.zx = 0.f;
+    if (cok) {
+        if (c8_from_a(bn, a_hi, c0, g.C)) c8_reduce_fast<DA2>(dA1, dA2, reinterpret_cast<const __half*>(a_hi), g, bn, c0, S);
+        else c8_reduce_general<DA2>(dA1, dA2, z, g, bn, c0, S);
+    }
+    c8_publish(S, g, partials);
 }
 
 template <bool DA2, bool OUT_F32>
@@ -1505,6 +1552,235 @@ bn_bwd_c8_apply_kernel(const GradRef dA1, const GradRef dA2, const float* __rest
         c8_apply_general<DA2, OUT_F32>(dA1, dA2, z, g, bn, c1, c2, dz, gscale, c0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compact backward of the block output  out = prelu3(bn3(z3) + r0)  (residual branch), eight channels per thread.
+// Fast path: the pre-activation y3 and its sign come from the float32 block output `out` (y = out > 0 ? out : out / slope,
+// exact to float32) instead of being recomputed from z3 AND zp; zhat3 still comes from the float32 z3 (taking it from
+// out - r0 with the half-precision r0 plane was measurably noisier on small networks).  8 bytes per element and pass
+// when the incoming gradient is a half plane, 12 for the 4-channel kernel.  Used where 1/64 <= slope3 <= 16; other channel
+// groups recompute y3 from z3 and zp.  Writes dz3 and the residual-branch gradient dres = dy as scaled half planes.
+struct C8ResIn {
+    uint4 g0, g1;       // incoming gradient: half (g0) or float32 (g0, g1)
+    uint4 o0, o1;       // z3 (float32)
+    uint4 r0, r1;       // fast: out (float32) ; general: zp (float32)
+};
+
+template <bool FAST>
+__device__ __forceinline__ void c8res_load(C8ResIn& in, const GradRef& dA, const float* z, const float* out, const __half* r0h,
+                                           const float* zr, long long idx) {
+    if (dA.half) {
+        in.g0 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(dA.p) + idx);
+    } else {
+        in.g0 = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dA.p) + idx);
+        in.g1 = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dA.p) + idx + 4);
+    }
+    in.o0 = *reinterpret_cast<const uint4*>(z + idx);
+    in.o1 = *reinterpret_cast<const uint4*>(z + idx + 4);
+    const float* src = FAST ? out : zr;
+    in.r0 = *reinterpret_cast<const uint4*>(src + idx);
+    in.r1 = *reinterpret_cast<const uint4*>(src + idx + 4);
+}
+
+__device__ __forceinline__ void f8_from(const uint4& a, const uint4& b, float (&f)[8]) {
+    const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(w[i]);
+}
+
+__device__ __forceinline__ bool c8res_fast_ok(const BnCoef& bn, const void* out, const void* r0h, int c0, int C) {
+    bool ok = out != nullptr && bn.slope != nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (c0 + i >= C) continue;
+        const float sl = bn.slope[c0 + i];
+        ok = ok && sl >= 0.015625f && sl <= 16.f;
+    }
+    return ok;
+}
+
+// dy (unscaled), zhat and the slope-gradient term of eight channels.  FAST: from out / r0; else from z3 / zp.
+template <bool FAST>
+struct C8ResCoef {
+    float sl[8], e[8], b[8], a[8];           // slope, (FAST: 1/slope ; else scale), invstd, -mean invstd
+    float sh[FAST ? 1 : 8], rsc[FAST ? 1 : 8], rsh[FAST ? 1 : 8], rsl[FAST ? 1 : 8];
+    bool r_has_sl;
+    __device__ __forceinline__ void load(const BnCoef& bn, const Residual& res, int c0, int C) {
+        r_has_sl = res.slope != nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool pad = c0 + i >= C;
+            const float sc = bn.scale[c0 + i], shv = bn.shift[c0 + i], mu = bn.mean[c0 + i], is = bn.invstd[c0 + i];
+            sl[i] = (bn.slope && !pad) ? bn.slope[c0 + i] : 1.f;
+            b[i] = is;
+            a[i] = -mu * is;
+            if (FAST) {
+                e[i] = 1.f / sl[i];
+            } else {
+                e[i] = sc; sh[i] = shv;
+                rsc[i] = res.scale[c0 + i]; rsh[i] = res.shift[c0 + i];
+                rsl[i] = (r_has_sl && !pad) ? res.slope[c0 + i] : 1.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void compute(const C8ResIn& in, bool g_half, float inv, float (&dy)[8], float (&zh)[8],
+                                            float (&dsl)[8]) const {
+        float g[8], o[8];
+        if (g_half) unpack8(in.g0, g);
+        else f8_from(in.g0, in.g1, g);
+        f8_from(in.o0, in.o1, o);
+        if (FAST) {
+            float ov[8];
+            f8_from(in.r0, in.r1, ov);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool pos = ov[i] > 0.f;
+                const float gi = g[i] * inv;
+                const float y = pos ? ov[i] : ov[i] * e[i];
+                dy[i] = pos ? gi : sl[i] * gi;
+                dsl[i] = pos ? 0.f : y * gi;
+                zh[i] = fmaf(o[i], b[i], a[i]);
+            }
+        } else {
+            float zp[8];
+            f8_from(in.r0, in.r1, zp);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float rr = fmaf(zp[i], rsc[i], rsh[i]);
+                if (r_has_sl) rr = rr > 0.f ? rr : rsl[i] * rr;
+                const float y = fmaf(o[i], e[i], sh[i]) + rr;
+                const bool pos = y > 0.f;
+                const float gi = g[i] * inv;
+                dy[i] = pos ? gi : sl[i] * gi;
+                dsl[i] = pos ? 0.f : y * gi;
+                zh[i] = fmaf(o[i], b[i], a[i]);
+            }
+        }
+    }
+};
+
+template <bool FAST>
+__device__ __forceinline__ void c8res_reduce_body(const GradRef& dA, const float* z, const float* out, const __half* r0h,
+                                                  const Geo& g, const BnCoef& bn, const Residual& res, int c0, C8Sums& S) {
+    C8ResCoef<FAST> k;
+    k.load(bn, res, c0, g.C);
+    const float inv = dA.half ? gs_pow2(-gs_exponent2(dA.bits, dA.mul)) : 1.f;
+    constexpr int ROWS = FAST ? 2 : 1;       // the general path carries twice the coefficients
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long row0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; row0 < g.rows; row0 += ROWS * stride) {
+        bool ok[ROWS];
+        C8ResIn in[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            const long long row = row0 + j * stride;
+            ok[j] = row < g.rows && (g.mask == nullptr || g.mask[row]);
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) c8res_load<FAST>(in[j], dA, z, out, r0h, res.zr, (row0 + j * stride) * g.Cs + c0);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) {
+                float dy[8], zh[8], dsl[8];
+                k.compute(in[j], dA.half != 0, inv, dy, zh, dsl);
+                float m = 0.f, zm = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    S.s0[i] += dy[i];
+                    S.s1[i] = fmaf(dy[i], zh[i], S.s1[i]);
+                    S.s2[i] += dsl[i];
+                    m = fmaxf(m, fabsf(dy[i]));
+                    zm = fmaxf(zm, fabsf(zh[i]));
+                }
+                S.mx = fmaxf(S.mx, m);
+                S.zx = fmaxf(S.zx, zm);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_c8res_reduce_kernel(const GradRef dA, const float* __restrict__ z, const float* __restrict__ out, const void* r0_hi,
+                           Geo g, BnCoef bn, Residual res, double* partials) {
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool cok = cv < g.Cs / 8;
+    const int c0 = cv * 8;
+    C8Sums S;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { S.s0[i] = 0.f; S.s1[i] = 0.f; S.s2[i] = 0.f; }
+    S.mx = 0.f; S.zx = 0.f;
+    if (cok) {
+        const __half* r0h = reinterpret_cast<const __half*>(r0_hi);
+        if (c8res_fast_ok(bn, out, r0_hi, c0, g.C)) c8res_reduce_body<true>(dA, z, out, r0h, g, bn, res, c0, S);
+        else c8res_reduce_body<false>(dA, z, out, r0h, g, bn, res, c0, S);
+    }
+    c8_publish(S, g, partials);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void c8res_apply_body(const GradRef& dA, const float* z, const float* out, const __half* r0h,
+                                                 const Geo& g, const BnCoef& bn, const Residual& res, const float* c1,
+                                                 const float* c2, __half* dz, float gscale, __half* dres, float dscale, int c0) {
+    C8ResCoef<FAST> k;
+    k.load(bn, res, c0, g.C);
+    const float inv = dA.half ? gs_pow2(-gs_exponent2(dA.bits, dA.mul)) : 1.f;
+    float pq[8], qq[8], rr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool pad = c0 + i >= g.C;
+        const float sc = pad ? 0.f : bn.scale[c0 + i] * gscale;
+        pq[i] = sc;
+        qq[i] = pad ? 0.f : -sc * c2[c0 + i];
+        rr[i] = pad ? 0.f : -sc * c1[c0 + i];
+    }
+    constexpr int ROWS = FAST ? 2 : 1;
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long row0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; row0 < g.rows; row0 += ROWS * stride) {
+        bool ok[ROWS];
+        C8ResIn in[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            const long long row = row0 + j * stride;
+            ok[j] = row < g.rows && (g.mask == nullptr || g.mask[row]);
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) c8res_load<FAST>(in[j], dA, z, out, r0h, res.zr, (row0 + j * stride) * g.Cs + c0);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (ok[j]) {
+                const long long idx = (row0 + j * stride) * g.Cs + c0;
+                float dy[8], zh[8], dsl[8];
+                k.compute(in[j], dA.half != 0, inv, dy, zh, dsl);
+                unsigned wz[4], wr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float o0 = fmaf(pq[2 * i], dy[2 * i], fmaf(qq[2 * i], zh[2 * i], rr[2 * i]));
+                    const float o1 = fmaf(pq[2 * i + 1], dy[2 * i + 1], fmaf(qq[2 * i + 1], zh[2 * i + 1], rr[2 * i + 1]));
+                    const __half2 hz = __floats2half2_rn(o0, o1);
+                    const __half2 hr = __floats2half2_rn(dy[2 * i] * dscale, dy[2 * i + 1] * dscale);
+                    wz[i] = *reinterpret_cast<const unsigned*>(&hz);
+                    wr[i] = *reinterpret_cast<const unsigned*>(&hr);
+                }
+                *reinterpret_cast<uint4*>(dz + idx) = make_uint4(wz[0], wz[1], wz[2], wz[3]);
+                if (dres) *reinterpret_cast<uint4*>(dres + idx) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_c8res_apply_kernel(const GradRef dA, const float* __restrict__ z, const float* __restrict__ out, const void* r0_hi,
+                          Geo g, BnCoef bn, Residual res, const float* c1, const float* c2, void* dz, const unsigned* absmax,
+                          void* dres, const unsigned* dres_bits) {
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= g.Cs / 8) return;
+    const int c0 = cv * 8;
+    const float gscale = gs_scale(absmax), dscale = gs_scale(dres_bits);
+    const __half* r0h = reinterpret_cast<const __half*>(r0_hi);
+    if (c8res_fast_ok(bn, out, r0_hi, c0, g.C))
+        c8res_apply_body<true>(dA, z, out, r0h, g, bn, res, c1, c2, (__half*)dz, gscale, (__half*)dres, dscale, c0);
+    else
+        c8res_apply_body<false>(dA, z, out, r0h, g, bn, res, c1, c2, (__half*)dz, gscale, (__half*)dres, dscale, c0);
+}
+
 static const int C8_MAX_BLOCKS = 592;   // 4 x 148 SMs
 
 static EwShape c8_shape(const Geo& g) {
@@ -1518,6 +1794,29 @@ static EwShape c8_shape(const Geo& g) {
     const int gx = ew_shape(g).grid.x;
     s.grid = dim3(gx < C8_MAX_BLOCKS ? gx : C8_MAX_BLOCKS, (cv + bx - 1) / bx);
     return s;
+}
+
+int bn_res_bwd_compact_reduce(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
+                              Residual res, double* partials, cudaStream_t s) {
+    EW_CHECK(g);
+    FSB_REQUIRE(g.Cs % 8 == 0 && res.zr && z, "compact residual BatchNorm backward: bad operands");
+    EwShape sh = c8_shape(g);
+    bn_bwd_c8res_reduce_kernel<<<sh.grid, sh.block, 0, s>>>(dA, z, out, r0_hi, g, bn, res, partials);
+    FSB_LAUNCHED();
+    return 0;
+}
+
+int bn_res_bwd_compact_blocks(const Geo& g) { return (int)c8_shape(g).grid.x; }
+
+int bn_res_bwd_compact_apply(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
+                             Residual res, const float* c1, const float* c2, void* dz, const unsigned* absmax, void* dres,
+                             const unsigned* dres_bits, cudaStream_t s) {
+    EW_CHECK(g);
+    FSB_REQUIRE(g.Cs % 8 == 0 && res.zr && z && absmax && (!dres || dres_bits), "compact residual BatchNorm backward: bad operands");
+    EwShape sh = c8_shape(g);
+    bn_bwd_c8res_apply_kernel<<<sh.grid, sh.block, 0, s>>>(dA, z, out, r0_hi, g, bn, res, c1, c2, dz, absmax, dres, dres_bits);
+    FSB_LAUNCHED();
+    return 0;
 }
 
 bool bn_bwd_compact_ok(const GradRef& dA1, const GradRef& dA2, const Geo& g, const Residual& res, const Dropout& dr) {

@@ -79,12 +79,18 @@ int gmax_forward(const float* x, const Geo& g, float* feat, int feat_stride, int
 // dx[argrow, c] += dfeat[n*feat_stride + feat_off + c]
 int gmax_backward(const float* dfeat, int feat_stride, int feat_off, const int* argrow, const Geo& g,
                   float* dx, cudaStream_t s);
+// the same into a scaled half plane (GradScale of `bits`)
+int gmax_backward_h16(const float* dfeat, int feat_stride, int feat_off, const int* argrow, const Geo& g, void* dx,
+                      const unsigned* bits, cudaStream_t s);
+// bits[0] = float32 bit pattern of max |x[i]|, i < n (one CTA)
+int absmax_bits(const float* x, long long n, unsigned* bits, cudaStream_t s);
 
 // backward of a = act(BN(z) [+ residual]) given dA = dA1 (+ dA2; dA2.p == nullptr: none):
 //   reduce  : partials [nblk][5][Cs] doubles = sum dy, sum dy*zhat, sum dslope, max |dy|, max |zhat|
 //   finalize: dgamma, dbeta, dslope (C entries, written) and c1 = mean dy, c2 = mean dy*zhat (Cs);
 //             absmax (optional, zeroed by the caller): atomicMax of the float32 bits of a bound on |dz| (GradScale);
-//             absmax_dy (optional): the same for |dy| (scale of a half-precision dres)
+//             absmax_dy (optional): the same for |dy| (scale of a half-precision dres);
+//             extra_bits (optional): bit pattern of a bound that is ADDED to the |dz| bound (a later scatter-add into dz)
 //   apply   : dz = scale * (dy - c1 - zhat*c2) -> fmt planes (half formats: times the GradScale of `absmax`);
 //             dres (optional) = dy, float32 or (dres_bits != nullptr) one half plane with that GradScale
 // Gradients come as float32 planes or scaled half planes (GradRef, common.cuh).  a_hi (optional, no residual): hi half
@@ -96,10 +102,21 @@ int bn_act_bwd_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi
 int bn_bwd_num_blocks(GradRef dA1, GradRef dA2, const Geo& g, Residual res, Dropout dr);
 int bn_bwd_finalize(const double* partials, int nblk, long long count, int C, int Cs, const float* bn_scale,
                     float* dgamma, float* dbeta, float* dslope, float* c1, float* c2, unsigned* absmax,
-                    unsigned* absmax_dy, cudaStream_t s);
+                    unsigned* absmax_dy, const unsigned* extra_bits, cudaStream_t s);
 int bn_act_bwd_apply(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
                      Residual res, Dropout dr, const float* c1, const float* c2, void* dz, int fmt, void* dres,
                      const unsigned* dres_bits, const unsigned* absmax, cudaStream_t s);
+
+// Compact backward of a residual activation out = prelu(BN(z) + r), r = prelu(res.zr * res.scale + res.shift) (mixed
+// mode): eight channels per thread; y and its sign from the float32 `out`, zhat from out and the hi half plane of r
+// (r0_hi) where that is well conditioned, from z / res.zr otherwise (out, r0_hi may be nullptr: always the latter).
+// Writes dz and dres = dy as ONE scaled half plane each.  Records: bn_res_bwd_compact_blocks(g) x [5][Cs].
+int bn_res_bwd_compact_reduce(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
+                              Residual res, double* partials, cudaStream_t s);
+int bn_res_bwd_compact_blocks(const Geo& g);
+int bn_res_bwd_compact_apply(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
+                             Residual res, const float* c1, const float* c2, void* dz, const unsigned* absmax, void* dres,
+                             const unsigned* dres_bits, cudaStream_t s);
 
 // column sums of a dense (rows, C) matrix with row stride ld (final Linear bias gradient)
 int colsum(const float* x, long long rows, int C, int ld, float* out, cudaStream_t s);

@@ -266,9 +266,9 @@ simt_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dZ, lon
 // dw[co][ci][t] = sum_split P[split][t][ci][co]   (fixed order: deterministic).  Threads walk P in its own
 // order (co fastest) so every split plane is read coalesced; the `splits` loads of a thread are independent.
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ P, int splits, ConvGeom c, float* dw,
-                                                             const unsigned* dz_absmax) {
+                                                                  const unsigned* dz_absmax) {
     const long long plane = (long long)c.ntaps * c.CsIn * c.CsOut;
-    const float unscale = gs_inv_scale(dz_absmax);      // dZ was written with its power-of-two GradScale (common.cuh)
+    const float unscale = gs_inv_scale(dz_absmax);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane;
          i += (long long)gridDim.x * blockDim.x) {
         const int co = (int)(i % c.CsOut);

@@ -145,6 +145,7 @@ struct fsb_net {
     void* conv0_scratch = nullptr;
     unsigned char* conv0_amax = nullptr;   // 2D block 0: arg-max position of every pool window (training)
     unsigned* gscale = nullptr;     // [num_blocks][B_PER_BLOCK] GradScale slots (common.cuh), zeroed at the start of backward
+    unsigned* gscale_out = nullptr; // [num_blocks + 1]: GradScale of the half d_out planes (compact backward); last: max |dfeats|
 
     // precision of the forward / backward GEMMs (cfg.precision 3 = mixed: three-product forward, single-pass backward)
     int prec_f = 0, prec_b = 0;
@@ -353,6 +354,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
     net->rnn_scratch = max_rnn ? b.take_bytes(max_rnn + 256) : nullptr;
     net->gscale = b.take<unsigned>((size_t)c.num_blocks * B_PER_BLOCK);
     net->wl1 = b.take<float>((size_t)c.num_blocks * 4);
+    net->gscale_out = b.take<unsigned>((size_t)c.num_blocks + 1);
     net->d_seed = b.take<unsigned long long>(1);
     return align_up(b.off, 256);
 }
@@ -884,11 +886,12 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
 // with its power-of-two scale; float32 outputs ignore it but the slot is still filled for a later converter)
 static int bn_backward(fsb_net* net, cudaStream_t s, GradRef dA1, GradRef dA2, const float* z, const void* a_hi,
                        const Geo& g, BnBuf& bn, const float* slope, Residual res, Dropout dr, float* dgamma, float* dbeta,
-                       float* dslope, void* dz, int fmt, void* dres, unsigned* dres_bits, unsigned* absmax, int cat) {
+                       float* dslope, void* dz, int fmt, void* dres, unsigned* dres_bits, unsigned* absmax, int cat,
+                       const unsigned* extra_bits = nullptr) {
     BnCoef coef = bn.coef(slope);
     RUN(cat, 0, bn_act_bwd_reduce(dA1, dA2, z, a_hi, g, coef, res, dr, net->partials, s));
     RUN(cat, 0, bn_bwd_finalize(net->partials, bn_bwd_num_blocks(dA1, dA2, g, res, dr), g.pixels, bn.C, bn.Cs, bn.scale,
-                                dgamma, dbeta, dslope, bn.c1, bn.c2, absmax, dres_bits, s));
+                                dgamma, dbeta, dslope, bn.c1, bn.c2, absmax, dres_bits, extra_bits, s));
     if (dz) RUN(cat, 0, bn_act_bwd_apply(dA1, dA2, z, a_hi, g, coef, res, dr, bn.c1, bn.c2, dz, fmt, dres, dres_bits,
                                          absmax, s));
     return 0;
@@ -927,6 +930,7 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
     // conv / linear biases that feed a batch-statistics BN have an analytically zero gradient
     FSB_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->total_params * sizeof(float), s));
     FSB_CUDA(cudaMemsetAsync(net->gscale, 0, (size_t)c.num_blocks * B_PER_BLOCK * sizeof(unsigned), s));
+    FSB_CUDA(cudaMemsetAsync(net->gscale_out, 0, ((size_t)c.num_blocks + 1) * sizeof(unsigned), s));
     FSB_TRY(ensure_side_stream(net));
     const bool overlap = net->overlap;
     cudaStream_t ws = overlap ? net->side : s;       // stream of the weight-gradient GEMMs
@@ -970,6 +974,11 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
     // dr0b and dzp are half planes scaled by the bounds their producers reduce; BatchNorm-backward recovers zhat and
     // the PReLU branch from the hi plane of the stored activation wherever that is well conditioned.
     const bool cmp = net->compact && prec == 2;
+    // d_out of every block but the last is a scaled half plane too (2D, global-max heads): its producer (the next block's
+    // input-BatchNorm backward) bounds it, plus max |dfeats| for the head gradient scattered into it afterwards
+    unsigned* const DF = net->gscale_out + c.num_blocks;
+    auto dout_half = [&](int k) { return cmp && c.two_d && c.aggregation == 0 && k >= 0 && k < c.num_blocks - 1; };
+    if (cmp && c.two_d && c.aggregation == 0) RUN(CAT_HEAD, 0, absmax_bits(net->dfeats, (long long)n * net->Ds, DF, s));
     for (int k = c.num_blocks - 1; k >= 0; --k) {
         BlockPlan& B = net->blocks[k];
         const int pb = k * P_PER_BLOCK;
@@ -988,13 +997,28 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
             RUN(CAT_HEAD, 0, rnn_head_backward(B.rnn, net->dfeats, net->Ds, B.head_off, params + rb, B.pk_rnn, GR, B.d_out,
                                                B.g, net->rnn_scratch, s));
         } else if (B.head_off >= 0) {
-            RUN(CAT_ELT_BWD, 0, gmax_backward(net->dfeats, net->Ds, B.head_off, B.argrow, B.g, B.d_out, s));
+            if (dout_half(k))
+                RUN(CAT_ELT_BWD, 0, gmax_backward_h16(net->dfeats, net->Ds, B.head_off, B.argrow, B.g, B.d_out,
+                                                      net->gscale_out + k, s));
+            else
+                RUN(CAT_ELT_BWD, 0, gmax_backward(net->dfeats, net->Ds, B.head_off, B.argrow, B.g, B.d_out, s));
         }
         // out = prelu3(bn3(z3) + r0)
         Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
-        FSB_TRY(bn_backward(net, s, grad_f32(B.d_out), kNoGrad, B.z3, nullptr, B.g, B.bn3, P[P_PRELU3], res, kNoDrop,
-                            G(pb + P_BN3_W), G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, cmp ? GS + B_IN : nullptr,
-                            GS + B_3, CAT_ELT_BWD));
+        const GradRef dout = dout_half(k) ? grad_h16(B.d_out, net->gscale_out + k) : grad_f32(B.d_out);
+        if (cmp) {
+            const BnCoef coef3 = B.bn3.coef(P[P_PRELU3]);
+            RUN(CAT_ELT_BWD, 0, bn_res_bwd_compact_reduce(dout, B.z3, B.out, B.r0, B.g, coef3, res, net->partials, s));
+            RUN(CAT_ELT_BWD, 0, bn_bwd_finalize(net->partials, bn_res_bwd_compact_blocks(B.g), B.g.pixels, B.bn3.C, B.bn3.Cs,
+                                                B.bn3.scale, G(pb + P_BN3_W), G(pb + P_BN3_B), G(pb + P_PRELU3), B.bn3.c1,
+                                                B.bn3.c2, GS + B_3, GS + B_IN, nullptr, s));
+            RUN(CAT_ELT_BWD, 0, bn_res_bwd_compact_apply(dout, B.z3, B.out, B.r0, B.g, coef3, res, B.bn3.c1, B.bn3.c2, B.dz3,
+                                                         GS + B_3, B.dr0b, GS + B_IN, s));
+        } else {
+            FSB_TRY(bn_backward(net, s, dout, kNoGrad, B.z3, nullptr, B.g, B.bn3, P[P_PRELU3], res, kNoDrop,
+                                G(pb + P_BN3_W), G(pb + P_BN3_B), G(pb + P_PRELU3), B.dz3, fmt, B.dr0b, nullptr, GS + B_3,
+                                CAT_ELT_BWD));
+        }
         FSB_TRY(fork());
         RUN_S(ws, CAT_GEMM_WGRAD, conv_flops(B.c3, B.g),
               conv_gemm_wgrad(prec, B.a2, B.dz3, G(pb + P_C3_W), net->wgrad_scratch, B.c3, GS + B_3, ws));
@@ -1055,9 +1079,11 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
                 conv_gemm_dgrad(prec_e, B.dzf, B.pk_entry, B.du, B.entry, GS + B_A, du_half ? L1 + 0 : nullptr, s));
             float* dprev = k > 0 ? net->blocks[k - 1].d_out : nullptr;
             const GradRef du = du_half ? grad_h16(B.du, GS + B_A, L1 + 0) : grad_f32((const float*)B.du);
+            const bool prev_half = dout_half(k - 1);      // d_out of block k - 1: half plane bounded by this BN + the head scatter
             FSB_TRY(bn_backward(net, s, du, kNoGrad, B.x_in, du_half ? B.u : nullptr, B.g_in, B.bn_in, nullptr, kNoRes,
-                                kNoDrop, G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, FMT_F32, nullptr, nullptr,
-                                nullptr, CAT_ELT_BWD));
+                                kNoDrop, G(pb + P_BNIN_W), G(pb + P_BNIN_B), nullptr, dprev, prev_half ? FMT_H16 : FMT_F32,
+                                nullptr, nullptr, prev_half ? net->gscale_out + (k - 1) : nullptr, CAT_ELT_BWD,
+                                prev_half ? DF : nullptr));
         }
     }
     if (overlap) {      // join: the caller's stream continues only after the last weight gradient has landed
