@@ -697,10 +697,64 @@ maxpool_bwd_amax_kernel(const GradRef dzp, Geo gp, const unsigned char* __restri
     }
 }
 
+// Half plane in, half plane out, same GradScale: eight channels per thread, the routing is a byte compare and a mask
+// (no conversion); every access is 16 bytes (8 for the arg-max bytes).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_amax8_kernel(const __half* __restrict__ dzp, Geo gp, const unsigned char* __restrict__ amax, Geo g, int pool_h,
+                         __half* dzf) {
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= g.Cs / 8) return;
+    const int c0 = cv * 8;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const bool odd_w = g.W > 2 * gp.W, odd_h = pool_h == 2 && g.H > 2 * gp.H;
+    for (long long prow = (long long)blockIdx.x * blockDim.y + threadIdx.y; prow < gp.rows;
+         prow += (long long)gridDim.x * blockDim.y) {
+        if (gp.mask != nullptr && !gp.mask[prow]) continue;
+        const unsigned img = (unsigned)(gp.Hp * gp.Wp);
+        const int n = (int)((unsigned long long)prow / img);
+        const unsigned rr = (unsigned)(prow - (long long)n * img);
+        const int py = (int)(rr / (unsigned)gp.Wp) - gp.padH, px = (int)(rr % (unsigned)gp.Wp) - gp.padW;
+        const long long r00 = geo_row(g, n, py * pool_h, 2 * px);
+        const uint4 gsrc = *reinterpret_cast<const uint4*>(dzp + prow * gp.Cs + c0);
+        const uint2 am = *reinterpret_cast<const uint2*>(amax + prow * gp.Cs + c0);
+        uint4 o[4];
+#pragma unroll
+        for (unsigned pos = 0; pos < 4; ++pos) {
+            const unsigned m_lo = __vcmpeq4(am.x, pos * 0x01010101u), m_hi = __vcmpeq4(am.y, pos * 0x01010101u);
+            o[pos] = make_uint4(gsrc.x & __byte_perm(m_lo, 0u, 0x1100u), gsrc.y & __byte_perm(m_lo, 0u, 0x3322u),
+                                gsrc.z & __byte_perm(m_hi, 0u, 0x1100u), gsrc.w & __byte_perm(m_hi, 0u, 0x3322u));
+        }
+        *reinterpret_cast<uint4*>(dzf + r00 * g.Cs + c0) = o[0];
+        *reinterpret_cast<uint4*>(dzf + (r00 + 1) * g.Cs + c0) = o[1];
+        if (pool_h == 2) {
+            *reinterpret_cast<uint4*>(dzf + (r00 + g.Wp) * g.Cs + c0) = o[2];
+            *reinterpret_cast<uint4*>(dzf + (r00 + g.Wp + 1) * g.Cs + c0) = o[3];
+        }
+        const bool last_x = odd_w && px == gp.W - 1, last_y = odd_h && py == gp.H - 1;
+        if (last_x) {
+            *reinterpret_cast<uint4*>(dzf + (r00 + 2) * g.Cs + c0) = zero;
+            if (pool_h == 2) *reinterpret_cast<uint4*>(dzf + (r00 + g.Wp + 2) * g.Cs + c0) = zero;
+        }
+        if (last_y) {
+            *reinterpret_cast<uint4*>(dzf + (r00 + 2 * g.Wp) * g.Cs + c0) = zero;
+            *reinterpret_cast<uint4*>(dzf + (r00 + 2 * g.Wp + 1) * g.Cs + c0) = zero;
+            if (last_x) *reinterpret_cast<uint4*>(dzf + (r00 + 2 * g.Wp + 2) * g.Cs + c0) = zero;
+        }
+    }
+}
+
 int maxpool_backward_amax(GradRef dzp, const Geo& gp, const unsigned char* amax, const Geo& gf, int pool_h, void* dzf,
                           int fmt, const unsigned* absmax, cudaStream_t s) {
     EW_CHECK(gf);
     EW_CHECK(gp);
+    if (dzp.half && fmt == FMT_H16 && dzp.bits == absmax && dzp.mul == nullptr && gf.Cs % 8 == 0 && gf.Cs == gp.Cs &&
+        gf.W - 2 * gp.W <= 1 && gf.W >= 2 * gp.W && (pool_h == 1 ? gf.H == gp.H : (gf.H - 2 * gp.H <= 1 && gf.H >= 2 * gp.H))) {
+        const int cv = gf.Cs / 8, bx = cv < 32 ? cv : 32, by = 256 / bx;
+        dim3 grid(ew_shape(gp).grid.x, (cv + bx - 1) / bx);
+        maxpool_bwd_amax8_kernel<<<grid, dim3(bx, by), 0, s>>>((const __half*)dzp.p, gp, amax, gf, pool_h, (__half*)dzf);
+        FSB_LAUNCHED();
+        return 0;
+    }
     FSB_REQUIRE(gf.W - 2 * gp.W <= 1 && gf.W >= 2 * gp.W && (pool_h == 1 ? gf.H == gp.H : (gf.H - 2 * gp.H <= 1 && gf.H >= 2 * gp.H)),
                 "maxpool_backward: geometries are not a floor-mode 2x pooling pair");
     EwShape sh = ew_shape(gp);
@@ -1566,7 +1620,7 @@ struct C8ResIn {
 };
 
 template <bool FAST>
-__device__ __forceinline__ void c8res_load(C8ResIn& in, const GradRef& dA, const float* z, const float* out, const __half* r0h,
+__device__ __forceinline__ void c8res_load(C8ResIn& in, const GradRef& dA, const float* z, const float* out,
                                            const float* zr, long long idx) {
     if (dA.half) {
         in.g0 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(dA.p) + idx);
@@ -1587,8 +1641,8 @@ __device__ __forceinline__ void f8_from(const uint4& a, const uint4& b, float (&
     for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(w[i]);
 }
 
-__device__ __forceinline__ bool c8res_fast_ok(const BnCoef& bn, const void* out, const void* r0h, int c0, int C) {
-    bool ok = out != nullptr && bn.slope != nullptr;
+__device__ __forceinline__ bool c8res_fast_ok(const BnCoef& bn, const void* out, const void* smask, int c0, int C) {
+    bool ok = out != nullptr && smask != nullptr && bn.slope != nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (c0 + i >= C) continue;
@@ -1623,7 +1677,8 @@ struct C8ResCoef {
         }
     }
     __device__ __forceinline__ void compute(const C8ResIn& in, bool g_half, float inv, float (&dy)[8], float (&zh)[8],
-                                            float (&dsl)[8]) const {
+                                            float (&dsl)[8], unsigned& posbits) const {
+        posbits = 0u;
         float g[8], o[8];
         if (g_half) unpack8(in.g0, g);
         else f8_from(in.g0, in.g1, g);
@@ -1634,6 +1689,7 @@ struct C8ResCoef {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool pos = ov[i] > 0.f;
+                posbits |= pos ? (1u << i) : 0u;
                 const float gi = g[i] * inv;
                 const float y = pos ? ov[i] : ov[i] * e[i];
                 dy[i] = pos ? gi : sl[i] * gi;
@@ -1659,7 +1715,7 @@ struct C8ResCoef {
 };
 
 template <bool FAST>
-__device__ __forceinline__ void c8res_reduce_body(const GradRef& dA, const float* z, const float* out, const __half* r0h,
+__device__ __forceinline__ void c8res_reduce_body(const GradRef& dA, const float* z, const float* out, unsigned char* smask,
                                                   const Geo& g, const BnCoef& bn, const Residual& res, int c0, C8Sums& S) {
     C8ResCoef<FAST> k;
     k.load(bn, res, c0, g.C);
@@ -1676,12 +1732,15 @@ __device__ __forceinline__ void c8res_reduce_body(const GradRef& dA, const float
         }
 #pragma unroll
         for (int j = 0; j < ROWS; ++j)
-            if (ok[j]) c8res_load<FAST>(in[j], dA, z, out, r0h, res.zr, (row0 + j * stride) * g.Cs + c0);
+            if (ok[j]) c8res_load<FAST>(in[j], dA, z, out, res.zr, (row0 + j * stride) * g.Cs + c0);
 #pragma unroll
         for (int j = 0; j < ROWS; ++j)
             if (ok[j]) {
                 float dy[8], zh[8], dsl[8];
-                k.compute(in[j], dA.half != 0, inv, dy, zh, dsl);
+                unsigned posbits;
+                k.compute(in[j], dA.half != 0, inv, dy, zh, dsl, posbits);
+                // the apply pass takes the PReLU branch from this byte instead of re-reading the float32 output
+                if (FAST) smask[(row0 + j * stride) * (g.Cs >> 3) + (c0 >> 3)] = (unsigned char)posbits;
                 float m = 0.f, zm = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -1698,7 +1757,7 @@ __device__ __forceinline__ void c8res_reduce_body(const GradRef& dA, const float
 }
 
 __global__ void __launch_bounds__(256, 2)
-bn_bwd_c8res_reduce_kernel(const GradRef dA, const float* __restrict__ z, const float* __restrict__ out, const void* r0_hi,
+bn_bwd_c8res_reduce_kernel(const GradRef dA, const float* __restrict__ z, const float* __restrict__ out, unsigned char* smask,
                            Geo g, BnCoef bn, Residual res, double* partials) {
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
     const bool cok = cv < g.Cs / 8;
@@ -1708,18 +1767,17 @@ bn_bwd_c8res_reduce_kernel(const GradRef dA, const float* __restrict__ z, const 
     for (int i = 0; i < 8; ++i) { S.s0[i] = 0.f; S.s1[i] = 0.f; S.s2[i] = 0.f; }
     S.mx = 0.f; S.zx = 0.f;
     if (cok) {
-        const __half* r0h = reinterpret_cast<const __half*>(r0_hi);
-        if (c8res_fast_ok(bn, out, r0_hi, c0, g.C)) c8res_reduce_body<true>(dA, z, out, r0h, g, bn, res, c0, S);
-        else c8res_reduce_body<false>(dA, z, out, r0h, g, bn, res, c0, S);
+        if (c8res_fast_ok(bn, out, smask, c0, g.C)) c8res_reduce_body<true>(dA, z, out, smask, g, bn, res, c0, S);
+        else c8res_reduce_body<false>(dA, z, out, smask, g, bn, res, c0, S);
     }
     c8_publish(S, g, partials);
 }
 
-template <bool FAST>
-__device__ __forceinline__ void c8res_apply_body(const GradRef& dA, const float* z, const float* out, const __half* r0h,
-                                                 const Geo& g, const BnCoef& bn, const Residual& res, const float* c1,
-                                                 const float* c2, __half* dz, float gscale, __half* dres, float dscale, int c0) {
-    C8ResCoef<FAST> k;
+// general path of the apply pass: y3 recomputed from z3 and zp
+__device__ __forceinline__ void c8res_apply_general(const GradRef& dA, const float* z, const Geo& g, const BnCoef& bn,
+                                                    const Residual& res, const float* c1, const float* c2, __half* dz,
+                                                    float gscale, __half* dres, float dscale, int c0) {
+    C8ResCoef<false> k;
     k.load(bn, res, c0, g.C);
     const float inv = dA.half ? gs_pow2(-gs_exponent2(dA.bits, dA.mul)) : 1.f;
     float pq[8], qq[8], rr[8];
@@ -1731,11 +1789,58 @@ __device__ __forceinline__ void c8res_apply_body(const GradRef& dA, const float*
         qq[i] = pad ? 0.f : -sc * c2[c0 + i];
         rr[i] = pad ? 0.f : -sc * c1[c0 + i];
     }
-    constexpr int ROWS = FAST ? 2 : 1;
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < g.rows; row += stride) {
+        if (g.mask != nullptr && !g.mask[row]) continue;
+        const long long idx = row * g.Cs + c0;
+        C8ResIn in;
+        c8res_load<false>(in, dA, z, nullptr, res.zr, idx);
+        float dy[8], zh[8], dsl[8];
+        unsigned posbits;
+        k.compute(in, dA.half != 0, inv, dy, zh, dsl, posbits);
+        unsigned wz[4], wr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float o0 = fmaf(pq[2 * i], dy[2 * i], fmaf(qq[2 * i], zh[2 * i], rr[2 * i]));
+            const float o1 = fmaf(pq[2 * i + 1], dy[2 * i + 1], fmaf(qq[2 * i + 1], zh[2 * i + 1], rr[2 * i + 1]));
+            const __half2 hz = __floats2half2_rn(o0, o1);
+            const __half2 hr = __floats2half2_rn(dy[2 * i] * dscale, dy[2 * i + 1] * dscale);
+            wz[i] = *reinterpret_cast<const unsigned*>(&hz);
+            wr[i] = *reinterpret_cast<const unsigned*>(&hr);
+        }
+        *reinterpret_cast<uint4*>(dz + idx) = make_uint4(wz[0], wz[1], wz[2], wz[3]);
+        if (dres) *reinterpret_cast<uint4*>(dres + idx) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+    }
+}
+
+// fast path of the apply pass: the PReLU branch comes from the sign byte the reduce pass left, so only the incoming
+// gradient and z3 are read:   dz = g (pos ? P1 : P2) + z Q + R ,  dres = g (pos ? D1 : D2)
+__device__ __forceinline__ void c8res_apply_fast(const GradRef& dA, const float* __restrict__ z,
+                                                 const unsigned char* __restrict__ smask, const Geo& g, const BnCoef& bn,
+                                                 const float* c1, const float* c2, __half* dz, float gscale, __half* dres,
+                                                 float dscale, int c0) {
+    const float inv = dA.half ? gs_pow2(-gs_exponent2(dA.bits, dA.mul)) : 1.f;
+    float P1[8], P2[8], Q[8], R[8], D2[8];
+    const float D1 = inv * dscale;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool pad = c0 + i >= g.C;
+        const float sl = pad ? 1.f : bn.slope[c0 + i];
+        const float sc = pad ? 0.f : bn.scale[c0 + i] * gscale, is = bn.invstd[c0 + i], mu = bn.mean[c0 + i];
+        const float q = pad ? 0.f : -sc * c2[c0 + i];
+        P1[i] = sc * inv;
+        P2[i] = P1[i] * sl;
+        Q[i] = q * is;
+        R[i] = pad ? 0.f : -sc * c1[c0 + i] - q * mu * is;
+        D2[i] = pad ? 0.f : D1 * sl;
+    }
+    const bool g_half = dA.half != 0;
+    constexpr int ROWS = 2;
     const long long stride = (long long)gridDim.x * blockDim.y;
     for (long long row0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; row0 < g.rows; row0 += ROWS * stride) {
         bool ok[ROWS];
-        C8ResIn in[ROWS];
+        uint4 g0[ROWS], g1[ROWS], z0[ROWS], z1[ROWS];
+        unsigned mk[ROWS];
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) {
             const long long row = row0 + j * stride;
@@ -1743,20 +1848,34 @@ __device__ __forceinline__ void c8res_apply_body(const GradRef& dA, const float*
         }
 #pragma unroll
         for (int j = 0; j < ROWS; ++j)
-            if (ok[j]) c8res_load<FAST>(in[j], dA, z, out, r0h, res.zr, (row0 + j * stride) * g.Cs + c0);
+            if (ok[j]) {
+                const long long row = row0 + j * stride, idx = row * g.Cs + c0;
+                if (g_half) {
+                    g0[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(dA.p) + idx);
+                } else {
+                    g0[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dA.p) + idx);
+                    g1[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dA.p) + idx + 4);
+                }
+                z0[j] = *reinterpret_cast<const uint4*>(z + idx);
+                z1[j] = *reinterpret_cast<const uint4*>(z + idx + 4);
+                mk[j] = smask[row * (g.Cs >> 3) + (c0 >> 3)];
+            }
 #pragma unroll
         for (int j = 0; j < ROWS; ++j)
             if (ok[j]) {
                 const long long idx = (row0 + j * stride) * g.Cs + c0;
-                float dy[8], zh[8], dsl[8];
-                k.compute(in[j], dA.half != 0, inv, dy, zh, dsl);
+                float gv[8], zv[8];
+                if (g_half) unpack8(g0[j], gv);
+                else f8_from(g0[j], g1[j], gv);
+                f8_from(z0[j], z1[j], zv);
                 unsigned wz[4], wr[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float o0 = fmaf(pq[2 * i], dy[2 * i], fmaf(qq[2 * i], zh[2 * i], rr[2 * i]));
-                    const float o1 = fmaf(pq[2 * i + 1], dy[2 * i + 1], fmaf(qq[2 * i + 1], zh[2 * i + 1], rr[2 * i + 1]));
+                    const bool p0 = (mk[j] >> (2 * i)) & 1u, p1 = (mk[j] >> (2 * i + 1)) & 1u;
+                    const float o0 = fmaf(gv[2 * i], p0 ? P1[2 * i] : P2[2 * i], fmaf(zv[2 * i], Q[2 * i], R[2 * i]));
+                    const float o1 = fmaf(gv[2 * i + 1], p1 ? P1[2 * i + 1] : P2[2 * i + 1], fmaf(zv[2 * i + 1], Q[2 * i + 1], R[2 * i + 1]));
                     const __half2 hz = __floats2half2_rn(o0, o1);
-                    const __half2 hr = __floats2half2_rn(dy[2 * i] * dscale, dy[2 * i + 1] * dscale);
+                    const __half2 hr = __floats2half2_rn(gv[2 * i] * (p0 ? D1 : D2[2 * i]), gv[2 * i + 1] * (p1 ? D1 : D2[2 * i + 1]));
                     wz[i] = *reinterpret_cast<const unsigned*>(&hz);
                     wr[i] = *reinterpret_cast<const unsigned*>(&hr);
                 }
@@ -1767,18 +1886,17 @@ __device__ __forceinline__ void c8res_apply_body(const GradRef& dA, const float*
 }
 
 __global__ void __launch_bounds__(256, 2)
-bn_bwd_c8res_apply_kernel(const GradRef dA, const float* __restrict__ z, const float* __restrict__ out, const void* r0_hi,
-                          Geo g, BnCoef bn, Residual res, const float* c1, const float* c2, void* dz, const unsigned* absmax,
-                          void* dres, const unsigned* dres_bits) {
+bn_bwd_c8res_apply_kernel(const GradRef dA, const float* __restrict__ z, const float* __restrict__ out,
+                          const unsigned char* smask, Geo g, BnCoef bn, Residual res, const float* c1, const float* c2,
+                          void* dz, const unsigned* absmax, void* dres, const unsigned* dres_bits) {
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
     if (cv >= g.Cs / 8) return;
     const int c0 = cv * 8;
     const float gscale = gs_scale(absmax), dscale = gs_scale(dres_bits);
-    const __half* r0h = reinterpret_cast<const __half*>(r0_hi);
-    if (c8res_fast_ok(bn, out, r0_hi, c0, g.C))
-        c8res_apply_body<true>(dA, z, out, r0h, g, bn, res, c1, c2, (__half*)dz, gscale, (__half*)dres, dscale, c0);
+    if (c8res_fast_ok(bn, out, smask, c0, g.C))
+        c8res_apply_fast(dA, z, smask, g, bn, c1, c2, (__half*)dz, gscale, (__half*)dres, dscale, c0);
     else
-        c8res_apply_body<false>(dA, z, out, r0h, g, bn, res, c1, c2, (__half*)dz, gscale, (__half*)dres, dscale, c0);
+        c8res_apply_general(dA, z, g, bn, res, c1, c2, (__half*)dz, gscale, (__half*)dres, dscale, c0);
 }
 
 static const int C8_MAX_BLOCKS = 592;   // 4 x 148 SMs
@@ -1796,25 +1914,25 @@ static EwShape c8_shape(const Geo& g) {
     return s;
 }
 
-int bn_res_bwd_compact_reduce(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
+int bn_res_bwd_compact_reduce(GradRef dA, const float* z, const float* out, unsigned char* smask, const Geo& g, BnCoef bn,
                               Residual res, double* partials, cudaStream_t s) {
     EW_CHECK(g);
     FSB_REQUIRE(g.Cs % 8 == 0 && res.zr && z, "compact residual BatchNorm backward: bad operands");
     EwShape sh = c8_shape(g);
-    bn_bwd_c8res_reduce_kernel<<<sh.grid, sh.block, 0, s>>>(dA, z, out, r0_hi, g, bn, res, partials);
+    bn_bwd_c8res_reduce_kernel<<<sh.grid, sh.block, 0, s>>>(dA, z, out, smask, g, bn, res, partials);
     FSB_LAUNCHED();
     return 0;
 }
 
 int bn_res_bwd_compact_blocks(const Geo& g) { return (int)c8_shape(g).grid.x; }
 
-int bn_res_bwd_compact_apply(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
+int bn_res_bwd_compact_apply(GradRef dA, const float* z, const float* out, const unsigned char* smask, const Geo& g, BnCoef bn,
                              Residual res, const float* c1, const float* c2, void* dz, const unsigned* absmax, void* dres,
                              const unsigned* dres_bits, cudaStream_t s) {
     EW_CHECK(g);
     FSB_REQUIRE(g.Cs % 8 == 0 && res.zr && z && absmax && (!dres || dres_bits), "compact residual BatchNorm backward: bad operands");
     EwShape sh = c8_shape(g);
-    bn_bwd_c8res_apply_kernel<<<sh.grid, sh.block, 0, s>>>(dA, z, out, r0_hi, g, bn, res, c1, c2, dz, absmax, dres, dres_bits);
+    bn_bwd_c8res_apply_kernel<<<sh.grid, sh.block, 0, s>>>(dA, z, out, smask, g, bn, res, c1, c2, dz, absmax, dres, dres_bits);
     FSB_LAUNCHED();
     return 0;
 }

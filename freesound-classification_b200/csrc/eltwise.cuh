@@ -108,15 +108,17 @@ int bn_act_bwd_apply(GradRef dA1, GradRef dA2, const float* z, const void* a_hi,
                      const unsigned* dres_bits, const unsigned* absmax, cudaStream_t s);
 
 // Compact backward of a residual activation out = prelu(BN(z) + r), r = prelu(res.zr * res.scale + res.shift) (mixed
-// mode): eight channels per thread; y and its sign from the float32 `out`, zhat from out and the hi half plane of r
-// (r0_hi) where that is well conditioned, from z / res.zr otherwise (out, r0_hi may be nullptr: always the latter).
-// Writes dz and dres = dy as ONE scaled half plane each.  Records: bn_res_bwd_compact_blocks(g) x [5][Cs].
-int bn_res_bwd_compact_reduce(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
+// mode): eight channels per thread.  Where the slope is well conditioned the reduce pass takes y and its sign from the
+// float32 `out` (instead of recomputing r from res.zr) and leaves one sign byte per (row, 8 channels) in `smask`
+// (rows * Cs / 8 bytes); the apply pass then reads only the gradient, z and that byte.  Other channel groups (or
+// out / smask == nullptr) recompute y from z and res.zr.  Writes dz and dres = dy as ONE scaled half plane each.
+// Records: bn_res_bwd_compact_blocks(g) x [5][Cs].
+int bn_res_bwd_compact_reduce(GradRef dA, const float* z, const float* out, unsigned char* smask, const Geo& g, BnCoef bn,
                               Residual res, double* partials, cudaStream_t s);
 int bn_res_bwd_compact_blocks(const Geo& g);
-int bn_res_bwd_compact_apply(GradRef dA, const float* z, const float* out, const void* r0_hi, const Geo& g, BnCoef bn,
-                             Residual res, const float* c1, const float* c2, void* dz, const unsigned* absmax, void* dres,
-                             const unsigned* dres_bits, cudaStream_t s);
+int bn_res_bwd_compact_apply(GradRef dA, const float* z, const float* out, const unsigned char* smask, const Geo& g,
+                             BnCoef bn, Residual res, const float* c1, const float* c2, void* dz, const unsigned* absmax,
+                             void* dres, const unsigned* dres_bits, cudaStream_t s);
 
 // column sums of a dense (rows, C) matrix with row stride ld (final Linear bias gradient)
 int colsum(const float* x, long long rows, int C, int ld, float* out, cudaStream_t s);

@@ -75,6 +75,7 @@ struct BlockPlan {
     RnnHead rnn;
     void* pk_rnn[2];     // packed W_ih / b_ih per direction
     unsigned char* pool_amax;   // training, blocks with an entry GEMM: arg-max position of every pool window
+    unsigned char* sign3;       // training: PReLU-branch bytes of the block output (compact bn3 backward), rows * Cs / 8
     // backward (compact mode: da2 / da1 / dr0a / dr0b / dzp / du are scaled half planes, common.cuh GradRef)
     float* d_out;
     void *da2, *da1, *dr0a, *dr0b, *dzp, *du;
@@ -266,6 +267,7 @@ size_t carve(fsb_net* net, char* base, int N, int T, int training) {
         }
         size_t pe = (size_t)B.g.rows * B.g.Cs;
         B.pool_amax = (!direct0 && training) ? b.take<unsigned char>(pe) : nullptr;
+        B.sign3 = training ? b.take<unsigned char>(pe / 8) : nullptr;
         B.zp = b.take<float>(pe);
         B.r0 = b.take_bytes(pe * 4);
         B.z1 = b.take<float>(pe);
@@ -1008,11 +1010,11 @@ static int backward_impl(fsb_net* net, const float* dlogits, const float* const*
         const GradRef dout = dout_half(k) ? grad_h16(B.d_out, net->gscale_out + k) : grad_f32(B.d_out);
         if (cmp) {
             const BnCoef coef3 = B.bn3.coef(P[P_PRELU3]);
-            RUN(CAT_ELT_BWD, 0, bn_res_bwd_compact_reduce(dout, B.z3, B.out, B.r0, B.g, coef3, res, net->partials, s));
+            RUN(CAT_ELT_BWD, 0, bn_res_bwd_compact_reduce(dout, B.z3, B.out, B.sign3, B.g, coef3, res, net->partials, s));
             RUN(CAT_ELT_BWD, 0, bn_bwd_finalize(net->partials, bn_res_bwd_compact_blocks(B.g), B.g.pixels, B.bn3.C, B.bn3.Cs,
                                                 B.bn3.scale, G(pb + P_BN3_W), G(pb + P_BN3_B), G(pb + P_PRELU3), B.bn3.c1,
                                                 B.bn3.c2, GS + B_3, GS + B_IN, nullptr, s));
-            RUN(CAT_ELT_BWD, 0, bn_res_bwd_compact_apply(dout, B.z3, B.out, B.r0, B.g, coef3, res, B.bn3.c1, B.bn3.c2, B.dz3,
+            RUN(CAT_ELT_BWD, 0, bn_res_bwd_compact_apply(dout, B.z3, B.out, B.sign3, B.g, coef3, res, B.bn3.c1, B.bn3.c2, B.dz3,
                                                          GS + B_3, B.dr0b, GS + B_IN, s));
         } else {
             FSB_TRY(bn_backward(net, s, dout, kNoGrad, B.z3, nullptr, B.g, B.bn3, P[P_PRELU3], res, kNoDrop,
