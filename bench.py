@@ -167,7 +167,9 @@ def ncu_traffic(kernel_substr, pick="max"):
 
         def val(r, i):
             return float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
-        vals = [val(r, ri) + val(r, wi) for r in rows[rows.index(header) + 2:] if len(r) == len(header) and kernel_substr in r[ki]]
+        names = kernel_substr if isinstance(kernel_substr, (tuple, list)) else (kernel_substr,)
+        vals = [val(r, ri) + val(r, wi) for r in rows[rows.index(header) + 2:]
+                if len(r) == len(header) and any(n in r[ki] for n in names)]
         if not vals:
             return None
         return max(vals) if pick == "max" else sum(vals) / len(vals)
@@ -395,9 +397,10 @@ def rooflines(args, acc, kind, batch, value_per_gpu, peaks, training=True):
     feat_ms = acc["feat"][0]
     feat_bytes = FEAT_MB_PER_CLIP[kind] * 1e6 * batch
     feat_gbs = feat_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else 0.0
-    roofline_feat = {"bound": "hbm", "kernel": "feat_kernel (framing + Hann + rFFT%s + log)" % (" + mel" if kind == "2d" else ""),
+    roofline_feat = {"bound": "hbm", "kernel": "%s (framing + Hann + rFFT%s + log)" % (
+                         "feat2048_mel_kernel" if kind == "2d" else "feat_kernel", " + mel" if kind == "2d" else ""),
                      "achieved": feat_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": feat_gbs / peaks["hbm"],
-                     "traffic": ncu_traffic("feat_kernel", "mean"), "ms_per_launch": feat_ms,
+                     "traffic": ncu_traffic(("feat2048_mel_kernel", "feat_kernel"), "mean"), "ms_per_launch": feat_ms,
                      "algorithmic_mb_per_launch": feat_bytes / 1e6, "peak_source": peaks["source"]}
     return roofline, roofline_feat
 

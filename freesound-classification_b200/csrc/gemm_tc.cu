@@ -84,6 +84,9 @@ struct ConvTcParams {
 constexpr int EPI_BOX_BYTES = 4096;             // one staged box: 32 rows x 128 bytes; 4 epilogue warps x nstg boxes
 constexpr int MAX_T = 2;
 
+// OUT_HALF: the compact-backward dgrad instantiation (half output planes); a template parameter so that the float32
+// epilogue of the forward GEMMs keeps its register allocation (a run-time branch cost the 1x1 layers 9 %)
+template <bool OUT_HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmZ32, const __grid_constant__ CUtensorMap tmZ16, const ConvTcParams p) {
@@ -223,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t stg0 = epi_stage + (uint32_t)(q * p.nstg) * EPI_BOX_BYTES;
         const unsigned char* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
         double* my_acc = stat_acc + (size_t)q * 2 * p.BN;
-        const float oscale = gs_inv_scale(p.out_scale) * (p.out_half ? gs_pow2(gs_exponent2(p.out_scale, p.out_mul)) : 1.f);
+        const float oscale = gs_inv_scale(p.out_scale) * (OUT_HALF ? gs_pow2(gs_exponent2(p.out_scale, p.out_mul)) : 1.f);
         // per-lane column statistics of this CTA's column tile: compensated float32 sums in registers (a DADD per panel
         // through shared memory was the top stall of the 1x1 layers); [128-column chunk][32-column panel][sum, sum of squares]
         float accS[2][4][2], accC[2][4][2];
@@ -299,7 +302,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 __syncwarp();
                                 const uint32_t stg = stg0 + sb * EPI_BOX_BYTES;
                                 const float* stg_g = reinterpret_cast<const float*>(stg0_g + sb * EPI_BOX_BYTES);
-                                if (p.out_half) {
+                                if (OUT_HALF) {
                                     // half output: 64-byte staged rows in the SWIZZLE_64B pattern (16-byte chunk index xor
                                     // address bits 7..8), or plain 32-byte rows for a 16-column panel
                                     const uint32_t rbh = wide ? 64u : 32u;
@@ -338,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     tma_store_2d(wide ? &tmZ32 : &tmZ16, stg, nt * p.BN + cl0, (int)m0 + q * 32);
                                     bulk_commit();
                                 }
-                                if (p.stats && (wide || lane < 16)) {
+                                if (!OUT_HALF && p.stats && (wide || lane < 16)) {
                                     // lane l sums column cl0 + l over this warp's interior rows, straight from the staged box
                                     const uint32_t bits = ibits[t];
                                     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains
@@ -372,7 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         if (lane == 0) bulk_wait_all();            // the staged boxes must be written before the CTA retires
-        if (p.stats) {
+        if (!OUT_HALF && p.stats) {
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
@@ -908,10 +911,12 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
     }
     static bool attr_set = false;
     if (!attr_set) {
-        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    conv_tc_kernel<<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
+    if (L->p.out_half) conv_tc_kernel<true><<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
+    else conv_tc_kernel<false><<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
     FSB_LAUNCHED();
     if (st) *st->nblk = L->grid;
     return 0;
