@@ -156,35 +156,52 @@ __global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_fwd_kernel(const Conv
             }
             tc_fence_before();
         };
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            const uint32_t buf = a_buf0 + (it & 1u) * C0T_ABUF;
+        // raw input patch of a tile, loaded one tile ahead: the loads complete behind the previous tile's epilogue
+        auto load_patch = [&](int tile, float (&f)[4][4], int& px, int& py, bool& live) {
             const long long q = (long long)tile * C0T_PX + r;
-            // ---- BN-applied 4 x 4 x 2 input patch of this pooled pixel (zero outside the image = conv padding)
-            float u0[4][4], u1[4][4];
-            if (q < p.npix) {
-                const int px = (int)(q % W2);
+            live = tile < p.ntiles && q < p.npix;
+            px = 0; py = 0;
+            if (live) {
+                px = (int)(q % W2);
                 const long long t = q / W2;
-                const int py = (int)(t % H2), n = (int)(t / H2);
+                py = (int)(t % H2);
+                const int n = (int)(t / H2);
                 const float* img = p.feat + (long long)n * p.H * p.W;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int y = 2 * py - 1 + i;
                     const bool yok = y >= 0 && y < p.H;
-                    const float e1 = yok ? fmaf(c0t_freq_enc(y, p.H), sc1, sh1) : 0.f;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int x = 2 * px - 1 + j;
-                        const bool ok = yok && x >= 0 && x < p.W;
-                        u0[i][j] = ok ? fmaf(__ldg(img + (long long)y * p.W + x), sc0, sh0) : 0.f;
-                        u1[i][j] = ok ? e1 : 0.f;
+                        f[i][j] = (yok && x >= 0 && x < p.W) ? __ldg(img + (long long)y * p.W + x) : 0.f;
                     }
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) u0[i][j] = u1[i][j] = 0.f;
             }
+        };
+        float fr[4][4];
+        int cpx, cpy;
+        bool clive;
+        load_patch(blockIdx.x, fr, cpx, cpy, clive);
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = a_buf0 + (it & 1u) * C0T_ABUF;
+            const long long q = (long long)tile * C0T_PX + r;
+            // ---- BN-applied 4 x 4 x 2 input patch of this pooled pixel (zero outside the image = conv padding)
+            float u0[4][4], u1[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int y = 2 * cpy - 1 + i;
+                const bool yok = clive && y >= 0 && y < p.H;
+                const float e1 = yok ? fmaf(c0t_freq_enc(y, p.H), sc1, sh1) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = 2 * cpx - 1 + j;
+                    const bool ok = yok && x >= 0 && x < p.W;
+                    u0[i][j] = ok ? fmaf(fr[i][j], sc0, sh0) : 0.f;
+                    u1[i][j] = ok ? e1 : 0.f;
+                }
+            }
+            load_patch(tile + (int)gridDim.x, fr, cpx, cpy, clive);      // the next tile's loads fly during the epilogue below
 #pragma unroll
             for (int pos = 0; pos < 4; ++pos) {
                 const int sy = pos >> 1, sx = pos & 1;

@@ -276,10 +276,20 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
         const int ci = (int)(u % c.CsIn);
         const int t = (int)(u / c.CsIn);
         if (co >= c.Cout || ci >= c.Cin) continue;
-        float s = 0.f;
-#pragma unroll 8
-        for (int sp = 0; sp < splits; ++sp) s += P[sp * plane + i];
-        dw[((long long)co * c.Cin + ci) * c.ntaps + t] = s * unscale;
+        // up to 128 partial planes per element and only ~10^4 elements in the 1x1 layers: the loop is latency bound, so
+        // 32 loads are kept in flight on four independent chains (fixed order: deterministic)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int sp = 0;
+        for (; sp + 32 <= splits; sp += 32) {
+            float v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = P[(long long)(sp + u) * plane + i];
+#pragma unroll
+            for (int u = 0; u < 32; u += 4) { s0 += v[u]; s1 += v[u + 1]; s2 += v[u + 2]; s3 += v[u + 3]; }
+        }
+#pragma unroll 4
+        for (; sp < splits; ++sp) s0 += P[(long long)sp * plane + i];
+        dw[((long long)co * c.Cin + ci) * c.ntaps + t] = ((s0 + s1) + (s2 + s3)) * unscale;
     }
 }
 
