@@ -1899,7 +1899,7 @@ bn_bwd_c8res_apply_kernel(const GradRef dA, const float* __restrict__ z, const f
         c8res_apply_general(dA, z, g, bn, res, c1, c2, (__half*)dz, gscale, (__half*)dres, dscale, c0);
 }
 
-static const int C8_MAX_BLOCKS = 592;   // 4 x 148 SMs
+static const int C8_MAX_BLOCKS = 296;   // 2 x 148 SMs: one resident wave (128 registers, 2 CTAs per SM)
 
 static EwShape c8_shape(const Geo& g) {
     const int cv = g.Cs / 8;
