@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "eltwise.cuh"
 
 namespace fsb {
@@ -13,7 +15,16 @@ struct EwShape {
     dim3 grid, block;
 };
 
-static const int EW_MAX_BLOCKS = 1184;  // 8 x 148 SMs
+static int ew_max_blocks() {            // 8 x 148 SMs by default; FSB200_EW_BLOCKS overrides (tuning)
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("FSB200_EW_BLOCKS");
+        v = e ? atoi(e) : 1184;
+        if (v < 1) v = 1184;
+    }
+    return v;
+}
+#define EW_MAX_BLOCKS ew_max_blocks()
 
 static EwShape ew_shape(const Geo& g) {
     int cv = g.Cs / 4;
