@@ -421,7 +421,9 @@ def test_compact_backward_matches_float32_gradient_planes(cls_name, tmp_path):
         rel = float((g_c[k].double() - g_f[k].double()).norm()) / denom
         # the input-BatchNorm beta of blocks >= 1 sums a gradient plane that telescopes to border terms:
         # the half rounding of that plane shows up most there
-        tol = 1e-2 if re.search(r"conv_modules\.[1-9]\.0\.bias$", k) else 5e-3
+        # (the two-element tensors of block 0's input BatchNorm get the 2e-2 of the full-size oracle test)
+        tol = 2e-2 if re.search(r"conv_modules\.0\.0\.(bias|weight)$", k) else \
+            1e-2 if re.search(r"conv_modules\.[1-9]\.0\.bias$", k) else 5e-3
         worst = max(worst, rel / tol)
         report.append((rel, k))
     report.sort(reverse=True)
