@@ -928,19 +928,15 @@ int absmax_bits(const float* x, long long n, unsigned* bits, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward of a = act(BN(z) [+ r]) : shared recomputation of dy (and the PReLU slope term)
-//
-// Compact backward (mixed mode): the incoming gradient may be ONE half plane with a GradScale (written by the dgrad
-// epilogue), and zhat / the PReLU branch may be taken from the hi plane of the stored activation `a` instead of the
-// float32 pre-activation z -- half the bytes per element on both inputs.  The inverse map a -> y -> zhat is used per
-// thread (four channels) only where it is well conditioned: 1/64 <= slope <= 16, gamma != 0 and |beta| <= 8 |gamma|
-// (zhat error <= 2^-12 (|zhat| + 8)); every other channel group reads z as before.
+// backward of a = act(BN(z) [+ r]) : shared recomputation of dy (and the PReLU slope term).
+// These 4-channel kernels serve the float32-plane backward (strict / float32 modes, FSB200_COMPACT_BWD=0, the FC head);
+// incoming gradients may be float32 planes or scaled half planes (GradRef).  The compact backward of the mixed mode runs
+// the 8-channel kernels further down.
 struct BwdCoef {
     Coef4 cb, cr;
-    float4 mean, invstd;      // from_a: beta, 1 / gamma
-    float4 rsl;               // from_a: 1 / slope
+    float4 mean, invstd;
     float inv1, inv2;         // inverse GradScale of the two incoming gradient planes (1 for float32 planes)
-    bool has_res, from_a;
+    bool has_res;
 };
 
 struct BwdIn {
@@ -950,10 +946,10 @@ struct BwdIn {
 
 // RES: the activation has a residual branch (res.zr); DA2: the incoming gradient is dA1 + dA2
 template <bool RES, bool DA2>
-__device__ __forceinline__ BwdIn bwd_load(const GradRef& dA1, const GradRef& dA2, const float* z, const __half* a,
-                                          bool from_a, const float* zr, long long idx) {
+__device__ __forceinline__ BwdIn bwd_load(const GradRef& dA1, const GradRef& dA2, const float* z, const float* zr,
+                                          long long idx) {
     BwdIn in;
-    in.z = from_a ? ldh4(a + idx) : ld4(z + idx);
+    in.z = ld4(z + idx);
     in.g = ld_grad(dA1, idx);
     if (RES) in.r = ld4(zr + idx);
     if (DA2) in.g2 = ld_grad(dA2, idx);
@@ -964,15 +960,7 @@ template <bool RES, bool DA2>
 __device__ __forceinline__ void bwd_compute(const BwdIn& in, const BwdCoef& k, const Dropout& dr, long long idx,
                                             float4& dy, float4& zhat, float4& dsl) {
     const float4 zz = in.z;
-    float4 y;
-    if (!RES && k.from_a) {
-        // zz holds a = prelu(y): invert the activation (slope > 0, so the sign of a is the sign of y)
-        y = k.cb.has_sl ? make_float4(zz.x > 0.f ? zz.x : zz.x * k.rsl.x, zz.y > 0.f ? zz.y : zz.y * k.rsl.y,
-                                      zz.z > 0.f ? zz.z : zz.z * k.rsl.z, zz.w > 0.f ? zz.w : zz.w * k.rsl.w)
-                        : zz;
-    } else {
-        y = affine4(zz, k.cb.sc, k.cb.sh);
-    }
+    float4 y = affine4(zz, k.cb.sc, k.cb.sh);
     if (RES) {
         float4 r = affine4(in.r, k.cr.sc, k.cr.sh);
         if (k.cr.has_sl) r = prelu4(r, k.cr.sl);
@@ -993,51 +981,21 @@ __device__ __forceinline__ void bwd_compute(const BwdIn& in, const BwdCoef& k, c
         dsl = make_float4(0.f, 0.f, 0.f, 0.f);
         dy = g;
     }
-    // (z - mean) * invstd, or (y - beta) * (1 / gamma) when working from the stored activation
-    const float4 base = (!RES && k.from_a) ? y : zz;
-    zhat = make_float4((base.x - k.mean.x) * k.invstd.x, (base.y - k.mean.y) * k.invstd.y,
-                       (base.z - k.mean.z) * k.invstd.z, (base.w - k.mean.w) * k.invstd.w);
+    zhat = make_float4((zz.x - k.mean.x) * k.invstd.x, (zz.y - k.mean.y) * k.invstd.y,
+                       (zz.z - k.mean.z) * k.invstd.z, (zz.w - k.mean.w) * k.invstd.w);
 }
 
 template <bool RES>
 __device__ __forceinline__ BwdCoef load_bwd(const BnCoef& bn, const Residual& res, const GradRef& dA1, const GradRef& dA2,
-                                            const void* a_hi, int c0) {
+                                            int c0) {
     BwdCoef k;
     k.cb = load_coef(bn.scale, bn.shift, bn.slope, c0);
     k.has_res = RES;
     if (RES) k.cr = load_coef(res.scale, res.shift, res.slope, c0);
     k.mean = ld4(bn.mean + c0);
     k.invstd = ld4(bn.invstd + c0);
-    k.rsl = make_float4(1.f, 1.f, 1.f, 1.f);
     k.inv1 = dA1.half ? gs_pow2(-gs_exponent2(dA1.bits, dA1.mul)) : 1.f;
     k.inv2 = (dA2.p && dA2.half) ? gs_pow2(-gs_exponent2(dA2.bits, dA2.mul)) : 1.f;
-    k.from_a = false;
-    if (!RES && a_hi) {
-        const float sc[4] = {k.cb.sc.x, k.cb.sc.y, k.cb.sc.z, k.cb.sc.w}, sh[4] = {k.cb.sh.x, k.cb.sh.y, k.cb.sh.z, k.cb.sh.w};
-        const float sl[4] = {k.cb.sl.x, k.cb.sl.y, k.cb.sl.z, k.cb.sl.w};
-        const float mu[4] = {k.mean.x, k.mean.y, k.mean.z, k.mean.w}, is[4] = {k.invstd.x, k.invstd.y, k.invstd.z, k.invstd.w};
-        float beta[4], rg[4], rs[4];
-        bool ok = true;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (sc[i] == 0.f && is[i] == 0.f) {          // padded channel: a = 0, zhat = 0
-                beta[i] = 0.f; rg[i] = 0.f; rs[i] = 1.f;
-                continue;
-            }
-            const float gamma = sc[i] / is[i];
-            beta[i] = fmaf(mu[i], sc[i], sh[i]);
-            rg[i] = 1.f / gamma;
-            rs[i] = 1.f / sl[i];
-            ok = ok && fabsf(gamma) > 0.f && fabsf(beta[i]) <= 8.f * fabsf(gamma) && fabsf(rg[i]) < 3.0e38f &&
-                 (!k.cb.has_sl || (sl[i] >= 0.015625f && sl[i] <= 16.f));
-        }
-        if (ok) {
-            k.from_a = true;
-            k.mean = make_float4(beta[0], beta[1], beta[2], beta[3]);
-            k.invstd = make_float4(rg[0], rg[1], rg[2], rg[3]);
-            k.rsl = make_float4(rs[0], rs[1], rs[2], rs[3]);
-        }
-    }
     return k;
 }
 
@@ -1056,15 +1014,14 @@ static int bn_bwd_c8_apply(GradRef dA1, GradRef dA2, const float* z, const void*
 // and cross-block reductions run in double.
 template <bool RES, bool DA2>
 __global__ void __launch_bounds__(256, 2)
-bn_act_bwd_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
+bn_act_bwd_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, Geo g,
                          BnCoef bn, Residual res, Dropout dr_in, double* partials) {
     const Dropout dr = resolve_seed(dr_in);
     EW_PROLOGUE
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
     float4 mx = s0, zx = s0;              // max |dy|, max |zhat|: bound of |dz| for the half-precision gradient scale
     if (cok) {
-        const BwdCoef k = load_bwd<RES>(bn, res, dA1, dA2, a_hi, c0);
-        const __half* ah = reinterpret_cast<const __half*>(a_hi);
+        const BwdCoef k = load_bwd<RES>(bn, res, dA1, dA2, c0);
         // ROWS rows in flight per thread (two loads each in the plain variant): see bn_act_fwd_simple_kernel
         constexpr int ROWS = (RES || DA2) ? 2 : 4;
         const long long stride = (long long)gridDim.x * blockDim.y;
@@ -1080,7 +1037,7 @@ bn_act_bwd_reduce_kernel(const GradRef dA1, const GradRef dA2, const float* __re
             }
 #pragma unroll
             for (int j = 0; j < ROWS; ++j)
-                if (ok[j]) in[j] = bwd_load<RES, DA2>(dA1, dA2, z, ah, k.from_a, res.zr, idx[j]);
+                if (ok[j]) in[j] = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idx[j]);
 #pragma unroll
             for (int j = 0; j < ROWS; ++j)
                 if (ok[j]) {
@@ -1106,11 +1063,11 @@ int bn_act_bwd_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi
     if (bn_bwd_compact_ok(dA1, dA2, g, res, dr)) return bn_bwd_c8_reduce(dA1, dA2, z, a_hi, g, bn, partials, s);
     EwShape sh = ew_shape(g);
     if (res.zr)
-        bn_act_bwd_reduce_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, partials);
+        bn_act_bwd_reduce_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
     else if (dA2.p)
-        bn_act_bwd_reduce_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, partials);
+        bn_act_bwd_reduce_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
     else
-        bn_act_bwd_reduce_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, partials);
+        bn_act_bwd_reduce_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, partials);
     FSB_LAUNCHED();
     return 0;
 }
@@ -1169,7 +1126,7 @@ __device__ __forceinline__ void store_dres(void* dres, const unsigned* dres_bits
 
 template <bool RES, bool DA2>
 __global__ void __launch_bounds__(256, 2)
-bn_act_bwd_apply_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, const void* a_hi, Geo g,
+bn_act_bwd_apply_kernel(const GradRef dA1, const GradRef dA2, const float* __restrict__ z, Geo g,
                         BnCoef bn, Residual res, Dropout dr_in, const float* c1, const float* c2, void* dz, int fmt,
                         void* dres, const unsigned* dres_bits, const unsigned* absmax) {
     const Dropout dr = resolve_seed(dr_in);
@@ -1177,15 +1134,14 @@ bn_act_bwd_apply_kernel(const GradRef dA1, const GradRef dA2, const float* __res
     if (!cok) return;
     const float gscale = gs_scale(absmax);
     const float dscale = gs_scale(dres_bits);
-    const BwdCoef k = load_bwd<RES>(bn, res, dA1, dA2, a_hi, c0);
-    const __half* ah = reinterpret_cast<const __half*>(a_hi);
+    const BwdCoef k = load_bwd<RES>(bn, res, dA1, dA2, c0);
     float4 m1 = ld4(c1 + c0), m2 = ld4(c2 + c0);
     const long long plane = g.rows * g.Cs;
     EW_PIXEL_LOOP2 {
         const long long idxA = rowA * g.Cs + c0, idxB = rowB * g.Cs + c0;
         BwdIn inA, inB;
-        if (okA) inA = bwd_load<RES, DA2>(dA1, dA2, z, ah, k.from_a, res.zr, idxA);
-        if (okB) inB = bwd_load<RES, DA2>(dA1, dA2, z, ah, k.from_a, res.zr, idxB);
+        if (okA) inA = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxA);
+        if (okB) inB = bwd_load<RES, DA2>(dA1, dA2, z, res.zr, idxB);
         float4 dy, zh, dsl;
         if (okA) {
             bwd_compute<RES, DA2>(inA, k, dr, idxA, dy, zh, dsl);
@@ -1214,11 +1170,11 @@ int bn_act_bwd_apply(GradRef dA1, GradRef dA2, const float* z, const void* a_hi,
         return bn_bwd_c8_apply(dA1, dA2, z, a_hi, g, bn, c1, c2, dz, fmt, absmax, s);
     EwShape sh = ew_shape(g);
     if (res.zr)
-        bn_act_bwd_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
+        bn_act_bwd_apply_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
     else if (dA2.p)
-        bn_act_bwd_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
+        bn_act_bwd_apply_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
     else
-        bn_act_bwd_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, a_hi, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
+        bn_act_bwd_apply_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(dA1, dA2, z, g, bn, res, dr, c1, c2, dz, fmt, dres, dres_bits, absmax);
     FSB_LAUNCHED();
     return 0;
 }
@@ -1265,36 +1221,29 @@ __device__ __forceinline__ bool c8_from_a(const BnCoef& bn, const void* a_hi, in
     return ok;
 }
 
-// Per-channel coefficients of one path.  FROM_A: y = a > 0 ? a : a * e (e = 1 / slope), zhat = y * b + a_ (b = 1 / gamma,
-// a_ = -beta / gamma).  From z: y = z * e + f (e = scale, f = shift), zhat = z * b + a_ (b = invstd, a_ = -mean * invstd).
-template <bool FROM_A>
+// General path (from the float32 pre-activation): y = z * e + f (e = scale, f = shift), zhat = z * b + a (b = invstd,
+// a = -mean * invstd).  The fast path (c8_reduce_fast / c8_apply_fast below) folds its coefficients differently.
 struct C8Coef {
-    float e[8], f[FROM_A ? 1 : 8], sl[8], a[8], b[8];
+    float e[8], f[8], sl[8], a[8], b[8];
     bool has_sl;
     __device__ __forceinline__ void load(const BnCoef& bn, int c0, int C) {
         has_sl = bn.slope != nullptr;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float sc = bn.scale[c0 + i], sh = bn.shift[c0 + i], mu = bn.mean[c0 + i], is = bn.invstd[c0 + i];
+            const float is = bn.invstd[c0 + i];
             sl[i] = (has_sl && c0 + i < C) ? bn.slope[c0 + i] : 1.f;     // padded channels: scale = shift = 0, everything stays 0
-            if (FROM_A) {
-                const bool pad = sc == 0.f && is == 0.f;
-                const float rg = pad ? 0.f : is / sc;                 // 1 / gamma
-                e[i] = 1.f / sl[i];
-                b[i] = rg;
-                a[i] = pad ? 0.f : -fmaf(mu, sc, sh) * rg;
-            } else {
-                e[i] = sc; f[i] = sh;
-                b[i] = is;
-                a[i] = -mu * is;
-            }
+            e[i] = bn.scale[c0 + i];
+            f[i] = bn.shift[c0 + i];
+            b[i] = is;
+            a[i] = -bn.mean[c0 + i] * is;
         }
     }
 };
 
+// raw operands of one row: the source is the stored activation's hi plane (FROM_A, s0 only) or z (two float4)
 template <bool DA2, bool FROM_A>
 struct C8In {
-    uint4 s0, s1;      // source: a (s0 only) or z (two float4)
+    uint4 s0, s1;
     uint4 g1, g2;
     __device__ __forceinline__ void load(const GradRef& dA1, const GradRef& dA2, const float* z, const __half* a, long long idx) {
         if (FROM_A) {
@@ -1308,18 +1257,12 @@ struct C8In {
     }
 };
 
-// dy, zhat and the PReLU-slope gradient term of the eight channels
-template <bool DA2, bool FROM_A>
-__device__ __forceinline__ void c8_compute(const C8In<DA2, FROM_A>& in, const C8Coef<FROM_A>& k, float inv1, float inv2,
+// dy, zhat and the PReLU-slope gradient term of the eight channels (general path)
+template <bool DA2>
+__device__ __forceinline__ void c8_compute(const C8In<DA2, false>& in, const C8Coef& k, float inv1, float inv2,
                                            float (&dy)[8], float (&zh)[8], float (&dsl)[8]) {
-    float src[8], g[8];
-    if (FROM_A) {
-        unpack8(in.s0, src);
-    } else {
-        const unsigned w[8] = {in.s0.x, in.s0.y, in.s0.z, in.s0.w, in.s1.x, in.s1.y, in.s1.z, in.s1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) src[i] = __uint_as_float(w[i]);
-    }
+    float g[8];
+    const unsigned w[8] = {in.s0.x, in.s0.y, in.s0.z, in.s0.w, in.s1.x, in.s1.y, in.s1.z, in.s1.w};
     unpack8(in.g1, g);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] *= inv1;
@@ -1331,12 +1274,12 @@ __device__ __forceinline__ void c8_compute(const C8In<DA2, FROM_A>& in, const C8
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float v = src[i];
-        const float y = FROM_A ? ((v > 0.f || !k.has_sl) ? v : v * k.e[i]) : fmaf(v, k.e[i], k.f[i]);
+        const float v = __uint_as_float(w[i]);
+        const float y = fmaf(v, k.e[i], k.f[i]);
         const bool pos = y > 0.f || !k.has_sl;
         dy[i] = pos ? g[i] : k.sl[i] * g[i];
         dsl[i] = pos ? 0.f : y * g[i];
-        zh[i] = fmaf(FROM_A ? y : v, k.b[i], k.a[i]);
+        zh[i] = fmaf(v, k.b[i], k.a[i]);
     }
 }
 
@@ -1489,7 +1432,7 @@ __device__ __forceinline__ void c8_apply_fast(const GradRef& dA1, const GradRef&
 template <bool DA2>
 __device__ __forceinline__ void c8_reduce_general(const GradRef& dA1, const GradRef& dA2, const float* __restrict__ z,
                                                   const Geo& g, const BnCoef& bn, int c0, C8Sums& S) {
-    C8Coef<false> k;
+    C8Coef k;
     k.load(bn, c0, g.C);
     const float inv1 = gs_pow2(-gs_exponent2(dA1.bits, dA1.mul));
     const float inv2 = DA2 ? gs_pow2(-gs_exponent2(dA2.bits, dA2.mul)) : 1.f;
@@ -1503,7 +1446,7 @@ __device__ __forceinline__ void c8_reduce_general(const GradRef& dA1, const Grad
         for (int j = 0; j < ROWS; ++j)
             if (ok[j]) {
                 float dy[8], zh[8], dsl[8];
-                c8_compute<DA2, false>(in[j], k, inv1, inv2, dy, zh, dsl);
+                c8_compute<DA2>(in[j], k, inv1, inv2, dy, zh, dsl);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     S.s0[i] += dy[i];
@@ -1565,7 +1508,7 @@ template <bool DA2, bool OUT_F32>
 __device__ __forceinline__ void c8_apply_general(const GradRef& dA1, const GradRef& dA2, const float* __restrict__ z,
                                                  const Geo& g, const BnCoef& bn, const float* c1, const float* c2, void* dz,
                                                  float gscale, int c0) {
-    C8Coef<false> k;
+    C8Coef k;
     k.load(bn, c0, g.C);
     const float inv1 = gs_pow2(-gs_exponent2(dA1.bits, dA1.mul));
     const float inv2 = DA2 ? gs_pow2(-gs_exponent2(dA2.bits, dA2.mul)) : 1.f;
@@ -1589,7 +1532,7 @@ __device__ __forceinline__ void c8_apply_general(const GradRef& dA1, const GradR
             if (ok[j]) {
                 const long long idx = (row0 + j * stride) * g.Cs + c0;
                 float dy[8], zh[8], dsl[8], o[8];
-                c8_compute<DA2, false>(in[j], k, inv1, inv2, dy, zh, dsl);
+                c8_compute<DA2>(in[j], k, inv1, inv2, dy, zh, dsl);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = fmaf(pq[i], dy[i], fmaf(qq[i], zh[i], rr[i]));
                 if (OUT_F32) {

@@ -93,9 +93,11 @@ int absmax_bits(const float* x, long long n, unsigned* bits, cudaStream_t s);
 //             extra_bits (optional): bit pattern of a bound that is ADDED to the |dz| bound (a later scatter-add into dz)
 //   apply   : dz = scale * (dy - c1 - zhat*c2) -> fmt planes (half formats: times the GradScale of `absmax`);
 //             dres (optional) = dy, float32 or (dres_bits != nullptr) one half plane with that GradScale
-// Gradients come as float32 planes or scaled half planes (GradRef, common.cuh).  a_hi (optional, no residual): hi half
-// plane of the stored activation a = act(BN(z)); channel groups whose inverse map a -> zhat is well conditioned read
-// it instead of the float32 z (half the bytes), see eltwise.cu.
+// Gradients come as float32 planes or scaled half planes (GradRef, common.cuh).  When every incoming gradient is a half
+// plane, there is no residual / dropout and dz is float32 or ONE half plane, the compact 8-channel kernels run
+// (eltwise.cu): a_hi (optional) is then the hi half plane of the stored activation a = act(BN(z)), and channel groups
+// whose inverse map a -> zhat is well conditioned read it instead of the float32 z (half the bytes).  The 4-channel
+// kernels ignore a_hi.
 int bn_act_bwd_reduce(GradRef dA1, GradRef dA2, const float* z, const void* a_hi, const Geo& g, BnCoef bn,
                       Residual res, Dropout dr, double* partials, cudaStream_t s);
 // number of partial records bn_act_bwd_reduce writes for these operands (the `nblk` of bn_bwd_finalize)
