@@ -50,6 +50,19 @@ struct FwdStats {
 };
 int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
                   cudaStream_t s);
+// Eval forward (tensor-core back ends) with the FOLLOWING BatchNorm + PReLU folded into the epilogue: with running
+// statistics the BatchNorm is a fixed per-channel affine map, so a = prelu((conv + bias) * scale + shift) is written straight
+// as the hi / lo operand planes of the next GEMM and the float32 pre-activation is never materialised.  scale / shift:
+// CsOut entries (bn_finalize in eval mode); slope: C entries or nullptr.
+struct FwdAct {
+    const float* scale;
+    const float* shift;
+    const float* slope;
+    int C;
+    const unsigned char* mask;    // interior mask of the output geometry (border rows are written as zeros); nullptr = no border
+};
+int conv_gemm_fwd_act(int precision, const void* A, const void* packed, void* a_out, const ConvGeom& c, const FwdAct& act,
+                      cudaStream_t s);
 // dz_absmax (optional, tensor-core back ends): GradScale of dZ (common.cuh) -- dZ holds 2^k * gradient, the result is
 // multiplied by 2^-k.
 // out_half_mul (optional, tensor-core back ends; needs dz_absmax): dA is written as ONE half plane holding 2^j * dA,
@@ -83,6 +96,8 @@ size_t tc_packed_weight_bytes(const ConvGeom& c);
 int tc_pack_weights(const float* w, const float* bias, const ConvGeom& c, void* packed, cudaStream_t s);
 int tc_fwd(int precision, const void* A, const void* packed, float* Z, const ConvGeom& c, const FwdStats* st,
            cudaStream_t s);
+int tc_fwd_act(int precision, const void* A, const void* packed, void* a_out, const ConvGeom& c, const FwdAct& act,
+               cudaStream_t s);
 int tc_max_ctas();
 int tc_dgrad(int precision, const void* dZ, const void* packed, void* dA, const ConvGeom& c, const unsigned* dz_absmax,
              const float* out_half_mul, cudaStream_t s);

@@ -332,6 +332,11 @@ int conv_gemm_fwd(int precision, const void* A, const void* packed, float* Z, co
     }
     return 0;
 }
+int conv_gemm_fwd_act(int precision, const void* A, const void* packed, void* a_out, const ConvGeom& c, const FwdAct& act,
+                      cudaStream_t s) {
+    FSB_REQUIRE(precision != 0, "conv_gemm_fwd_act: tensor-core back ends only");
+    return tc_fwd_act(precision, A, packed, a_out, c, act, s);
+}
 int conv_gemm_dgrad(int precision, const void* dZ, const void* packed, void* dA, const ConvGeom& c,
                     const unsigned* dz_absmax, const float* out_half_mul, cudaStream_t s) {
     FSB_REQUIRE(precision != 0 || !out_half_mul, "conv_gemm_dgrad: the float32 back end writes float32 only");

@@ -79,17 +79,27 @@ struct ConvTcParams {
     // device float, the max column L1 norm of the weights: |D| <= max|dZ| * out_mul); tmZ32 / tmZ16 are half maps then
     int out_half;
     const float* out_mul;
+    // eval forward with the following BatchNorm + PReLU folded into the epilogue (EPI 2): the output is the NEXT GEMM's
+    // operand, a = prelu((acc + bias) * act_scale + act_shift), written as hi / lo half planes (tmZ32 / tmZ16 are 3-D half
+    // maps then); act_slope may be nullptr (no activation); vectors have ldz entries except act_slope (act_c)
+    const float* act_scale;
+    const float* act_shift;
+    const float* act_slope;
+    int act_c;
 };
 
 constexpr int EPI_BOX_BYTES = 4096;             // one staged box: 32 rows x 128 bytes; 4 epilogue warps x nstg boxes
 constexpr int MAX_T = 2;
 
-// OUT_HALF: the compact-backward dgrad instantiation (half output planes); a template parameter so that the float32
-// epilogue of the forward GEMMs keeps its register allocation (a run-time branch cost the 1x1 layers 9 %)
-template <bool OUT_HALF>
+// EPI 0: float32 output (+ bias, + BatchNorm statistics); 1: the compact-backward dgrad instantiation (one scaled half
+// plane); 2: eval forward with BatchNorm + PReLU folded in (hi / lo operand planes of the next GEMM).  A template
+// parameter so that the float32 epilogue of the training forward keeps its register allocation (a run-time branch cost
+// the 1x1 layers 9 %)
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmZ32, const __grid_constant__ CUtensorMap tmZ16, const ConvTcParams p) {
+    constexpr bool OUT_HALF = EPI == 1, OUT_ACT = EPI == 2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [stage ring: T x (hi, lo) activation boxes | tpg x (hi, lo) weight tiles][epilogue staging][barriers][bias][statistics]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -124,6 +134,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (p.stats)
         for (int i = threadIdx.x; i < 8 * p.BN; i += TC_THREADS) stat_acc[i] = 0.0;
+    // EPI 2: per-column (scale, shift incl. the conv bias, slope) in the statistics region (no statistics in eval)
+    float* act_s = reinterpret_cast<float*>(stat_acc);                                          // [3][BN]
+    if (OUT_ACT)
+        for (int i = threadIdx.x; i < p.BN; i += TC_THREADS) {
+            const int cg = nt * p.BN + i;
+            const bool in = cg < p.ldz;
+            const float sc = in ? p.act_scale[cg] : 0.f, sh = in ? p.act_shift[cg] : 0.f;
+            const float b = (p.bias && in) ? p.bias[cg] : 0.f;
+            act_s[i] = sc;
+            act_s[p.BN + i] = fmaf(sc, b, sh);
+            act_s[2 * p.BN + i] = (p.act_slope && cg < p.act_c) ? p.act_slope[cg] : 1.f;
+        }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nstages; ++i) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
@@ -240,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int t = 0; t < MAX_T; ++t) {
                 const long long row = ((long long)grp * p.T + t) * BM + rl;
-                inext[t] = (p.stats && grp < n_groups && t < p.T && row < p.rows) ? (p.mask ? p.mask[row] : 1) : 0;
+                inext[t] = ((p.stats || OUT_ACT) && grp < n_groups && t < p.T && row < p.rows) ? (p.mask ? p.mask[row] : 1) : 0;
             }
         };
         load_flags(grp0);
@@ -302,7 +324,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 __syncwarp();
                                 const uint32_t stg = stg0 + sb * EPI_BOX_BYTES;
                                 const float* stg_g = reinterpret_cast<const float*>(stg0_g + sb * EPI_BOX_BYTES);
-                                if (OUT_HALF) {
+                                if (OUT_ACT) {
+                                    // a = prelu(acc * scale + shift') split into hi / lo halves: two staged boxes (hi at
+                                    // the slot base, lo 2 KB above), rows as in the half-output case below
+                                    // border rows of the padded-flat output are the zero padding of the next conv: they
+                                    // must stay zero (the stand-alone BN-apply pass simply skips them)
+                                    const uint32_t rbh = wide ? 64u : 32u;
+                                    const bool has_sl = p.act_slope != nullptr;
+                                    const bool interior = (ibits[t] >> lane) & 1u;
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        if (wide || j < 2) {
+                                            const uint32_t ch = wide ? (uint32_t)((j ^ ((lane >> 1) & 3)) << 4) : (uint32_t)(j << 4);
+                                            const float* vv = v + pn * 32 + 8 * j;
+                                            const float* sc = act_s + cl0 + 8 * j;
+                                            uint32_t wh[4], wl[4];
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                float y0 = fmaf(vv[2 * e], sc[2 * e], sc[p.BN + 2 * e]);
+                                                float y1 = fmaf(vv[2 * e + 1], sc[2 * e + 1], sc[p.BN + 2 * e + 1]);
+                                                if (has_sl) {
+                                                    y0 = y0 > 0.f ? y0 : sc[2 * p.BN + 2 * e] * y0;
+                                                    y1 = y1 > 0.f ? y1 : sc[2 * p.BN + 2 * e + 1] * y1;
+                                                }
+                                                __half h0, l0, h1, l1;
+                                                split_h16(interior ? y0 : 0.f, h0, l0);
+                                                split_h16(interior ? y1 : 0.f, h1, l1);
+                                                wh[e] = pack_h2(h0, h1);
+                                                wl[e] = pack_h2(l0, l1);
+                                            }
+                                            st_shared_v4_u32(stg + (uint32_t)lane * rbh + ch, wh[0], wh[1], wh[2], wh[3]);
+                                            st_shared_v4_u32(stg + 2048u + (uint32_t)lane * rbh + ch, wl[0], wl[1], wl[2], wl[3]);
+                                        }
+                                    }
+                                } else if (OUT_HALF) {
                                     // half output: 64-byte staged rows in the SWIZZLE_64B pattern (16-byte chunk index xor
                                     // address bits 7..8), or plain 32-byte rows for a 16-column panel
                                     const uint32_t rbh = wide ? 64u : 32u;
@@ -338,10 +393,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 fence_async_smem();
                                 __syncwarp();
                                 if (lane == 0 && m0 + q * 32 < p.rows) {
-                                    tma_store_2d(wide ? &tmZ32 : &tmZ16, stg, nt * p.BN + cl0, (int)m0 + q * 32);
+                                    if (OUT_ACT) {
+                                        tma_store_3d(wide ? &tmZ32 : &tmZ16, stg, nt * p.BN + cl0, (int)m0 + q * 32, 0);
+                                        tma_store_3d(wide ? &tmZ32 : &tmZ16, stg + 2048u, nt * p.BN + cl0, (int)m0 + q * 32, 1);
+                                    } else {
+                                        tma_store_2d(wide ? &tmZ32 : &tmZ16, stg, nt * p.BN + cl0, (int)m0 + q * 32);
+                                    }
                                     bulk_commit();
                                 }
-                                if (!OUT_HALF && p.stats && (wide || lane < 16)) {
+                                if (EPI == 0 && p.stats && (wide || lane < 16)) {
                                     // lane l sums column cl0 + l over this warp's interior rows, straight from the staged box
                                     const uint32_t bits = ibits[t];
                                     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains
@@ -375,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         if (lane == 0) bulk_wait_all();            // the staged boxes must be written before the CTA retires
-        if (!OUT_HALF && p.stats) {
+        if (EPI == 0 && p.stats) {
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
@@ -731,6 +791,28 @@ int make_out_map_h(CUtensorMap* m, const void* base, long long rows, int ldz, in
     return 0;
 }
 
+// hi / lo half operand planes (Cs, rows, 2), box (box_cols, 32, 1): TMA-store target of the eval epilogue with the folded
+// BatchNorm + PReLU
+int make_out_map_act(CUtensorMap* m, const void* base, long long rows, int Cs, int box_cols, bool swizzle) {
+    auto fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return FSB_E_NODEVICE;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)Cs, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)Cs * 2, (cuuint64_t)rows * Cs * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(act output rows=%lld Cs=%d box=%d) failed: %d", rows, Cs, box_cols, (int)r);
+        return FSB_E_INVALID;
+    }
+    return 0;
+}
+
 // FSB200_* tuning switches, read once per process
 struct TcEnv {
     int mode;      // FSB200_TC_MODE: bit 0 = one TMA box per tap (no dx sharing), bit 1 = descriptor base_offset = row
@@ -815,7 +897,7 @@ LaunchCache<ConvLaunch> g_conv_cache;
 
 int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
                  const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
-                 const FwdStats* st, const unsigned* out_scale, const float* out_half_mul) {
+                 const FwdStats* st, const unsigned* out_scale, const float* out_half_mul, const FwdAct* act) {
     ConvTcParams& p = L.p;
     memset(&p, 0, sizeof(p));
     p.rows = rows;
@@ -833,6 +915,11 @@ int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacke
     p.out_half = out_half_mul ? 1 : 0;
     p.out_mul = out_half_mul;
     FSB_REQUIRE(!(st && out_half_mul), "conv_tc: fused statistics need the float32 output");
+    FSB_REQUIRE(!(act && (st || out_half_mul)), "conv_tc: the folded BatchNorm + PReLU epilogue is an eval-forward option");
+    if (act) {
+        p.act_scale = act->scale; p.act_shift = act->shift; p.act_slope = act->slope; p.act_c = act->C;
+        p.mask = act->mask;
+    }
     if (st) {
         const Geo& g = *st->g;
         FSB_REQUIRE(g.rows == rows && g.Cs == ldz, "conv_tc: statistics geometry does not match the output");
@@ -879,7 +966,10 @@ int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacke
     L.smem = fixed + stage * p.nstages;
     FSB_TRY(make_act_map(&L.tmA, A, rows, K, p.a_box_rows, p.bk));
     FSB_TRY(make_w_map(&L.tmW, wpacked, (long long)2 * c.ntaps * w_npad, w_kpad, bn, p.bk));
-    if (p.out_half) {
+    if (act) {
+        FSB_TRY(make_out_map_act(&L.tmZ32, Z, rows, ldz, 32, true));
+        FSB_TRY(make_out_map_act(&L.tmZ16, Z, rows, ldz, 16, false));
+    } else if (p.out_half) {
         FSB_TRY(make_out_map_h(&L.tmZ32, Z, rows, ldz, 32, true));
         FSB_TRY(make_out_map_h(&L.tmZ16, Z, rows, ldz, 16, false));
     } else {
@@ -894,7 +984,8 @@ int plan_conv_tc(ConvLaunch& L, int precision, const void* A, const void* wpacke
 
 int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad, int w_npad, int bn, int nt,
                    const float* bias, float* Z, long long rows, int K, int ldz, const ConvGeom& c, int sign,
-                   const FwdStats* st, const unsigned* out_scale, const float* out_half_mul, cudaStream_t s) {
+                   const FwdStats* st, const unsigned* out_scale, const float* out_half_mul, const FwdAct* act,
+                   cudaStream_t s) {
     const LaunchKey key = {(uint64_t)(uintptr_t)A, (uint64_t)(uintptr_t)wpacked, (uint64_t)(uintptr_t)Z, (uint64_t)rows,
                            (uint64_t)(uintptr_t)bias, (uint64_t)(uintptr_t)(st ? st->partials : nullptr),
                            (uint64_t)(uintptr_t)(st ? st->g->mask : nullptr), (uint64_t)(uintptr_t)out_scale,
@@ -902,21 +993,24 @@ int launch_conv_tc(int precision, const void* A, const void* wpacked, int w_kpad
                            ((uint64_t)(uint32_t)w_kpad << 32) | (uint32_t)w_npad,
                            ((uint64_t)(uint32_t)precision << 32) | (uint32_t)(sign + 1),
                            ((uint64_t)(uint32_t)c.ntaps << 32) | (uint32_t)c.offs[0], (uint64_t)(uint32_t)c.offs[1],
-                           (uint64_t)(uintptr_t)out_half_mul, 0};
+                           (uint64_t)(uintptr_t)out_half_mul,
+                           act ? ((uint64_t)(uintptr_t)act->scale ^ ((uint64_t)(uintptr_t)act->slope << 1) ^ ((uint64_t)act->C << 48) ^ 1u) : 0};
     ConvLaunch* L = g_conv_cache.find(key);
     if (!L) {
         ConvLaunch fresh;
-        FSB_TRY(plan_conv_tc(fresh, precision, A, wpacked, w_kpad, w_npad, bn, nt, bias, Z, rows, K, ldz, c, sign, st, out_scale, out_half_mul));
+        FSB_TRY(plan_conv_tc(fresh, precision, A, wpacked, w_kpad, w_npad, bn, nt, bias, Z, rows, K, ldz, c, sign, st, out_scale, out_half_mul, act));
         L = g_conv_cache.insert(key, fresh);
     }
     static bool attr_set = false;
     if (!attr_set) {
-        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        FSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    if (L->p.out_half) conv_tc_kernel<true><<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
-    else conv_tc_kernel<false><<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
+    if (L->p.act_scale) conv_tc_kernel<2><<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
+    else if (L->p.out_half) conv_tc_kernel<1><<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
+    else conv_tc_kernel<0><<<L->grid, TC_THREADS, L->smem, s>>>(L->tmA, L->tmW, L->tmZ32, L->tmZ16, L->p);
     FSB_LAUNCHED();
     if (st) *st->nblk = L->grid;
     return 0;
@@ -949,7 +1043,17 @@ int tc_fwd(int precision, const void* A, const void* packed, float* Z, const Con
     TcPackLayout L = pack_layout(c);
     const char* base = tc_pack_base(packed);
     return launch_conv_tc(precision, A, base + L.off_fwd, L.kpad_f, L.npad_f, L.bn_f, L.nt_f,
-                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, st, nullptr, nullptr, s);
+                          (const float*)(base + L.off_bias), Z, c.rows, c.CsIn, c.CsOut, c, +1, st, nullptr, nullptr, nullptr, s);
+}
+
+int tc_fwd_act(int precision, const void* A, const void* packed, void* a_out, const ConvGeom& c, const FwdAct& act,
+               cudaStream_t s) {
+    TcPackLayout L = pack_layout(c);
+    const char* base = tc_pack_base(packed);
+    FSB_REQUIRE(act.scale && act.shift, "tc_fwd_act: BatchNorm scale / shift required");
+    return launch_conv_tc(precision, A, base + L.off_fwd, L.kpad_f, L.npad_f, L.bn_f, L.nt_f,
+                          (const float*)(base + L.off_bias), (float*)a_out, c.rows, c.CsIn, c.CsOut, c, +1, nullptr, nullptr,
+                          nullptr, &act, s);
 }
 
 int tc_dgrad(int precision, const void* dZ, const void* packed, void* dA, const ConvGeom& c, const unsigned* dz_absmax,
@@ -958,7 +1062,7 @@ int tc_dgrad(int precision, const void* dZ, const void* packed, void* dA, const 
     const char* base = tc_pack_base(packed);
     FSB_REQUIRE(!out_half_mul || dz_absmax, "tc_dgrad: the half output needs the GradScale of dZ");
     return launch_conv_tc(precision, dZ, base + L.off_dgr, L.kpad_d, L.npad_d, L.bn_d, L.nt_d, nullptr, (float*)dA, c.rows,
-                          c.CsOut, c.CsIn, c, -1, nullptr, dz_absmax, out_half_mul, s);
+                          c.CsOut, c.CsIn, c, -1, nullptr, dz_absmax, out_half_mul, nullptr, s);
 }
 
 struct WgradShape {

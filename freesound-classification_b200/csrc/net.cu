@@ -105,6 +105,8 @@ struct fsb_net {
     // dzp are single scaled half planes, BatchNorm-backward reads the hi plane of the stored activation instead of the
     // float32 pre-activation, max-pool backward routes by stored arg-max bytes.
     bool compact = false;
+    int fuse_eval = 2;          // eval forward: BN1 (bit 0) / BN2 (bit 1) + PReLU folded into the conv GEMM epilogues
+                                // (FSB200_FUSE_EVAL; default: conv2 only, measured best)
     float* wl1 = nullptr;       // [num_blocks][4] max column L1 norm of the entry / conv1 / conv2 / conv3 weights
     // CUDA graphs: the launch sequence of a forward (or backward) call with a given set of pointers / shapes is captured
     // on its second occurrence and replayed afterwards (~130 launches become one cudaGraphLaunch).
@@ -455,6 +457,8 @@ extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, c
         net->conv0_tc = !(e && atoi(e) == 0);
         e = getenv("FSB200_GRAPHS");
         net->graphs = !(e && atoi(e) == 0);
+        e = getenv("FSB200_FUSE_EVAL");
+        net->fuse_eval = e ? atoi(e) & 3 : 2;
         e = getenv("FSB200_COMPACT_BWD");
         net->compact = net->prec_b == 2 && !(e && atoi(e) == 0);
     }
@@ -833,16 +837,33 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
         int nblk = 0;
         FwdStats st = {net->partials, &B.g, &nblk};
         const FwdStats* stp = training ? &st : nullptr;
-        RUN(CAT_GEMM_FWD, conv_flops(B.c1, B.g), conv_gemm_fwd(prec, B.r0, B.pk1, B.z1, B.c1, stp, s));
-        FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn1, P[P_BN1_W], P[P_BN1_B], RM[B_1], RV[B_1], cnt(B_1), training,
-                                 CAT_ELT_FWD));
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z1, B.g, B.bn1.coef(P[P_PRELU1]), kNoRes, kNoDrop, B.a1, fmt, nullptr,
-                                           nullptr, s));
-        RUN(CAT_GEMM_FWD, conv_flops(B.c2, B.g), conv_gemm_fwd(prec, B.a1, B.pk2, B.z2, B.c2, stp, s));
-        FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn2, P[P_BN2_W], P[P_BN2_B], RM[B_2], RV[B_2], cnt(B_2), training,
-                                 CAT_ELT_FWD));
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z2, B.g, B.bn2.coef(P[P_PRELU2]), kNoRes, kNoDrop, B.a2, fmt, nullptr,
-                                           nullptr, s));
+        // eval: BatchNorm is a fixed affine map (running statistics), so BN + PReLU can ride in the epilogue of the producing
+        // GEMM and the activation is written straight as operand planes (the float32 pre-activation is never materialised).
+        // fuse_eval bit 0: conv1 (1x1 -- its epilogue is the kernel's bottleneck, so the fold roughly breaks even),
+        // bit 1: conv2 (3x3, tensor-pipe bound: the fold is free).
+        const bool fuse1 = !training && prec != 0 && (net->fuse_eval & 1), fuse2 = !training && prec != 0 && (net->fuse_eval & 2);
+        if (fuse1) {
+            FSB_TRY(bn_finalize_from(net, s, 0, B.g, B.bn1, P[P_BN1_W], P[P_BN1_B], RM[B_1], RV[B_1], cnt(B_1), 0, CAT_ELT_FWD));
+            const FwdAct act1 = {B.bn1.scale, B.bn1.shift, P[P_PRELU1], B.C, B.g.mask};
+            RUN(CAT_GEMM_FWD, conv_flops(B.c1, B.g), conv_gemm_fwd_act(prec, B.r0, B.pk1, B.a1, B.c1, act1, s));
+        } else {
+            RUN(CAT_GEMM_FWD, conv_flops(B.c1, B.g), conv_gemm_fwd(prec, B.r0, B.pk1, B.z1, B.c1, stp, s));
+            FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn1, P[P_BN1_W], P[P_BN1_B], RM[B_1], RV[B_1], cnt(B_1), training,
+                                     CAT_ELT_FWD));
+            RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z1, B.g, B.bn1.coef(P[P_PRELU1]), kNoRes, kNoDrop, B.a1, fmt, nullptr,
+                                               nullptr, s));
+        }
+        if (fuse2) {
+            FSB_TRY(bn_finalize_from(net, s, 0, B.g, B.bn2, P[P_BN2_W], P[P_BN2_B], RM[B_2], RV[B_2], cnt(B_2), 0, CAT_ELT_FWD));
+            const FwdAct act2 = {B.bn2.scale, B.bn2.shift, P[P_PRELU2], B.C, B.g.mask};
+            RUN(CAT_GEMM_FWD, conv_flops(B.c2, B.g), conv_gemm_fwd_act(prec, B.a1, B.pk2, B.a2, B.c2, act2, s));
+        } else {
+            RUN(CAT_GEMM_FWD, conv_flops(B.c2, B.g), conv_gemm_fwd(prec, B.a1, B.pk2, B.z2, B.c2, stp, s));
+            FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn2, P[P_BN2_W], P[P_BN2_B], RM[B_2], RV[B_2], cnt(B_2), training,
+                                     CAT_ELT_FWD));
+            RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z2, B.g, B.bn2.coef(P[P_PRELU2]), kNoRes, kNoDrop, B.a2, fmt, nullptr,
+                                               nullptr, s));
+        }
         RUN(CAT_GEMM_FWD, conv_flops(B.c3, B.g), conv_gemm_fwd(prec, B.a2, B.pk3, B.z3, B.c3, stp, s));
         FSB_TRY(bn_finalize_from(net, s, nblk, B.g, B.bn3, P[P_BN3_W], P[P_BN3_B], RM[B_3], RV[B_3], cnt(B_3), training,
                                  CAT_ELT_FWD));
