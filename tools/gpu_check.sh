@@ -18,5 +18,8 @@ $FULL -k regex:wgrad_tc_kernel -s 34 -c 4 -f -o gpurun_out/${TAG}_wgrad_tc pytho
 $FULL -k regex:'feat2048_mel_kernel|feat_kernel|conv0_tc_fwd_kernel|conv0_tc_bwd_kernel' -s 3 -c 3 -f -o gpurun_out/${TAG}_feat_conv0 python tools/one_step.py 2 64 > gpurun_out/${TAG}_feat_conv0.log 2>&1
 tail -2 gpurun_out/${TAG}_feat_conv0.log
 # compact BatchNorm-backward kernels of block 0 (the last launches of the step)
-$FULL -k regex:'bn_bwd_c8_reduce_kernel|bn_bwd_c8_apply_kernel|bn_bwd_c8res_reduce_kernel|bn_bwd_c8res_apply_kernel' -s 86 -c 10 -f -o gpurun_out/${TAG}_bn_bwd python tools/one_step.py 2 64 > gpurun_out/${TAG}_bn_bwd.log 2>&1
-$FULL -k regex:'bn_act_fwd_simple_kernel|bn_act_fwd_kernel' -s 24 -c 4 -f -o gpurun_out/${TAG}_elt_fwd python tools/one_step.py 2 64 > gpurun_out/${TAG}_elt_fwd.log 2>&1
+# (gpurun merges at most 64 MiB back: the element-wise captures go without source import)
+LIGHT="$NCU --set full"
+$LIGHT -k regex:'bn_bwd_c8_reduce_kernel|bn_bwd_c8_apply_kernel|bn_bwd_c8res_reduce_kernel|bn_bwd_c8res_apply_kernel' -s 86 -c 6 -f -o gpurun_out/${TAG}_bn_bwd python tools/one_step.py 2 64 > gpurun_out/${TAG}_bn_bwd.log 2>&1
+$LIGHT -k regex:'bn_act_fwd_simple_kernel|bn_act_fwd_kernel' -s 26 -c 2 -f -o gpurun_out/${TAG}_elt_fwd python tools/one_step.py 2 64 > gpurun_out/${TAG}_elt_fwd.log 2>&1
+du -sh gpurun_out
