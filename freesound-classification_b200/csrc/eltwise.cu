@@ -421,7 +421,7 @@ __device__ __forceinline__ float4 fwd_compute(const FwdIn& in, const Coef4& cb, 
 template <bool STATS>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr_in, void* a_mma,
-                  int fmt, float* a_f32, double* out_stats) {
+                  int fmt, float* a_f32, double* out_stats, BnCoef post) {
     const Dropout dr = resolve_seed(dr_in);
     EW_PROLOGUE
     if (!STATS && !cok) return;
@@ -433,6 +433,15 @@ bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, D
         const bool has_res = res.zr != nullptr;
         if (has_res) cr = load_coef(res.scale, res.shift, res.slope, c0);
         const long long plane = g.rows * g.Cs;
+        // post (eval): the operand planes receive post(v) = the NEXT BatchNorm (+ PReLU) applied to this output
+        const bool has_post = post.scale != nullptr;
+        Coef4 cp = cb;
+        if (has_post) cp = load_coef(post.scale, post.shift, post.slope, c0);
+        auto post_apply = [&](float4 v) {
+            if (!has_post) return v;
+            float4 y = affine4(v, cp.sc, cp.sh);
+            return cp.has_sl ? prelu4(y, cp.sl) : y;
+        };
         EW_PIXEL_LOOP2 {
             const long long idxA = rowA * g.Cs + c0, idxB = rowB * g.Cs + c0;
             FwdIn inA, inB;
@@ -441,7 +450,7 @@ bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, D
             if (okA) {
                 float4 v = fwd_compute(inA, cb, cr, has_res, dr, idxA);
                 if (a_f32) st4(a_f32 + idxA, v);
-                if (a_mma) store_fmt(a_mma, fmt, plane, idxA, v);
+                if (a_mma) store_fmt(a_mma, fmt, plane, idxA, post_apply(v));
                 if (STATS) {
                     acc[0].add(v);
                     acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
@@ -450,7 +459,7 @@ bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, D
             if (okB) {
                 float4 v = fwd_compute(inB, cb, cr, has_res, dr, idxB);
                 if (a_f32) st4(a_f32 + idxB, v);
-                if (a_mma) store_fmt(a_mma, fmt, plane, idxB, v);
+                if (a_mma) store_fmt(a_mma, fmt, plane, idxB, post_apply(v));
                 if (STATS) {
                     acc[0].add(v);
                     acc[1].add(make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
@@ -495,18 +504,20 @@ bn_act_fwd_simple_kernel(const float* __restrict__ z, Geo g, BnCoef bn, void* a_
 }
 
 int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropout dr, void* a_mma, int fmt,
-                   float* a_f32, double* out_stats, cudaStream_t s) {
+                   float* a_f32, double* out_stats, cudaStream_t s, const BnCoef* post) {
     EW_CHECK(g);
     EwShape sh = ew_shape(g);
-    if (!out_stats && !res.zr && dr.p == 0.f && !a_f32 && a_mma) {
+    const BnCoef no_post = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const BnCoef pc = post ? *post : no_post;
+    if (!out_stats && !res.zr && dr.p == 0.f && !a_f32 && a_mma && !post) {
         bn_act_fwd_simple_kernel<<<sh.grid, sh.block, 0, s>>>(z, g, bn, a_mma, fmt);
         FSB_LAUNCHED();
         return 0;
     }
     if (out_stats)
-        bn_act_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, out_stats);
+        bn_act_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, out_stats, pc);
     else
-        bn_act_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, nullptr);
+        bn_act_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, nullptr, pc);
     FSB_LAUNCHED();
     return 0;
 }
@@ -521,12 +532,16 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 template <bool STATS>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int pool_h, double* out_stats,
-                   unsigned char* amax) {
+                   unsigned char* amax, BnCoef post, void* a_mma, int fmt) {
     EW_PROLOGUE
     if (!STATS && !cok) return;
     Acc4 acc[2];
     if (STATS) { acc[0].init(); acc[1].init(); }
     if (cok) {
+        const bool has_post = a_mma != nullptr;
+        Coef4 cp;
+        if (has_post) cp = load_coef(post.scale, post.shift, post.slope, c0);
+        const long long plane = g.rows * g.Cs;
         EW_PIXEL_LOOP {
             const unsigned img = (unsigned)(g.Hp * g.Wp);
             const int n = (int)((unsigned long long)row / img);
@@ -543,6 +558,11 @@ maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int p
                 m = max4(m, max4(v2, v3));
             }
             st4(zp + row * g.Cs + c0, m);
+            if (has_post) {              // eval: the BatchNorm + PReLU that follows, straight into the operand planes
+                float4 y = affine4(m, cp.sc, cp.sh);
+                if (cp.has_sl) y = prelu4(y, cp.sl);
+                store_fmt(a_mma, fmt, plane, row * g.Cs + c0, y);
+            }
             if (amax) {
                 const float a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w};
                 const float a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w};
@@ -570,13 +590,16 @@ maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int p
 }
 
 int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, double* out_stats,
-                    unsigned char* amax, cudaStream_t s) {
+                    unsigned char* amax, cudaStream_t s, const BnCoef* post, void* a_mma, int fmt) {
     EW_CHECK(gp);
+    FSB_REQUIRE(!post == !a_mma, "maxpool_forward: the fused BatchNorm output needs both its coefficients and its planes");
     EwShape sh = ew_shape(gp);
+    const BnCoef no_post = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const BnCoef pc = post ? *post : no_post;
     if (out_stats)
-        maxpool_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, out_stats, amax);
+        maxpool_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, out_stats, amax, pc, a_mma, fmt);
     else
-        maxpool_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr, amax);
+        maxpool_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr, amax, pc, a_mma, fmt);
     FSB_LAUNCHED();
     return 0;
 }

@@ -55,14 +55,18 @@ int freq_encoding_stats(int H, long long n_times_w, double* partials16, cudaStre
 // a = act(BN(z) [+ residual]) ; writes any of: GEMM-format plane(s) `a_mma` (fmt), float32 `a_f32`;
 // out_stats (optional): per-block partial sum / sum of squares of `a` ([ew_num_blocks(g)][2][Cs] doubles),
 // i.e. the batch statistics of the NEXT BatchNorm, gathered while the data is in registers
+// post (optional, eval): the operand planes receive post(a) -- the NEXT BatchNorm (+ PReLU), a fixed affine map when it runs
+// on running statistics -- while a_f32 still receives a
 int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropout dr, void* a_mma,
-                   int fmt, float* a_f32, double* out_stats, cudaStream_t s);
+                   int fmt, float* a_f32, double* out_stats, cudaStream_t s, const BnCoef* post = nullptr);
 
 // 2x2 (pool_h = 2) or 1x2 (pool_h = 1) max pool, floor mode: zf (gf) -> zp (gp)
 // out_stats (optional): partial sum / sum of squares of zp, [ew_num_blocks(gp)][2][Cs] doubles
 // amax (optional): position 0..3 of the first maximum of every window, one byte per pooled element (gp.rows * Cs bytes)
+// post + a_mma (optional, eval): additionally writes act(BN(zp)) of the BatchNorm that follows as GEMM operand planes (fmt)
 int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, int pool_h, double* out_stats,
-                    unsigned char* amax, cudaStream_t s);
+                    unsigned char* amax, cudaStream_t s, const BnCoef* post = nullptr, void* a_mma = nullptr,
+                    int fmt = FMT_F32);
 // dzf (fmt planes, full-res geometry) <- dzp routed to the first maximum of every window
 // absmax (optional): GradScale of the half-precision destination (common.cuh)
 int maxpool_backward(const float* dzp, const Geo& gp, const float* zf, const Geo& gf, int pool_h,

@@ -105,8 +105,9 @@ struct fsb_net {
     // dzp are single scaled half planes, BatchNorm-backward reads the hi plane of the stored activation instead of the
     // float32 pre-activation, max-pool backward routes by stored arg-max bytes.
     bool compact = false;
-    int fuse_eval = 2;          // eval forward: BN1 (bit 0) / BN2 (bit 1) + PReLU folded into the conv GEMM epilogues
-                                // (FSB200_FUSE_EVAL; default: conv2 only, measured best)
+    int fuse_eval = 14;         // eval forward folds (FSB200_FUSE_EVAL): bit 0 / 1: BN1 / BN2 + PReLU in the epilogue of conv1 /
+                                // conv2; bit 2: the next block's BN_in in the block-output kernel; bit 3: BN_a + PReLU_a in
+                                // the pooling kernel.  Default 14: everything but conv1 (measured best)
     float* wl1 = nullptr;       // [num_blocks][4] max column L1 norm of the entry / conv1 / conv2 / conv3 weights
     // CUDA graphs: the launch sequence of a forward (or backward) call with a given set of pointers / shapes is captured
     // on its second occurrence and replayed afterwards (~130 launches become one cudaGraphLaunch).
@@ -458,7 +459,7 @@ extern "C" int fsb_net_create(const fsb_net_config* cfg, const float* fb_vals, c
         e = getenv("FSB200_GRAPHS");
         net->graphs = !(e && atoi(e) == 0);
         e = getenv("FSB200_FUSE_EVAL");
-        net->fuse_eval = e ? atoi(e) & 3 : 2;
+        net->fuse_eval = e ? atoi(e) & 15 : 14;
         e = getenv("FSB200_COMPACT_BWD");
         net->compact = net->prec_b == 2 && !(e && atoi(e) == 0);
     }
@@ -713,6 +714,7 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
     net->dropout_seed = dropout_seed;
     const int frames = net->frames;
     int carried_nblk = 0;      // partial records left in net->partials by the previous block's last pass
+    bool u_ready = false;      // eval: the previous block's output kernel already wrote this block's BN_in output u
 
     // Weight packing (float32 -> bf16 hi/lo K-major tiles) depends on the parameters only: it runs on the side stream
     // in the shadow of the feature kernel and the block-0 entry conv; the first GEMM waits for it.
@@ -764,7 +766,8 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
 
     for (int k = 0; k < c.num_blocks; ++k) {
         BlockPlan& B = net->blocks[k];
-        bool zp_stats_ready = false;
+        bool zp_stats_ready = false, r0_ready = false;
+        const bool fuse_pool = !training && prec != 0 && (net->fuse_eval & 8);
         const float* const* P = params + (size_t)k * P_PER_BLOCK;
         float* const* RM = bn_mean + (size_t)k * B_PER_BLOCK;
         float* const* RV = bn_var + (size_t)k * B_PER_BLOCK;
@@ -809,29 +812,43 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
                                                       (long long)B.g_in.Hp * B.g_in.Wp * B.g_in.Cs, 1, B.g_in.Cs, s));
                 FSB_TRY(bn_forward_stats(net, s, B.x_in, B.g_in, B.bn_in, P[P_BNIN_W], P[P_BNIN_B], RM[B_IN], RV[B_IN],
                                          cnt(B_IN), training, CAT_ELT_FWD));
-            } else {
+            } else if (!u_ready) {
                 // statistics of the block input were gathered by the previous block's last element-wise pass
                 FSB_TRY(bn_finalize_from(net, s, carried_nblk, B.g_in, B.bn_in, P[P_BNIN_W], P[P_BNIN_B], RM[B_IN],
                                          RV[B_IN], cnt(B_IN), training, CAT_ELT_FWD));
             }
-            RUN(CAT_ELT_FWD, 0, bn_act_forward(B.x_in, B.g_in, B.bn_in.coef(nullptr), kNoRes, kNoDrop, B.u, fmt,
-                                               nullptr, nullptr, s));
+            if (!u_ready)
+                RUN(CAT_ELT_FWD, 0, bn_act_forward(B.x_in, B.g_in, B.bn_in.coef(nullptr), kNoRes, kNoDrop, B.u, fmt,
+                                                   nullptr, nullptr, s));
+            u_ready = false;
             FSB_TRY(join_packs());
             RUN(CAT_GEMM_FWD, conv_flops(B.entry, B.g_in),
                 conv_gemm_fwd(prec, B.u, B.pk_entry, B.zf, B.entry, nullptr, s));
-            RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1,
-                                                training ? net->partials : nullptr, B.pool_amax, s));
+            if (fuse_pool) {
+                // eval: BN_a + PReLU_a (fixed affine map) ride in the pooling kernel: zp and r0 in one pass
+                FSB_TRY(bn_finalize_from(net, s, 0, B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A], cnt(B_A), 0,
+                                         CAT_ELT_FWD));
+                const BnCoef ca = B.bn_a.coef(P[P_PRELUA]);
+                RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1, nullptr, nullptr, s, &ca,
+                                                    B.r0, fmt));
+                r0_ready = true;
+            } else {
+                RUN(CAT_ELT_FWD, 0, maxpool_forward(B.zf, B.g_full, B.zp, B.g, c.two_d ? 2 : 1,
+                                                    training ? net->partials : nullptr, B.pool_amax, s));
+            }
             zp_stats_ready = true;
         }
         // BN_a + PReLU_a -> r0
-        if (zp_stats_ready)
-            FSB_TRY(bn_finalize_from(net, s, ew_num_blocks(B.g), B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A],
-                                     cnt(B_A), training, CAT_ELT_FWD));
-        else
-            FSB_TRY(bn_forward_stats(net, s, B.zp, B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A], cnt(B_A),
-                                     training, CAT_ELT_FWD));
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.zp, B.g, B.bn_a.coef(P[P_PRELUA]), kNoRes, kNoDrop, B.r0, fmt, nullptr,
-                                           nullptr, s));
+        if (!r0_ready) {
+            if (zp_stats_ready)
+                FSB_TRY(bn_finalize_from(net, s, ew_num_blocks(B.g), B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A],
+                                         cnt(B_A), training, CAT_ELT_FWD));
+            else
+                FSB_TRY(bn_forward_stats(net, s, B.zp, B.g, B.bn_a, P[P_BNA_W], P[P_BNA_B], RM[B_A], RV[B_A], cnt(B_A),
+                                         training, CAT_ELT_FWD));
+            RUN(CAT_ELT_FWD, 0, bn_act_forward(B.zp, B.g, B.bn_a.coef(P[P_PRELUA]), kNoRes, kNoDrop, B.r0, fmt, nullptr,
+                                               nullptr, s));
+        }
         // resnet block: every conv GEMM gathers the batch statistics of its output in the epilogue
         FSB_TRY(join_packs());
         int nblk = 0;
@@ -870,8 +887,22 @@ static int forward_impl(fsb_net* net, const float* signal, const float* features
         Residual res = {B.zp, B.bn_a.scale, B.bn_a.shift, P[P_PRELUA]};
         // the block output feeds the next block's input BatchNorm: gather its statistics here
         const bool next_stats = training && k + 1 < c.num_blocks;
-        RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z3, B.g, B.bn3.coef(P[P_PRELU3]), res, kNoDrop, nullptr, fmt, B.out,
-                                           next_stats ? net->partials : nullptr, s));
+        if (!training && prec != 0 && (net->fuse_eval & 4) && k + 1 < c.num_blocks) {
+            // eval: the next block's input BatchNorm (fixed affine map) rides in this kernel: out (float32, for the head)
+            // and u of block k + 1 (operand planes of its entry conv) in one pass
+            BlockPlan& Bn = net->blocks[k + 1];
+            const float* const* Pn = params + (size_t)(k + 1) * P_PER_BLOCK;
+            FSB_TRY(bn_finalize_from(net, s, 0, Bn.g_in, Bn.bn_in, Pn[P_BNIN_W], Pn[P_BNIN_B],
+                                     bn_mean[(size_t)(k + 1) * B_PER_BLOCK + B_IN], bn_var[(size_t)(k + 1) * B_PER_BLOCK + B_IN],
+                                     bn_count ? bn_count[(size_t)(k + 1) * B_PER_BLOCK + B_IN] : nullptr, 0, CAT_ELT_FWD));
+            const BnCoef cn = Bn.bn_in.coef(nullptr);
+            RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z3, B.g, B.bn3.coef(P[P_PRELU3]), res, kNoDrop, Bn.u, fmt, B.out, nullptr, s,
+                                               &cn));
+            u_ready = true;
+        } else {
+            RUN(CAT_ELT_FWD, 0, bn_act_forward(B.z3, B.g, B.bn3.coef(P[P_PRELU3]), res, kNoDrop, nullptr, fmt, B.out,
+                                               next_stats ? net->partials : nullptr, s));
+        }
         carried_nblk = ew_num_blocks(B.g);
         if (B.rnn_index >= 0) {
             const float* const* PR = params + (size_t)c.num_blocks * P_PER_BLOCK + (size_t)B.rnn_index * R_PER_HEAD;
