@@ -508,3 +508,38 @@ def test_compact_backward_falls_back_on_ill_conditioned_channels(tmp_path):
     report_c.sort(reverse=True)
     print("FALLBACK compact vs oracle: %s" % ", ".join("%s %.2e" % (k, v) for v, k in report_c[:6]))
     assert ab_report[0][0] < 1e-2, ab_report[:3]
+
+
+@pytest.mark.parametrize("cls_name", ["TwoDimensionalCNNClassificationModel", "HierarchicalCNNClassificationModel"])
+def test_eval_folds_do_not_change_the_logits(cls_name, tmp_path):
+    """Eval forward: BatchNorm on running statistics is a fixed affine map, so BN2 + PReLU2 ride in the 3x3 conv's GEMM
+    epilogue, BN_a + PReLU_a in the pooling kernel and the next block's BN_in in the block-output kernel
+    (FSB200_FUSE_EVAL, csrc/net.cu).  Against the same forward with separate BN-apply passes (FSB200_FUSE_EVAL=0) and
+    with every fold incl. conv1 (15): same logits up to the rounding of one fused multiply-add per fold."""
+    cfg = dict(conv_base_depth=24, growth_rate=1.5)
+    if cls_name.startswith("Hier"):
+        cfg["features"] = "stft_256_128"
+    n, t = 5, 70000
+    signal = torch.from_numpy(restate.synth_waveforms(n, t, seed=8))[..., None]
+    outs = {}
+    for mask in ("0", "14", "15"):
+        os.environ["FSB200_FUSE_EVAL"] = mask
+        try:
+            model = _build(cls_name, cfg, "mixed", tmp=str(tmp_path))
+            # running statistics away from their initial (0, 1) so that the folded affine maps are not trivial
+            with torch.no_grad():
+                g = torch.Generator().manual_seed(3)
+                for name, buf in model.named_buffers():
+                    if name.endswith("running_mean"):
+                        buf.copy_((0.3 * torch.randn(buf.shape, generator=g)).to(buf.device))
+                    elif name.endswith("running_var"):
+                        buf.copy_((0.5 + torch.rand(buf.shape, generator=g)).to(buf.device))
+            model.eval()
+            with torch.no_grad():
+                outs[mask] = model(signal.cuda())["class_logits"].cpu()
+            del model
+        finally:
+            os.environ.pop("FSB200_FUSE_EVAL", None)
+    scale = float(outs["0"].abs().max())
+    for mask in ("14", "15"):
+        assert float((outs[mask] - outs["0"]).abs().max()) < 2e-5 * scale, mask
