@@ -2,6 +2,10 @@
 // + magnitude + banded mel projection + log.  One launch replaces the reference's torch.stft /
 // pow / sum / sqrt / conv1d / log chain (ops/utils.py:110-127, networks/classifiers.py:565-579).
 //
+// Two kernels: `feat2048_mel_kernel` (n_fft = 2048 + mel + log, the 2D model's features: register-resident radix-16
+// passes, four frames per group, see its own header further down) and the generic `feat_kernel<LOG2N>` described here
+// (every other n_fft / mode, e.g. the 1D model's `stft_256_128`).
+//
 // Work decomposition: one CTA of 256 threads owns FPB = 16 consecutive frames of one clip.  A real
 // n_fft-point transform is computed as an M = n_fft/2 point complex transform of the even/odd packed
 // samples followed by the split post-processing; 256 threads execute M/4 radix-4 butterflies per
