@@ -135,7 +135,10 @@ __device__ __forceinline__ int gs_exponent2(const unsigned* absmax_bits, const f
     if (mul) b = __float_as_uint(__uint_as_float(b) * (*mul));
     return gs_exponent(b);
 }
-__device__ __forceinline__ float gs_pow2(int k) { return __uint_as_float((unsigned)(127 + k) << 23); }
+__device__ __forceinline__ float gs_pow2(int k) {          // 2^k, k clamped to the normal float32 range
+    k = k < -126 ? -126 : (k > 127 ? 127 : k);
+    return __uint_as_float((unsigned)(127 + k) << 23);
+}
 
 // A gradient tensor as the element-wise backward kernels read it: a float32 plane, or (compact backward of the mixed
 // mode) ONE half plane holding 2^k * gradient with k = gs_exponent2(bits, mul).
