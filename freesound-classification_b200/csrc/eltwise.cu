@@ -418,7 +418,8 @@ __device__ __forceinline__ float4 fwd_compute(const FwdIn& in, const Coef4& cb, 
     return v;
 }
 
-template <bool STATS>
+// POST (eval only): a compile-time switch, so that the training instantiations keep their register allocation
+template <bool STATS, bool POST>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, Dropout dr_in, void* a_mma,
                   int fmt, float* a_f32, double* out_stats, BnCoef post) {
@@ -434,11 +435,10 @@ bn_act_fwd_kernel(const float* __restrict__ z, Geo g, BnCoef bn, Residual res, D
         if (has_res) cr = load_coef(res.scale, res.shift, res.slope, c0);
         const long long plane = g.rows * g.Cs;
         // post (eval): the operand planes receive post(v) = the NEXT BatchNorm (+ PReLU) applied to this output
-        const bool has_post = post.scale != nullptr;
         Coef4 cp = cb;
-        if (has_post) cp = load_coef(post.scale, post.shift, post.slope, c0);
+        if (POST) cp = load_coef(post.scale, post.shift, post.slope, c0);
         auto post_apply = [&](float4 v) {
-            if (!has_post) return v;
+            if (!POST) return v;
             float4 y = affine4(v, cp.sc, cp.sh);
             return cp.has_sl ? prelu4(y, cp.sl) : y;
         };
@@ -514,10 +514,14 @@ int bn_act_forward(const float* z, const Geo& g, BnCoef bn, Residual res, Dropou
         FSB_LAUNCHED();
         return 0;
     }
-    if (out_stats)
-        bn_act_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, out_stats, pc);
-    else
-        bn_act_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, nullptr, pc);
+    if (post) {
+        FSB_REQUIRE(!out_stats, "bn_act_forward: the post map is an eval option (no statistics)");
+        bn_act_fwd_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, nullptr, pc);
+    } else if (out_stats) {
+        bn_act_fwd_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, out_stats, pc);
+    } else {
+        bn_act_fwd_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(z, g, bn, res, dr, a_mma, fmt, a_f32, nullptr, pc);
+    }
     FSB_LAUNCHED();
     return 0;
 }
@@ -529,7 +533,7 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 
 // amax (optional, training): position 0..3 of the first maximum of every window in scan order, one byte per pooled
 // element -- the backward pass routes by it instead of re-reading the four full-resolution planes
-template <bool STATS>
+template <bool STATS, bool POST>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int pool_h, double* out_stats,
                    unsigned char* amax, BnCoef post, void* a_mma, int fmt) {
@@ -538,9 +542,8 @@ maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int p
     Acc4 acc[2];
     if (STATS) { acc[0].init(); acc[1].init(); }
     if (cok) {
-        const bool has_post = a_mma != nullptr;
         Coef4 cp;
-        if (has_post) cp = load_coef(post.scale, post.shift, post.slope, c0);
+        if (POST) cp = load_coef(post.scale, post.shift, post.slope, c0);
         const long long plane = g.rows * g.Cs;
         EW_PIXEL_LOOP {
             const unsigned img = (unsigned)(g.Hp * g.Wp);
@@ -558,7 +561,7 @@ maxpool_fwd_kernel(const float* __restrict__ zf, Geo gf, float* zp, Geo g, int p
                 m = max4(m, max4(v2, v3));
             }
             st4(zp + row * g.Cs + c0, m);
-            if (has_post) {              // eval: the BatchNorm + PReLU that follows, straight into the operand planes
+            if (POST) {                  // eval: the BatchNorm + PReLU that follows, straight into the operand planes
                 float4 y = affine4(m, cp.sc, cp.sh);
                 if (cp.has_sl) y = prelu4(y, cp.sl);
                 store_fmt(a_mma, fmt, plane, row * g.Cs + c0, y);
@@ -596,10 +599,14 @@ int maxpool_forward(const float* zf, const Geo& gf, float* zp, const Geo& gp, in
     EwShape sh = ew_shape(gp);
     const BnCoef no_post = {nullptr, nullptr, nullptr, nullptr, nullptr};
     const BnCoef pc = post ? *post : no_post;
-    if (out_stats)
-        maxpool_fwd_kernel<true><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, out_stats, amax, pc, a_mma, fmt);
-    else
-        maxpool_fwd_kernel<false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr, amax, pc, a_mma, fmt);
+    if (post) {
+        FSB_REQUIRE(!out_stats, "maxpool_forward: the fused BatchNorm output is an eval option (no statistics)");
+        maxpool_fwd_kernel<false, true><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr, amax, pc, a_mma, fmt);
+    } else if (out_stats) {
+        maxpool_fwd_kernel<true, false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, out_stats, amax, pc, a_mma, fmt);
+    } else {
+        maxpool_fwd_kernel<false, false><<<sh.grid, sh.block, 0, s>>>(zf, gf, zp, gp, pool_h, nullptr, amax, pc, a_mma, fmt);
+    }
     FSB_LAUNCHED();
     return 0;
 }
